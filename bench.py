@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- env steps/s (and legal-movegen positions/s) of the batched gym-chess v2 env on B200.
+
+    python bench.py [--gpus N --steps K --warmup W]                 our CUDA path (default N=1)
+    python bench.py --impl reference [--gpus N --steps K --warmup W]  the reference algorithm on the host cores
+    torchrun ... bench.py --gpus N ...                              one rank per GPU, weak scaling
+
+Workload (BASELINE.json configs[3] "4M envs sharded across 8xB200", per-GPU shard): 524,288 envs per GPU, random
+self-play (opponent "none"), uniformly random legal action per ply drawn on the device (Philox4x32-10), auto-reset.
+A "step" is one ChessEnvV2.step() of every env of the rank = one launch of the fused step kernel.  `value` = env
+steps of all ranks / max-over-ranks device time, state resident in HBM.  `e2e` = the same metric through the
+host-buffer C ABI call gcb_env_step_index_host (what a binding of the reference env would call): per step the
+caller's random words are copied H2D from pinned memory and reward/done/flags D2H, inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 524288
+METRIC = "env_steps_per_sec"
+UNIT = "env steps/s"
+WORKLOAD = ("random self-play, opponent=none, auto-reset, on-device Philox action draw; %d envs per GPU "
+            "(BASELINE.json configs[3]: 4M envs over 8xB200, per-GPU shard)")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(sample_envs, steps_per_env, threads):
+    """the oracle (C restatement of lib.rs + chess_v2.py) on the host cores; kind = "port" because the reference's own
+    Rust engine cannot be built here (no cargo/rustc)"""
+    from oracle import oracle as orc
+
+    t0 = time.time()
+    st = orc.selfplay_mt(0, 0, sample_envs, steps_per_env, threads)
+    dt = time.time() - t0
+    return st["steps"] / dt, dt, st
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # a step = one env step of a bounded sample of the workload's envs
+    sample = 2048
+    from oracle import oracle as orc
+
+    for _ in range(args.warmup):
+        orc.selfplay_mt(0, 0, sample, 1, threads)
+    t0 = time.time()
+    st = orc.selfplay_mt(0, 0, sample, args.steps, threads)
+    dt = time.time() - t0
+    v = st["steps"] / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": WORKLOAD % ENVS_PER_GPU, "sample": "%d envs x %d steps" % (sample, args.steps)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d envs x %d steps of the same self-play workload, C oracle (restates src/lib.rs + "
+                                   "chess_v2.py; the Rust engine is unbuildable here), %d pthreads" % (sample, args.steps, threads)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "published_reference": {"steps_per_sec": 3205, "source": "gym_chess/test/v2/test_benchmark.py:46-50 (1851 steps in 0.5776 s, 1 thread, unspecified CPU)"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--burn-in", type=int, default=600, help="untimed steps so that game phases are mixed")
+    ap.add_argument("--no-extras", action="store_true", help="skip the movegen / small-config / cpu_baseline legs")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert args.warmup >= 3, "W >= 3 warm-up steps"
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from gym_chess_b200 import BatchedChessEnv, _lib
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    N = args.envs_per_gpu
+    env = BatchedChessEnv(N, opponent="none", seed=2, device=local_rank, auto_reset=True, env_id_offset=rank * N)
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- burn-in (game phases mix: episodes are ~270 plies long) + warm-up
+    env.step_sampled(args.burn_in)
+    env.step_sampled(args.warmup)
+    env.reset_stats()
+    # ---- timed region 1: kernel-only, state resident in HBM.  Working set (48 B state + 288 B legal list + 4 KB
+    # history ring per env = 2.3 GB at 524,288 envs) is far larger than the 126 MB L2: no flush needed.
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = L.gcb_launch_count()
+    ev0.record()
+    env.step_sampled(args.steps)
+    ev1.record()
+    barrier()
+    launches = L.gcb_launch_count() - launches0
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clk = clocks.stop() if rank == 0 else None
+    st = env.stats()
+    value = world * N * args.steps / (ms * 1e-3)
+
+    # ---- final NCCL reduce of the episode statistics (the only collective of the job)
+    stats_t = env.stats_tensor().clone()
+    if world > 1:
+        dist.all_reduce(stats_t, op=dist.ReduceOp.SUM)
+    tot = stats_t.cpu().numpy()
+
+    # ---- timed region 2: end to end through the host-buffer C ABI call, pinned host memory
+    words = torch.empty((8, N), dtype=torch.int32).pin_memory()
+    words.random_(-2 ** 31, 2 ** 31 - 1)
+    h_r = torch.empty(N, dtype=torch.int32).pin_memory()
+    h_d = torch.empty(N, dtype=torch.uint8).pin_memory()
+    h_f = torch.empty(N, dtype=torch.uint8).pin_memory()
+    wn, rn, dn, fn = words.numpy().view(np.uint32), h_r.numpy(), h_d.numpy(), h_f.numpy()
+    e2e_steps = max(10, min(args.steps, 100))
+    for i in range(3):
+        env.step_index_host(wn[i % 8], rn, dn, fn)
+    barrier()
+    ev0.record()
+    for i in range(e2e_steps):
+        env.step_index_host(wn[i % 8], rn, dn, fn)
+    ev1.record()
+    barrier()
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    e2e_value = world * N * e2e_steps / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_env_step<sampled>): algorithmic bytes per env step, SURVEY.md 8(d):
+    # 40 B state read + 40 B state write + 4 B action + 4 B reward + 1 B done + 8 B history append + 8 B x W scanned
+    W = st["hist_scanned"] / max(1, st["plies"])
+    bytes_per_step = 97.0 + 8.0 * W
+    kernel_ms = ms / args.steps  # one launch per step, nothing else in the timed region
+    achieved = bytes_per_step * N / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD % N, "envs_per_gpu": N, "total_envs": world * N, "burn_in_steps": args.burn_in,
+                   "l2": "inputs larger than L2 (2.3 GB resident state per GPU vs 126 MB L2), no flush"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 6 * N,
+                "steps": e2e_steps, "api": "gcb_env_step_index_host (BatchedChessEnv.step_index_host), pinned host buffers"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_env_step<MODE_SAMPLED>", "bytes_per_unit": bytes_per_step,
+                     "mean_hist_window": W, "peak_source": peak_src,
+                     "note": "integer-pipe / divergence bound, not HBM bound: see DESIGN.md and profiles/"},
+        "episode_stats_all_ranks": {k: int(tot[i]) for i, k in enumerate(
+            ("steps", "plies", "episodes", "mates", "repetitions", "caps", "wedged", "invalid", "reward_sum", "legal_sum",
+             "in_check", "hist_overflow", "list_overflow", "hist_scanned"))},
+    }
+    if clk is not None:
+        line["clocks"] = clk
+
+    if rank == 0 and not args.no_extras:
+        import ctypes as C
+        from gym_chess_b200._lib import Positions, check
+
+        # ---- legal-movegen positions/s on 1,048,576 positions (BASELINE.json configs[1]); positions = the first 1M
+        # resident env states of this rank (mid-game mix after burn-in), packed form, kernel-only
+        M = min(N, 1 << 20)
+        info = env.info_tensor()
+        pl = (info[:M, 0] < 0).to(torch.uint8).contiguous()
+        rt = (info[:M, 1] + 2 * info[:M, 2] + 4 * info[:M, 3] + 8 * info[:M, 4]).to(torch.uint8).contiguous()
+        p = env.positions()
+        pos = Positions(p.bb01, p.bb23, pl.data_ptr(), rt.data_ptr())
+        out = torch.empty((M, 144), dtype=torch.int16, device=dev)
+        cnt = torch.empty(M, dtype=torch.int32, device=dev)
+        for _ in range(3):
+            check(L.gcb_get_possible_moves(M, pos, 0, 0, out.data_ptr(), 144, cnt.data_ptr(), None, None))
+        reps = 20
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            check(L.gcb_get_possible_moves(M, pos, 0, 0, out.data_ptr(), 144, cnt.data_ptr(), None, None))
+        ev1.record()
+        torch.cuda.synchronize()
+        mg_ms = ev0.elapsed_time(ev1) / reps
+        nl = float(cnt.float().mean().item())
+        mg_bytes = 40 + 2 + 2 * nl
+        line["movegen"] = {"metric": "legal_movegen_positions_per_sec", "value": M / (mg_ms * 1e-3), "positions": M,
+                           "ms_per_launch": mg_ms, "mean_legal": nl, "bytes_per_position": mg_bytes,
+                           "hbm_frac": mg_bytes * M / (mg_ms * 1e-3) / 1e9 / peak, "kernel": "k_movegen<false>"}
+        # ---- BASELINE.json configs[2]: 65,536 envs on one GPU
+        small = BatchedChessEnv(65536, opponent="none", seed=2, device=local_rank)
+        small.step_sampled(args.burn_in)
+        torch.cuda.synchronize()
+        ev0.record()
+        small.step_sampled(args.steps)
+        ev1.record()
+        torch.cuda.synchronize()
+        line["config_65536_envs"] = {"value": 65536 * args.steps / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT}
+        small.close()
+        # ---- CPU baseline on this box's host cores (bounded sample)
+        threads = os.cpu_count() or 1
+        v, dt, _ = cpu_baseline(128 * threads, 5000, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d envs x 5000 steps of the same self-play workload (%.1f s), C oracle on %d "
+                                          "pthreads; reference's published single-thread figure: 3.2e3 steps/s" % (128 * threads, dt, threads)}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,215 @@
+"""BatchedChessEnv -- N gym-chess v2 envs resident in B200 HBM, advanced by the fused step kernel.
+
+Host-side mirror of the reference's env interface (`ChessEnvV2`, gym_chess/envs/chess_v2.py:132-294) with a
+leading batch dimension: same constructor vocabulary (`player_color`, `opponent`, `initial_board`), same
+`reset` / `step` / `possible_actions` / `state` / `info` notions, same action encoding, rewards and done rules
+(including the reference's quirks).  All compute happens in libgymchess_b200.so
+(hand-written sm_100a kernels behind the C ABI of include/gymchess_b200.h); torch is only used for device
+buffers and streams.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EnvConfig, Positions, check
+
+WHITE, BLACK = "WHITE", "BLACK"
+
+F_INVALID, F_MATE, F_REPETITION, F_CAP, F_WEDGED, F_RESET = 1, 2, 4, 8, 16, 32
+STAT_NAMES = ("steps", "plies", "episodes", "mates", "repetitions", "caps", "wedged", "invalid", "reward_sum",
+              "legal_sum", "in_check", "hist_overflow", "list_overflow", "hist_scanned")
+INFO_NAMES = ("current_player", "white_king_castle_is_possible", "white_queen_castle_is_possible",
+              "black_king_castle_is_possible", "black_queen_castle_is_possible", "white_king_is_checked",
+              "black_king_is_checked", "done", "move_count", "n_legal", "episode", "step_in_episode", "hist_len")
+
+
+class _DevArray:
+    """zero-copy view of library-owned device memory through __cuda_array_interface__"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class BatchedChessEnv:
+    def __init__(self, num_envs, opponent="random", player_color=WHITE, seed=0, device=0, auto_reset=True,
+                 initial_boards=None, env_id_offset=0, legal_stride=144, history_cap=512, moves_max=149):
+        """
+        opponent      "random" (the bot replies inside step, chess_v2.py:277-288) or "none" (self-play)
+        player_color  "WHITE" | "BLACK" (BLACK needs opponent="random", like the reference: Q23)
+        initial_boards  None (DEFAULT_BOARD) or int8 [T,8,8] / [8,8]; env with global id g starts from board g % T
+        env_id_offset   global id of local env 0 -- shards of one job use disjoint id ranges so that the
+                        Philox draws (counter = global env id, episode, step) do not depend on the sharding
+        """
+        _lib.require_gpu()
+        if opponent not in ("random", "none"):
+            raise ValueError("opponent must be 'random' or 'none' (callables: see gym_chess_b200.ChessEnvV2)")
+        self.num_envs, self.opponent, self.player_color = int(num_envs), opponent, player_color
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        self.auto_reset, self.seed, self.env_id_offset = bool(auto_reset), int(seed), int(env_id_offset)
+        self.legal_stride = int(legal_stride)
+        cfg = EnvConfig()
+        cfg.num_envs, cfg.env_id_offset, cfg.seed = self.num_envs, self.env_id_offset, self.seed
+        cfg.opponent, cfg.agent_black, cfg.auto_reset = int(opponent == "random"), int(player_color == BLACK), int(auto_reset)
+        cfg.legal_stride, cfg.history_cap, cfg.moves_max = legal_stride, history_cap, moves_max
+        self._templates = None
+        if initial_boards is not None:
+            tb = np.ascontiguousarray(np.asarray(initial_boards, dtype=np.int8).reshape(-1, 64))
+            self._templates = tb
+            cfg.n_templates, cfg.template_boards = len(tb), tb.ctypes.data
+        cfg.device = self.device.index or 0
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gcb_env_create(C.byref(cfg), C.byref(self._h)))
+            N = self.num_envs
+            self.reward = torch.zeros(N, dtype=torch.int32, device=self.device)
+            self.done = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self.flags = torch.zeros(N, dtype=torch.uint8, device=self.device)
+        self.observation_shape, self.num_actions = (8, 8), 64 * 64 + 4 + 1  # Box(-6,6,(8,8)), Discrete(4101)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().gcb_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # ------------------------------------------------------------------ stepping (device tensors)
+    def reset(self, mask=None):
+        """ChessEnvV2.reset for all envs (or those with mask != 0); returns the board observation."""
+        with torch.cuda.device(self.device):
+            m = None
+            if mask is not None:
+                m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            check(_lib.lib().gcb_env_reset(self._h, C.c_void_p(m.data_ptr()) if m is not None else None, _stream_ptr()))
+        return self.observe()
+
+    def _outs(self):
+        return C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()), C.c_void_p(self.flags.data_ptr())
+
+    def step(self, actions):
+        """actions: int32 [N] cuda tensor.  -> (reward int32[N], done uint8[N], flags uint8[N]) (reused buffers)."""
+        a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gcb_env_step(self._h, C.c_void_p(a.data_ptr()), *self._outs(), _stream_ptr()))
+        return self.reward, self.done, self.flags
+
+    def step_index(self, u32):
+        """env i plays legal[i][(u32[i] * n_legal[i]) >> 32]: make_random_policy's uniform draw with caller words."""
+        u = torch.as_tensor(u32, device=self.device)
+        if u.dtype not in (torch.int32, torch.uint32):
+            u = u.to(torch.int64).to(torch.int32)
+        u = u.contiguous()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gcb_env_step_index(self._h, C.c_void_p(u.data_ptr()), *self._outs(), _stream_ptr()))
+        return self.reward, self.done, self.flags
+
+    def step_sampled(self, nsteps=1, record=False):
+        """`nsteps` self-play / vs-bot steps with on-device Philox draws.  record=True also returns the actions
+        taken, int32 [nsteps, N] (agent) and [nsteps, N] (bot, -1 = none)."""
+        acts = bots = None
+        with torch.cuda.device(self.device):
+            if record:
+                acts = torch.empty((nsteps, self.num_envs), dtype=torch.int32, device=self.device)
+                bots = torch.empty((nsteps, self.num_envs), dtype=torch.int32, device=self.device)
+            check(_lib.lib().gcb_env_step_sampled(
+                self._h, int(nsteps), *self._outs(), C.c_void_p(acts.data_ptr()) if record else None,
+                C.c_void_p(bots.data_ptr()) if record else None, _stream_ptr()))
+        if record:
+            return self.reward, self.done, self.flags, acts, bots
+        return self.reward, self.done, self.flags
+
+    # ------------------------------------------------------------------ stepping (host buffers, copies inside)
+    def step_host(self, actions, reward=None, done=None, flags=None):
+        """numpy in / numpy out through gcb_env_step_host (H2D + kernel + D2H inside the call)."""
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        return self._host_call(_lib.lib().gcb_env_step_host, a, reward, done, flags)
+
+    def step_index_host(self, u32, reward=None, done=None, flags=None):
+        u = np.ascontiguousarray(u32, dtype=np.uint32)
+        return self._host_call(_lib.lib().gcb_env_step_index_host, u, reward, done, flags)
+
+    def _host_call(self, fn, inp, reward, done, flags):
+        N = self.num_envs
+        assert inp.shape == (N,)
+        reward = np.empty(N, np.int32) if reward is None else reward
+        done = np.empty(N, np.uint8) if done is None else done
+        flags = np.empty(N, np.uint8) if flags is None else flags
+        check(fn(self._h, inp.ctypes.data, reward.ctypes.data, done.ctypes.data, flags.ctypes.data))
+        return reward, done, flags
+
+    # ------------------------------------------------------------------ observation / state
+    def observe(self):
+        """`state["board"]` for every env: int8 [N,8,8] (the Box(-6,6,(8,8)) observation, chess_v2.py:156)."""
+        with torch.cuda.device(self.device):
+            b = torch.empty((self.num_envs, 8, 8), dtype=torch.int8, device=self.device)
+            check(_lib.lib().gcb_env_export(self._h, C.c_void_p(b.data_ptr()), None, _stream_ptr()))
+        return b
+
+    def info_tensor(self):
+        """int32 [N,16]: columns INFO_NAMES (current_player is +1 WHITE / -1 BLACK)."""
+        with torch.cuda.device(self.device):
+            t = torch.empty((self.num_envs, 16), dtype=torch.int32, device=self.device)
+            check(_lib.lib().gcb_env_export(self._h, None, C.c_void_p(t.data_ptr()), _stream_ptr()))
+        return t
+
+    def legal_actions(self):
+        """(legal uint16-as-int16 [N, stride] zero-copy view, n_legal int32 [N]) = possible_actions, reference order."""
+        ptr, stride = C.c_void_p(), C.c_int32()
+        check(_lib.lib().gcb_env_legal_ptr(self._h, C.byref(ptr), C.byref(stride)))
+        with torch.cuda.device(self.device):
+            view = torch.as_tensor(_DevArray(ptr.value, (self.num_envs, stride.value), "<i2"), device=self.device)
+        return view, self.info_tensor()[:, 9].contiguous()
+
+    def legal_mask(self):
+        """uint8 [N, 4101] mask of possible_actions."""
+        with torch.cuda.device(self.device):
+            m = torch.empty((self.num_envs, 4101), dtype=torch.uint8, device=self.device)
+            check(_lib.lib().gcb_env_legal_mask(self._h, C.c_void_p(m.data_ptr()), _stream_ptr()))
+        return m
+
+    def export_numpy(self):
+        """(boards int8[N,64], info int32[N,16], legal uint16[N,stride]) on the host -- test / debug helper."""
+        boards = self.observe().reshape(self.num_envs, 64).cpu().numpy()
+        info = self.info_tensor().cpu().numpy()
+        legal = self.legal_actions()[0].cpu().numpy().view(np.uint16)
+        return boards, info, legal
+
+    def state(self, i):
+        """The reference's state dict (chess_v2.py:301-313) of env i."""
+        boards, info, _ = self.export_numpy()
+        r = info[i]
+        return dict(board=boards[i].reshape(8, 8).tolist(), current_player=WHITE if r[0] > 0 else BLACK,
+                    white_king_castle_is_possible=bool(r[1]), white_queen_castle_is_possible=bool(r[2]),
+                    black_king_castle_is_possible=bool(r[3]), black_queen_castle_is_possible=bool(r[4]),
+                    white_king_is_checked=bool(r[5]), black_king_is_checked=bool(r[6]))
+
+    # ------------------------------------------------------------------ statistics
+    def stats(self):
+        out = np.zeros(16, np.uint64)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gcb_env_stats(self._h, out.ctypes.data, _stream_ptr()))
+        d = {k: int(out[i]) for i, k in enumerate(STAT_NAMES)}
+        d["reward_sum"] = int(out[8:9].view(np.int64)[0])
+        return d
+
+    def stats_tensor(self):
+        """zero-copy int64 [16] view of the device counters (for an NCCL reduce)."""
+        ptr = C.c_void_p()
+        check(_lib.lib().gcb_env_stats_ptr(self._h, C.byref(ptr)))
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_DevArray(ptr.value, (16,), "<i8"), device=self.device)
+
+    def reset_stats(self):
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gcb_env_stats_reset(self._h, _stream_ptr()))
+
+    def positions(self):
+        p = Positions()
+        check(_lib.lib().gcb_env_positions(self._h, C.byref(p)))
+        return p

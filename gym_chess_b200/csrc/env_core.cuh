@@ -1,0 +1,401 @@
+// env_core.cuh -- per-env step / reset logic of the batched env (ChessEnvV2, chess_v2.py:183-294,
+// 393-412) over the resident structure-of-arrays state.  One call of env_step_one() advances ONE
+// env by one `step()`; the kernels in gcb_kernels.cu run it with one thread per env.
+//
+// Layout in HBM (structure of arrays):
+//   bb01[N]  ulonglong2 {t0,t1}       16 B   piece-code bit-planes
+//   bb23[N]  ulonglong2 {t2,white}    16 B
+//   meta[N]  u64                       8 B   stm | rights | check flags | done | n_legal | move_count |
+//                                            step_in_episode | hist_len
+//   zkey[N]  u64                       8 B   Zobrist key of the current board (board only)
+//   episode[N] u32                     4 B
+//   legal[N][stride] u16                     cached ordered legal list = ChessEnvV2.possible_moves
+//   hist[H][N] u64                           Zobrist ring; slot = global tick * plies-per-step + k, so that
+//                                            appends and window scans are coalesced across envs
+#pragma once
+#include "chess_core.cuh"
+
+#if !defined(__CUDACC__)
+struct ulonglong2 {
+    u64 x, y;
+};
+static inline ulonglong2 make_ulonglong2(u64 x, u64 y) {
+    ulonglong2 r = {x, y};
+    return r;
+}
+#endif
+
+// per-env flags (mirrors include/gymchess_b200.h GCB_F_*)
+#define EF_INVALID 1u
+#define EF_MATE 2u
+#define EF_REPETITION 4u
+#define EF_CAP 8u
+#define EF_WEDGED 16u
+#define EF_RESET 32u
+
+// ordered move list -> global memory, two 16-bit entries per 32-bit store
+struct ListWriter {
+    uint16_t* out;
+    int n, cap;
+    u32 pend;
+    GCB_HD ListWriter(uint16_t* o, int c) : out(o), n(0), cap(c), pend(0) {}
+    GCB_HD void push(int action) {
+        if (n & 1) {
+            if (n < cap) *reinterpret_cast<u32*>(out + n - 1) = pend | ((u32)action << 16);
+        } else {
+            pend = (u32)action;
+        }
+        n++;
+    }
+    GCB_HD void flush() {
+        if ((n & 1) && n <= cap) out[n - 1] = (uint16_t)pend;
+    }
+};
+
+// meta word
+#define M_RIGHTS_SHIFT 1
+#define M_NLEGAL_SHIFT 8
+#define M_MOVECOUNT_SHIFT 20
+#define M_STEP_SHIFT 36
+#define M_HIST_SHIFT 52
+
+enum { ST_STEPS = 0, ST_PLIES, ST_EPISODES, ST_MATES, ST_REPS, ST_CAPS, ST_WEDGED, ST_INVALID, ST_REWARD, ST_LEGAL,
+       ST_INCHECK, ST_HISTOVF, ST_LISTOVF, ST_HISTSCAN, ST_USED, ST_COUNT = 16 };
+
+struct EnvView {
+    ulonglong2* bb01;
+    ulonglong2* bb23;
+    u64* meta;
+    u64* zkey;
+    u32* episode;
+    uint16_t* legal;
+    u64* hist;
+    const ulonglong2* t_bb01;
+    const ulonglong2* t_bb23;
+    const u64* t_meta;
+    const u64* t_zkey;
+    const uint16_t* t_legal;
+    u64* stats;
+    u64 seed;
+    int N, stride, hist_mask, n_templates;
+    u32 env_offset;
+    int moves_max, opponent, agent_black, auto_reset, pps;
+};
+
+struct EnvRegs {
+    Board b;
+    u64 zk;
+    u32 rights, chk;  // chk bit0 white checked, bit1 black checked
+    int stm_black, done, n_legal, move_count, step, hist_len;
+};
+
+GCB_HD void unpack_meta(u64 m, EnvRegs& s) {
+    s.stm_black = (int)(m & 1);
+    s.rights = (u32)(m >> M_RIGHTS_SHIFT) & 15u;
+    s.chk = (u32)(m >> 5) & 3u;
+    s.done = (int)(m >> 7) & 1;
+    s.n_legal = (int)(m >> M_NLEGAL_SHIFT) & 0xFFF;
+    s.move_count = (int)(m >> M_MOVECOUNT_SHIFT) & 0xFFFF;
+    s.step = (int)(m >> M_STEP_SHIFT) & 0xFFFF;
+    s.hist_len = (int)(m >> M_HIST_SHIFT) & 0x3FF;
+}
+GCB_HD u64 pack_meta(const EnvRegs& s) {
+    return (u64)(s.stm_black & 1) | ((u64)(s.rights & 15u) << M_RIGHTS_SHIFT) | ((u64)(s.chk & 3u) << 5) |
+           ((u64)(s.done & 1) << 7) | ((u64)(s.n_legal & 0xFFF) << M_NLEGAL_SHIFT) |
+           ((u64)(s.move_count & 0xFFFF) << M_MOVECOUNT_SHIFT) | ((u64)(s.step & 0xFFFF) << M_STEP_SHIFT) |
+           ((u64)(s.hist_len & 0x3FF) << M_HIST_SHIFT);
+}
+
+GCB_HD bool stm_checked(const EnvRegs& s) { return (s.chk >> s.stm_black) & 1u; }
+
+// history ring bookkeeping: `cursor` = next slot of this tick; hist_len = length of the contiguous
+// window of slots behind the cursor that may hold an equal board (reset by irreversible plies)
+struct HistCursor {
+    u64 base;    // tick * pps
+    int cursor;  // 0..pps
+};
+
+GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int k, int* ovf) {
+    while (hc.cursor < k) {
+        if (s.hist_len > 0) {
+            v.hist[((hc.base + hc.cursor) & (u64)v.hist_mask) * (u64)v.N + e] = 0;  // "no ply in this slot"
+            if (s.hist_len < v.hist_mask) s.hist_len++;
+            else (*ovf)++;
+        }
+        hc.cursor++;
+    }
+}
+
+// One ply = player_move (chess_v2.py:393-412: engine.next_state + repetition count on the PRE-move
+// board) + the state setter (315-323) + switch_player (296-299) + get_possible_moves for the new
+// side to move (573-582).  apply=false only switches the side and regenerates (BLACK-agent reset
+// when White has no move).  Returns the ply reward.
+GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int slot, int action, bool apply, bool* rep,
+                           int* hist_ovf, int* hist_scanned) {
+    int r = 0;
+    *rep = false;
+    if (apply) {
+        hist_skip_to(v, e, s, hc, slot, hist_ovf);
+        const u64 key = hist_key(s.zk);
+        const u64 cur = hc.base + slot;
+        int cnt = 0;
+        for (int j = 1; j <= s.hist_len; j++) cnt += (v.hist[((cur - j) & (u64)v.hist_mask) * (u64)v.N + e] == key);
+        *rep = cnt >= 2;  // saved_boards[key] reaches 3 with this ply
+        *hist_scanned += s.hist_len;
+        v.hist[(cur & (u64)v.hist_mask) * (u64)v.N + e] = key;
+        hc.cursor = slot + 1;
+
+        const Board old = s.b;
+        u32 rights = mask_rights(s.b, s.rights);  // engine entry masks by the INPUT board (Q21)
+        int st;
+        bool irr;
+        r = apply_action(s.b, rights, !s.stm_black, action, &st, &irr);
+        s.rights = rights;
+        // incremental Zobrist over the squares that changed
+        u64 diff = (old.t0 ^ s.b.t0) | (old.t1 ^ s.b.t1) | (old.t2 ^ s.b.t2) | (old.w ^ s.b.w);
+        while (diff) {
+            int sq = gcb_lsb(diff);
+            diff &= diff - 1;
+            int po = piece_id(old, sq), pn = piece_id(s.b, sq);
+            if (po) s.zk ^= zobrist_piece(po, sq);
+            if (pn) s.zk ^= zobrist_piece(pn, sq);
+        }
+        if (irr) s.hist_len = 0;
+        else if (s.hist_len < v.hist_mask) s.hist_len++;
+        else (*hist_ovf)++;
+    }
+    s.stm_black ^= 1;
+    ListWriter lw(v.legal + (size_t)e * v.stride, v.stride);
+    bool inchk = false;
+    u64 eatt;
+    gen_moves<false>(s.b, !s.stm_black, mask_rights(s.b, s.rights), lw, &eatt, &inchk);
+    lw.flush();
+    s.n_legal = lw.n;
+    // both check flags (update_state, lib.rs:1386-1393): the side to move from its movegen attack map,
+    // the side that just moved by the symmetric single-square test
+    u32 chk = inchk ? (1u << s.stm_black) : 0u;
+    {
+        const u64 occ = bb_occ(s.b);
+        const u64 stm_side = s.stm_black ? (occ & ~s.b.w) : s.b.w;
+        const u64 mk = bb_kings(s.b) & occ & ~stm_side;
+        if (mk && square_attacked_by(s.b, ref_king_square(mk), stm_side, !s.stm_black)) chk |= 1u << (s.stm_black ^ 1);
+    }
+    s.chk = chk;
+    return r;
+}
+
+enum { MODE_ACTION = 0, MODE_INDEX = 1, MODE_SAMPLED = 2, MODE_RESET = 3 };
+enum { PH_AGENT = 0, PH_BOT = 1, PH_FINAL = 2, PH_RESETBOT = 3, PH_END = 4 };
+
+struct StepIO {
+    const void* in;      // MODE_ACTION: int32 actions; MODE_INDEX: u32 words; MODE_RESET: uint8 mask or NULL
+    int32_t* reward;     // any output may be NULL
+    uint8_t* done;
+    uint8_t* flags;
+    int32_t* act_out;
+    int32_t* bot_out;
+    u64 tick;
+    int ep_inc;
+};
+
+struct StepStats {
+    int v[ST_USED];
+};
+
+// chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step)
+template <int MODE>
+GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& st) {
+    EnvRegs s;
+    {
+        ulonglong2 a = v.bb01[e], c = v.bb23[e];
+        s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
+    }
+    unpack_meta(v.meta[e], s);
+    s.zk = v.zkey[e];
+    u32 ep = v.episode[e];
+    const u32 genv = v.env_offset + (u32)e;
+    uint16_t* mylist = v.legal + (size_t)e * v.stride;
+    HistCursor hc;
+    hc.base = io.tick * (u64)v.pps, hc.cursor = 0;
+
+    int action = ACT_RESIGN, bot_action = -1, R = 0, phase;
+    u32 fl = 0;
+    bool d_out = false, agent_ply = false;
+    const int n0 = s.n_legal;
+    const bool was_done = s.done, capped = s.move_count > v.moves_max;
+    const u32 step_idx = (u32)s.step;
+
+    if (MODE == MODE_RESET) {
+        phase = PH_FINAL;
+    } else {
+        bool valid = false;
+        const int nread = n0 < v.stride ? n0 : v.stride;  // entries beyond the stride were dropped (list_overflow)
+        if (MODE == MODE_ACTION) {
+            action = reinterpret_cast<const int32_t*>(io.in)[e];
+            for (int k = 0; k < nread; k++) valid |= (mylist[k] == action);  // action in possible_actions
+        } else {
+            u32 u = (MODE == MODE_INDEX) ? reinterpret_cast<const u32*>(io.in)[e] : philox_draw(v.seed, genv, ep, step_idx, 0u);
+            if (n0 > 0) {
+                int idx = (int)gcb_umulhi(u, (u32)n0);
+                action = mylist[idx < nread ? idx : nread - 1];
+                valid = true;
+            }
+        }
+        st.v[ST_STEPS] += 1, st.v[ST_LEGAL] += n0, st.v[ST_INCHECK] += stm_checked(s) ? 1 : 0;
+        s.step++;
+        if (!valid) {  // chess_v2.py:240-242, before the done test (Q16)
+            R = -10, d_out = s.done, fl |= EF_INVALID, st.v[ST_INVALID] += 1;
+            phase = PH_FINAL;
+        } else if (s.done) {  // chess_v2.py:245-251
+            R = 0, d_out = true;
+            phase = PH_FINAL;
+        } else if (capped) {  // chess_v2.py:252-258: done is NOT latched (Q12)
+            R = 0, d_out = true, fl |= EF_CAP;
+            phase = PH_FINAL;
+        } else {
+            R = -10;  // chess_v2.py:261 (sic)
+            phase = PH_AGENT;
+        }
+    }
+
+    bool do_apply = true;
+    int slot = 0, cur = action;  // cur = the action of the ply being executed
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    while (phase != PH_END) {
+        if (phase == PH_FINAL) {
+            bool terminal;
+            if (MODE == MODE_RESET) {
+                terminal = true;
+            } else {
+                if (agent_ply) d_out = s.done;
+                terminal = d_out || s.n_legal == 0;
+                if (!d_out && s.n_legal == 0) fl |= EF_WEDGED;
+                if (n0 == 0 || was_done || (fl & EF_INVALID)) {
+                } else if (capped) st.v[ST_CAPS] += 1;
+                else if (d_out) {
+                    if (fl & EF_MATE) st.v[ST_MATES] += 1;
+                    else st.v[ST_REPS] += 1;
+                } else if (s.n_legal == 0) st.v[ST_WEDGED] += 1;
+                if (terminal) st.v[ST_EPISODES] += 1;
+                st.v[ST_REWARD] += R;
+                if (v.auto_reset && terminal) fl |= EF_RESET;
+                if (io.reward) io.reward[e] = R;
+                if (io.done) io.done[e] = d_out ? 1 : 0;
+                if (io.flags) io.flags[e] = (uint8_t)fl;
+                if (io.act_out) io.act_out[e] = action;
+            }
+            if ((MODE == MODE_RESET) || (v.auto_reset && terminal)) {
+                // ChessEnvV2.reset, chess_v2.py:183-217: copy the prepared initial state
+                const int t = (int)(genv % (u32)v.n_templates);
+                ulonglong2 a = v.t_bb01[t], c = v.t_bb23[t];
+                s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
+                unpack_meta(v.t_meta[t], s);
+                s.zk = v.t_zkey[t];
+                const uint16_t* tl = v.t_legal + (size_t)t * v.stride;
+                const int lim = s.n_legal < v.stride ? s.n_legal : v.stride;
+                for (int k = 0; k < lim; k += 2) *reinterpret_cast<u32*>(mylist + k) = *reinterpret_cast<const u32*>(tl + k);
+                ep += (u32)io.ep_inc;
+                if (v.agent_black) {
+                    // the bot opens for White (chess_v2.py:208-216)
+                    if (s.n_legal > 0) {
+                        u32 u = philox_draw(v.seed, genv, ep, 0u, 2u);
+                        int idx = (int)gcb_umulhi(u, (u32)s.n_legal);
+                        cur = mylist[idx < v.stride ? idx : v.stride - 1];
+                        do_apply = true;
+                    } else {
+                        do_apply = false;
+                    }
+                    slot = v.pps - 1;
+                    phase = PH_RESETBOT;
+                    continue;
+                }
+            }
+            phase = PH_END;
+            continue;
+        }
+        bool rep;
+        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, &st.v[ST_HISTOVF], &st.v[ST_HISTSCAN]);
+        if (do_apply) st.v[ST_PLIES] += 1;
+        if (s.n_legal > v.stride) st.v[ST_LISTOVF] += 1;
+        const bool mate = s.n_legal == 0 && stm_checked(s);
+        if (phase == PH_AGENT) {
+            agent_ply = true;
+            R += r;
+            s.done = rep;
+            if (rep) fl |= EF_REPETITION;
+            if (mate) s.done = 1, R += 100, fl |= EF_MATE;  // chess_v2.py:270-272
+            if (!s.done && v.opponent == 1) {
+                if (s.n_legal > 0) {  // chess_v2.py:277-288
+                    u32 u = philox_draw(v.seed, genv, ep, step_idx, 1u);
+                    int idx = (int)gcb_umulhi(u, (u32)s.n_legal);
+                    bot_action = mylist[idx < v.stride ? idx : v.stride - 1];
+                    cur = bot_action, slot = 1, phase = PH_BOT;
+                    continue;
+                }
+                // bot without moves and not in check: the reference raises TypeError (Q9); stop here
+            } else if (!s.done) {
+                if (!s.stm_black) s.move_count++;  // chess_v2.py:291-292
+            }
+            phase = PH_FINAL;
+        } else if (phase == PH_BOT) {
+            R -= r;
+            s.done = rep;
+            if (rep) fl |= EF_REPETITION;
+            if (mate) s.done = 1, R -= 100, fl |= EF_MATE;  // chess_v2.py:286-288
+            if (!s.stm_black) s.move_count++;
+            phase = PH_FINAL;
+        } else {                // PH_RESETBOT
+            s.move_count += 1;  // chess_v2.py:214
+            s.done = 0;
+            phase = PH_END;
+        }
+    }
+    hist_skip_to(v, e, s, hc, v.pps, &st.v[ST_HISTOVF]);
+    if (MODE != MODE_RESET && io.bot_out) io.bot_out[e] = bot_action;
+
+    v.bb01[e] = make_ulonglong2(s.b.t0, s.b.t1);
+    v.bb23[e] = make_ulonglong2(s.b.t2, s.b.w);
+    v.meta[e] = pack_meta(s);
+    v.zkey[e] = s.zk;
+    v.episode[e] = ep;
+}
+
+// initial state of one template board (ChessEnvV2.reset up to the first movegen, chess_v2.py:188-206)
+GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulonglong2* bb23, u64* meta, u64* zkey,
+                              uint16_t* legal, int stride) {
+    Board b = board_from_mailbox(boards + (size_t)i * 64);
+    EnvRegs s;
+    s.b = b;
+    s.zk = zobrist_full(b);
+    s.rights = mask_rights(b, 15u);  // all four True, then engine.update_state masks them (chess_v2.py:195-204)
+    s.chk = check_flags(b);
+    s.stm_black = 0, s.done = 0, s.move_count = 0, s.step = 0, s.hist_len = 0;
+    ListWriter lw(legal + (size_t)i * stride, stride);
+    u64 eatt;
+    bool chk;
+    gen_moves<false>(b, 1, s.rights, lw, &eatt, &chk);
+    lw.flush();
+    s.n_legal = lw.n;
+    bb01[i] = make_ulonglong2(b.t0, b.t1);
+    bb23[i] = make_ulonglong2(b.t2, b.w);
+    meta[i] = pack_meta(s);
+    zkey[i] = s.zk;
+}
+
+// unpacked view of one env for export: board int8[64] (may be NULL) and info int32[16]
+GCB_HD void env_export_one(const EnvView& v, int e, int8_t* board, int32_t* info) {
+    EnvRegs s;
+    ulonglong2 a = v.bb01[e], c = v.bb23[e];
+    s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
+    unpack_meta(v.meta[e], s);
+    if (board)
+        for (int sq = 0; sq < 64; sq++) board[sq] = (int8_t)piece_id(s.b, sq);
+    if (info) {
+        info[0] = s.stm_black ? -1 : 1, info[1] = s.rights & RT_WK ? 1 : 0, info[2] = s.rights & RT_WQ ? 1 : 0;
+        info[3] = s.rights & RT_BK ? 1 : 0, info[4] = s.rights & RT_BQ ? 1 : 0, info[5] = s.chk & 1, info[6] = (s.chk >> 1) & 1;
+        info[7] = s.done, info[8] = s.move_count, info[9] = s.n_legal, info[10] = (int)v.episode[e], info[11] = s.step;
+        info[12] = s.hist_len, info[13] = 0, info[14] = 0, info[15] = 0;
+    }
+}

@@ -1,0 +1,653 @@
+// gcb_kernels.cu -- kernels + C ABI of libgymchess_b200.so (sm_100a).  See include/gymchess_b200.h.
+//
+// The per-env logic lives in env_core.cuh / chess_core.cuh; this file holds the kernels (one thread per env or
+// position), the block-level statistics reduction and the host-side C ABI.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "../../include/gymchess_b200.h"
+#include "env_core.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* what, const char* detail) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, detail ? detail : "");
+    return code;
+}
+#define CU(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return fail(GCB_E_CUDA, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define LAUNCHED()                                                                \
+    do {                                                                          \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                       \
+        cudaError_t e_ = cudaGetLastError();                                      \
+        if (e_ != cudaSuccess) return fail(GCB_E_CUDA, "kernel launch", cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* gcb_last_error(void) { return g_err; }
+extern "C" int gcb_version(void) { return 100; }
+extern "C" uint64_t gcb_launch_count(void) { return g_launches.load(); }
+extern "C" int gcb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+#define GCB_BLOCK 128
+static inline int grid_for(int n) { return (n + GCB_BLOCK - 1) / GCB_BLOCK; }
+
+// ------------------------------------------------------------------------------------------------ pack / unpack
+__global__ void __launch_bounds__(GCB_BLOCK) k_pack(int n, const int8_t* __restrict__ boards,
+                                                    const int8_t* __restrict__ players,
+                                                    const uint8_t* __restrict__ rights4, gcb_positions out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4* src = reinterpret_cast<const int4*>(boards + (size_t)i * 64);
+    alignas(16) int8_t m[64];
+#pragma unroll
+    for (int k = 0; k < 4; k++) *reinterpret_cast<int4*>(m + 16 * k) = __ldg(src + k);
+    Board b = board_from_mailbox(m);
+    reinterpret_cast<ulonglong2*>(out.bb01)[i] = make_ulonglong2(b.t0, b.t1);
+    reinterpret_cast<ulonglong2*>(out.bb23)[i] = make_ulonglong2(b.t2, b.w);
+    if (out.player) out.player[i] = players ? (players[i] < 0 ? 1 : 0) : 0;
+    if (out.rights) {
+        uint8_t r = 0;
+        if (rights4) {
+            uchar4 q = reinterpret_cast<const uchar4*>(rights4)[i];
+            r = (q.x ? RT_WK : 0) | (q.y ? RT_WQ : 0) | (q.z ? RT_BK : 0) | (q.w ? RT_BQ : 0);
+        }
+        out.rights[i] = r;
+    }
+}
+
+__device__ __forceinline__ void board_to_mailbox(const Board& b, int8_t* m) {
+#pragma unroll
+    for (int sq = 0; sq < 64; sq++) m[sq] = (int8_t)piece_id(b, sq);
+}
+
+__global__ void __launch_bounds__(GCB_BLOCK) k_unpack(int n, gcb_positions in, int8_t* __restrict__ boards,
+                                                      int8_t* __restrict__ players, uint8_t* __restrict__ rights4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ulonglong2 a = reinterpret_cast<const ulonglong2*>(in.bb01)[i], c = reinterpret_cast<const ulonglong2*>(in.bb23)[i];
+    Board b = {a.x, a.y, c.x, c.y};
+    if (boards) {
+        alignas(16) int8_t m[64];
+        board_to_mailbox(b, m);
+        int4* dst = reinterpret_cast<int4*>(boards + (size_t)i * 64);
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k] = *reinterpret_cast<int4*>(m + 16 * k);
+    }
+    if (players && in.player) players[i] = in.player[i] ? -1 : 1;
+    if (rights4 && in.rights) {
+        uint8_t r = in.rights[i];
+        reinterpret_cast<uchar4*>(rights4)[i] = make_uchar4(r & RT_WK ? 1 : 0, r & RT_WQ ? 1 : 0, r & RT_BK ? 1 : 0, r & RT_BQ ? 1 : 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ engine kernels
+template <bool ATTACK>
+__global__ void __launch_bounds__(GCB_BLOCK) k_movegen(int n, gcb_positions pos, int castles_only,
+                                                       uint16_t* __restrict__ actions, int stride,
+                                                       int32_t* __restrict__ counts, uint8_t* __restrict__ incheck) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ulonglong2 a = reinterpret_cast<const ulonglong2*>(pos.bb01)[i], c = reinterpret_cast<const ulonglong2*>(pos.bb23)[i];
+    Board b = {a.x, a.y, c.x, c.y};
+    const int white = pos.player[i] == 0;
+    const u32 rights = mask_rights(b, pos.rights[i]);  // convert_py_state -> State::new, lib.rs:1267-1274
+    ListWriter lw(actions + (size_t)i * stride, stride);
+    bool chk = false;
+    u64 eatt;
+    gen_moves<ATTACK>(b, white, rights, lw, &eatt, &chk);
+    lw.flush();
+    int cnt = lw.n;
+    if (castles_only) {  // get_castle_moves, lib.rs:1482-1500: the castle tail of the same list
+        uint16_t* l = actions + (size_t)i * stride;
+        int m = 0, lim = cnt < stride ? cnt : stride;
+        for (int k = 0; k < lim; k++) {
+            uint16_t v = l[k];
+            if (v >= 4096) l[m++] = v;
+        }
+        cnt = m;
+    }
+    counts[i] = cnt;
+    if (incheck) incheck[i] = chk;
+}
+
+__global__ void __launch_bounds__(GCB_BLOCK) k_next_state(int n, gcb_positions pos, const int32_t* __restrict__ actions,
+                                                          gcb_positions out, uint8_t* __restrict__ checks,
+                                                          int32_t* __restrict__ reward, int8_t* __restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ulonglong2 a = reinterpret_cast<const ulonglong2*>(pos.bb01)[i], c = reinterpret_cast<const ulonglong2*>(pos.bb23)[i];
+    Board b = {a.x, a.y, c.x, c.y};
+    const int black = pos.player[i] != 0;
+    u32 rights = mask_rights(b, pos.rights[i]);  // Q21: masked by the INPUT board, then cloned
+    Board nb = b;
+    int st;
+    bool irr;
+    int r = apply_action(nb, rights, !black, actions[i], &st, &irr);
+    if (st) nb = b, r = 0;
+    reinterpret_cast<ulonglong2*>(out.bb01)[i] = make_ulonglong2(nb.t0, nb.t1);
+    reinterpret_cast<ulonglong2*>(out.bb23)[i] = make_ulonglong2(nb.t2, nb.w);
+    if (out.player) out.player[i] = st ? black : !black;  // lib.rs:779-780
+    if (out.rights) out.rights[i] = (uint8_t)rights;
+    if (checks) checks[i] = (uint8_t)check_flags(nb);  // update_state, lib.rs:1440
+    if (reward) reward[i] = r;
+    if (status) status[i] = (int8_t)st;
+}
+
+__global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions pos, uint8_t* __restrict__ rights_out,
+                                                            uint8_t* __restrict__ checks) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ulonglong2 a = reinterpret_cast<const ulonglong2*>(pos.bb01)[i], c = reinterpret_cast<const ulonglong2*>(pos.bb23)[i];
+    Board b = {a.x, a.y, c.x, c.y};
+    if (rights_out) rights_out[i] = (uint8_t)mask_rights(b, pos.rights[i]);
+    if (checks) checks[i] = (uint8_t)check_flags(b);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GCB_BLOCK) k_env_step(EnvView v, StepIO io) {
+    __shared__ unsigned long long s_stats[ST_COUNT];
+    if (MODE != MODE_RESET) {
+        if (threadIdx.x < ST_COUNT) s_stats[threadIdx.x] = 0;
+        __syncthreads();
+    }
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    StepStats st;
+#pragma unroll
+    for (int k = 0; k < ST_USED; k++) st.v[k] = 0;
+    bool active = e < v.N;
+    if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;
+    if (active) env_step_one<MODE>(v, io, e, st);
+    if (MODE != MODE_RESET) {
+        // episode statistics: warp reduce -> shared atomics -> one global atomic per counter per block
+#pragma unroll
+        for (int k = 0; k < ST_USED; k++) {
+            int t = __reduce_add_sync(0xffffffffu, st.v[k]);
+            if ((threadIdx.x & 31) == 0 && t) atomicAdd(&s_stats[k], (unsigned long long)(long long)t);
+        }
+        __syncthreads();
+        if (threadIdx.x < ST_USED && s_stats[threadIdx.x]) atomicAdd((unsigned long long*)&v.stats[threadIdx.x], s_stats[threadIdx.x]);
+    }
+}
+
+__global__ void k_make_templates(int n, const int8_t* __restrict__ boards, ulonglong2* bb01, ulonglong2* bb23, u64* meta,
+                                 u64* zkey, uint16_t* legal, int stride) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    make_template_one(i, boards, bb01, bb23, meta, zkey, legal, stride);
+}
+
+__global__ void __launch_bounds__(GCB_BLOCK) k_env_export(EnvView v, int8_t* __restrict__ boards, int32_t* __restrict__ info) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.N) return;
+    alignas(16) int8_t m[64];
+    alignas(16) int32_t inf[16];
+    env_export_one(v, e, boards ? m : nullptr, info ? inf : nullptr);
+    if (boards) {
+        int4* dst = reinterpret_cast<int4*>(boards + (size_t)e * 64);
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k] = *reinterpret_cast<int4*>(m + 16 * k);
+    }
+    if (info) {
+        int4* o = reinterpret_cast<int4*>(info + (size_t)e * 16);
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = *reinterpret_cast<int4*>(inf + 4 * k);
+    }
+}
+
+__global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_mask(EnvView v, uint8_t* __restrict__ mask) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.N) return;
+    int n = (int)(v.meta[e] >> M_NLEGAL_SHIFT) & 0xFFF;
+    if (n > v.stride) n = v.stride;
+    const uint16_t* l = v.legal + (size_t)e * v.stride;
+    uint8_t* m = mask + (size_t)e * 4101;
+    for (int k = 0; k < n; k++) m[l[k]] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int need_gpu() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(GCB_E_NOGPU, "no CUDA device", "this library has no CPU fallback");
+    return GCB_OK;
+}
+
+extern "C" int gcb_pack(int n, const int8_t* d_boards, const int8_t* d_players, const uint8_t* d_rights4, gcb_positions out,
+                        void* stream) {
+    if (n < 0 || !d_boards || !out.bb01 || !out.bb23) return fail(GCB_E_ARG, "gcb_pack", "null pointer or n < 0");
+    if (n == 0) return GCB_OK;
+    k_pack<<<grid_for(n), GCB_BLOCK, 0, (cudaStream_t)stream>>>(n, d_boards, d_players, d_rights4, out);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_unpack(int n, gcb_positions in, int8_t* d_boards, int8_t* d_players, uint8_t* d_rights4, void* stream) {
+    if (n < 0 || !in.bb01 || !in.bb23) return fail(GCB_E_ARG, "gcb_unpack", "null pointer or n < 0");
+    if (n == 0) return GCB_OK;
+    k_unpack<<<grid_for(n), GCB_BLOCK, 0, (cudaStream_t)stream>>>(n, in, d_boards, d_players, d_rights4);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_get_possible_moves(int n, gcb_positions pos, int attack, int castles_only, uint16_t* d_actions, int stride,
+                                      int32_t* d_counts, uint8_t* d_incheck, void* stream) {
+    if (n < 0 || !pos.bb01 || !pos.bb23 || !pos.player || !pos.rights || !d_actions || !d_counts || stride <= 0 || (stride & 1))
+        return fail(GCB_E_ARG, "gcb_get_possible_moves", "null pointer, n < 0 or odd stride");
+    if (n == 0) return GCB_OK;
+    if (attack)
+        k_movegen<true><<<grid_for(n), GCB_BLOCK, 0, (cudaStream_t)stream>>>(n, pos, 0, d_actions, stride, d_counts, d_incheck);
+    else
+        k_movegen<false><<<grid_for(n), GCB_BLOCK, 0, (cudaStream_t)stream>>>(n, pos, castles_only, d_actions, stride, d_counts,
+                                                                               d_incheck);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_next_state(int n, gcb_positions pos, const int32_t* d_actions, gcb_positions out, uint8_t* d_checks,
+                              int32_t* d_reward, int8_t* d_status, void* stream) {
+    if (n < 0 || !pos.bb01 || !pos.bb23 || !pos.player || !pos.rights || !d_actions || !out.bb01 || !out.bb23)
+        return fail(GCB_E_ARG, "gcb_next_state", "null pointer or n < 0");
+    if (n == 0) return GCB_OK;
+    k_next_state<<<grid_for(n), GCB_BLOCK, 0, (cudaStream_t)stream>>>(n, pos, d_actions, out, d_checks, d_reward, d_status);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_update_state(int n, gcb_positions pos, uint8_t* d_rights_out, uint8_t* d_checks, void* stream) {
+    if (n < 0 || !pos.bb01 || !pos.bb23 || !pos.rights) return fail(GCB_E_ARG, "gcb_update_state", "null pointer or n < 0");
+    if (n == 0) return GCB_OK;
+    k_update_state<<<grid_for(n), GCB_BLOCK, 0, (cudaStream_t)stream>>>(n, pos, d_rights_out, d_checks);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+// ---- host-buffer engine calls: one scratch arena per call (these are the convenience / binding entry points)
+struct Arena {
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
+    int init(size_t bytes) {
+        cap = bytes;
+        return cudaMalloc(&base, bytes ? bytes : 256) == cudaSuccess ? 0 : -1;
+    }
+    template <class T>
+    T* take(size_t count) {
+        size_t off = (used + 255) & ~(size_t)255;
+        used = off + count * sizeof(T);
+        return reinterpret_cast<T*>(base + off);
+    }
+    ~Arena() {
+        if (base) cudaFree(base);
+    }
+};
+static size_t al(size_t x) { return ((x + 255) & ~(size_t)255) + 256; }
+
+static gcb_positions arena_positions(Arena& A, int n) {
+    gcb_positions p;
+    p.bb01 = A.take<uint64_t>((size_t)n * 2);
+    p.bb23 = A.take<uint64_t>((size_t)n * 2);
+    p.player = A.take<uint8_t>(n);
+    p.rights = A.take<uint8_t>(n);
+    return p;
+}
+static size_t positions_bytes(int n) { return al((size_t)n * 16) * 2 + al(n) * 2; }
+
+extern "C" int gcb_host_get_possible_moves(int n, const int8_t* boards, const int8_t* players, const uint8_t* rights4, int attack,
+                                           int castles_only, uint16_t* actions, int stride, int32_t* counts, uint8_t* incheck) {
+    if (int rc = need_gpu()) return rc;
+    if (n < 0 || !boards || !players || !rights4 || !actions || !counts || stride <= 0 || (stride & 1))
+        return fail(GCB_E_ARG, "gcb_host_get_possible_moves", "null pointer, n < 0 or odd stride");
+    if (n == 0) return GCB_OK;
+    Arena A;
+    size_t bytes = al((size_t)n * 64) + al(n) + al((size_t)n * 4) + positions_bytes(n) + al((size_t)n * stride * 2) +
+                   al((size_t)n * 4) + al(n);
+    if (A.init(bytes)) return fail(GCB_E_NOMEM, "cudaMalloc", "scratch");
+    int8_t* d_b = A.take<int8_t>((size_t)n * 64);
+    int8_t* d_p = A.take<int8_t>(n);
+    uint8_t* d_r = A.take<uint8_t>((size_t)n * 4);
+    gcb_positions pos = arena_positions(A, n);
+    uint16_t* d_a = A.take<uint16_t>((size_t)n * stride);
+    int32_t* d_c = A.take<int32_t>(n);
+    uint8_t* d_i = A.take<uint8_t>(n);
+    CU(cudaMemcpyAsync(d_b, boards, (size_t)n * 64, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(d_p, players, n, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(d_r, rights4, (size_t)n * 4, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemsetAsync(d_a, 0, (size_t)n * stride * 2, 0));
+    if (int rc = gcb_pack(n, d_b, d_p, d_r, pos, 0)) return rc;
+    if (int rc = gcb_get_possible_moves(n, pos, attack, castles_only, d_a, stride, d_c, d_i, 0)) return rc;
+    CU(cudaMemcpyAsync(actions, d_a, (size_t)n * stride * 2, cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(counts, d_c, (size_t)n * 4, cudaMemcpyDeviceToHost, 0));
+    if (incheck) CU(cudaMemcpyAsync(incheck, d_i, n, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return GCB_OK;
+}
+
+extern "C" int gcb_host_next_state(int n, const int8_t* boards, const int8_t* players, const uint8_t* rights4,
+                                   const int32_t* actions, int8_t* out_boards, uint8_t* out_rights4, uint8_t* out_checks,
+                                   int32_t* out_reward, int8_t* out_status) {
+    if (int rc = need_gpu()) return rc;
+    if (n < 0 || !boards || !players || !rights4 || !actions || !out_boards || !out_rights4 || !out_checks || !out_reward ||
+        !out_status)
+        return fail(GCB_E_ARG, "gcb_host_next_state", "null pointer or n < 0");
+    if (n == 0) return GCB_OK;
+    Arena A;
+    size_t bytes = al((size_t)n * 64) * 2 + al(n) * 2 + al((size_t)n * 4) * 4 + positions_bytes(n) * 2 + al(n) * 2;
+    if (A.init(bytes)) return fail(GCB_E_NOMEM, "cudaMalloc", "scratch");
+    int8_t* d_b = A.take<int8_t>((size_t)n * 64);
+    int8_t* d_p = A.take<int8_t>(n);
+    uint8_t* d_r = A.take<uint8_t>((size_t)n * 4);
+    int32_t* d_a = A.take<int32_t>(n);
+    gcb_positions pos = arena_positions(A, n), out = arena_positions(A, n);
+    int8_t* d_ob = A.take<int8_t>((size_t)n * 64);
+    uint8_t* d_or = A.take<uint8_t>((size_t)n * 4);
+    uint8_t* d_oc = A.take<uint8_t>(n);
+    int32_t* d_rw = A.take<int32_t>(n);
+    int8_t* d_st = A.take<int8_t>(n);
+    CU(cudaMemcpyAsync(d_b, boards, (size_t)n * 64, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(d_p, players, n, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(d_r, rights4, (size_t)n * 4, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(d_a, actions, (size_t)n * 4, cudaMemcpyHostToDevice, 0));
+    if (int rc = gcb_pack(n, d_b, d_p, d_r, pos, 0)) return rc;
+    if (int rc = gcb_next_state(n, pos, d_a, out, d_oc, d_rw, d_st, 0)) return rc;
+    if (int rc = gcb_unpack(n, out, d_ob, nullptr, d_or, 0)) return rc;
+    CU(cudaMemcpyAsync(out_boards, d_ob, (size_t)n * 64, cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(out_rights4, d_or, (size_t)n * 4, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    // checks come back as 2 bytes per position (wchk, bchk) like the oracle's batch call
+    uint8_t* tmp = new (std::nothrow) uint8_t[n];
+    if (!tmp) return fail(GCB_E_NOMEM, "new", "host scratch");
+    cudaError_t e1 = cudaMemcpy(tmp, d_oc, n, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n && e1 == cudaSuccess; i++) out_checks[2 * i] = tmp[i] & 1, out_checks[2 * i + 1] = (tmp[i] >> 1) & 1;
+    delete[] tmp;
+    if (e1 != cudaSuccess) return fail(GCB_E_CUDA, "cudaMemcpy", cudaGetErrorString(e1));
+    CU(cudaMemcpy(out_reward, d_rw, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_status, d_st, n, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+
+extern "C" int gcb_host_update_state(int n, const int8_t* boards, const uint8_t* rights4, uint8_t* out_rights4,
+                                     uint8_t* out_checks) {
+    if (int rc = need_gpu()) return rc;
+    if (n < 0 || !boards || !rights4 || !out_rights4 || !out_checks) return fail(GCB_E_ARG, "gcb_host_update_state", "null pointer");
+    if (n == 0) return GCB_OK;
+    Arena A;
+    size_t bytes = al((size_t)n * 64) + al((size_t)n * 4) + positions_bytes(n) + al(n) * 2;
+    if (A.init(bytes)) return fail(GCB_E_NOMEM, "cudaMalloc", "scratch");
+    int8_t* d_b = A.take<int8_t>((size_t)n * 64);
+    uint8_t* d_r = A.take<uint8_t>((size_t)n * 4);
+    gcb_positions pos = arena_positions(A, n);
+    uint8_t* d_or = A.take<uint8_t>(n);
+    uint8_t* d_oc = A.take<uint8_t>(n);
+    CU(cudaMemcpyAsync(d_b, boards, (size_t)n * 64, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(d_r, rights4, (size_t)n * 4, cudaMemcpyHostToDevice, 0));
+    if (int rc = gcb_pack(n, d_b, nullptr, d_r, pos, 0)) return rc;
+    if (int rc = gcb_update_state(n, pos, d_or, d_oc, 0)) return rc;
+    uint8_t* tmp = new (std::nothrow) uint8_t[2 * (size_t)n];
+    if (!tmp) return fail(GCB_E_NOMEM, "new", "host scratch");
+    cudaError_t e1 = cudaMemcpy(tmp, d_or, n, cudaMemcpyDeviceToHost);
+    cudaError_t e2 = cudaMemcpy(tmp + n, d_oc, n, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; i++) {
+        uint8_t r = tmp[i], c = tmp[n + i];
+        out_rights4[4 * i] = r & 1, out_rights4[4 * i + 1] = (r >> 1) & 1, out_rights4[4 * i + 2] = (r >> 2) & 1,
+                        out_rights4[4 * i + 3] = (r >> 3) & 1;
+        out_checks[2 * i] = c & 1, out_checks[2 * i + 1] = (c >> 1) & 1;
+    }
+    delete[] tmp;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(GCB_E_CUDA, "cudaMemcpy", "update_state results");
+    return GCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ env object
+struct gcb_env {
+    gcb_env_config cfg;
+    EnvView v;
+    ulonglong2 *t_bb01 = nullptr, *t_bb23 = nullptr;
+    u64 *t_meta = nullptr, *t_zkey = nullptr;
+    uint16_t* t_legal = nullptr;
+    u64 tick = 0;
+    // staging for the host-buffer step calls
+    int32_t *d_in = nullptr, *d_reward = nullptr;
+    uint8_t *d_done = nullptr, *d_flags = nullptr;
+};
+
+static const int8_t kDefaultBoard[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6, -6, -6, -6, -6, -6, -6, 0, 0, 0, 0, 0, 0,
+                                         0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0, 0, 0, 0, 0, 0,
+                                         0,  0,  0,  0,  6,  6,  6,  6,  6,  6,  6,  6,  3,  5,  4,  2,  1, 4, 5, 3};
+
+template <int MODE>
+static int launch_step(gcb_env* env, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, int32_t* act_out,
+                       int32_t* bot_out, int ep_inc, cudaStream_t s) {
+    StepIO io;
+    io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
+    io.tick = env->tick, io.ep_inc = ep_inc;
+    k_env_step<MODE><<<grid_for(env->v.N), GCB_BLOCK, 0, s>>>(env->v, io);
+    env->tick++;
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_destroy(gcb_env* env) {
+    if (!env) return GCB_OK;
+    cudaSetDevice(env->cfg.device);
+    cudaFree(env->v.bb01), cudaFree(env->v.bb23), cudaFree(env->v.meta), cudaFree(env->v.zkey), cudaFree(env->v.episode);
+    cudaFree(env->v.legal), cudaFree(env->v.hist), cudaFree(env->v.stats);
+    cudaFree(env->t_bb01), cudaFree(env->t_bb23), cudaFree(env->t_meta), cudaFree(env->t_zkey), cudaFree(env->t_legal);
+    cudaFree(env->d_in), cudaFree(env->d_reward), cudaFree(env->d_done), cudaFree(env->d_flags);
+    delete env;
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
+    if (!cfg_in || !out) return fail(GCB_E_ARG, "gcb_env_create", "null pointer");
+    if (int rc = need_gpu()) return rc;
+    gcb_env_config cfg = *cfg_in;
+    if (cfg.num_envs <= 0) return fail(GCB_E_ARG, "gcb_env_create", "num_envs <= 0");
+    if (cfg.legal_stride == 0) cfg.legal_stride = 144;
+    if (cfg.history_cap == 0) cfg.history_cap = 512;
+    if (cfg.moves_max < 0) cfg.moves_max = 149;
+    if (cfg.legal_stride < 2 || (cfg.legal_stride & 1) || cfg.legal_stride > 4094)
+        return fail(GCB_E_ARG, "gcb_env_create", "legal_stride must be even and in [2, 4094]");
+    if (cfg.history_cap < 8 || cfg.history_cap > 1024 || (cfg.history_cap & (cfg.history_cap - 1)))
+        return fail(GCB_E_ARG, "gcb_env_create", "history_cap must be a power of two in [8, 1024]");
+    if (cfg.opponent != 0 && cfg.opponent != 1) return fail(GCB_E_ARG, "gcb_env_create", "opponent must be 0 or 1");
+    if (cfg.agent_black && cfg.opponent != 1)  // chess_v2.py:208-209 calls opponent_policy(None) -> TypeError (Q23)
+        return fail(GCB_E_ARG, "gcb_env_create", "player_color BLACK needs opponent 'random' (the reference raises TypeError)");
+    if (cfg.n_templates < 0 || (cfg.n_templates > 0 && !cfg.template_boards))
+        return fail(GCB_E_ARG, "gcb_env_create", "template_boards missing");
+    CU(cudaSetDevice(cfg.device));
+    gcb_env* env = new (std::nothrow) gcb_env();
+    if (!env) return fail(GCB_E_NOMEM, "new", "gcb_env");
+    const int N = cfg.num_envs, T = cfg.n_templates > 0 ? cfg.n_templates : 1, S = cfg.legal_stride, H = cfg.history_cap;
+    env->cfg = cfg;
+    env->cfg.template_boards = nullptr;
+    EnvView& v = env->v;
+    memset(&v, 0, sizeof(v));
+    int8_t* d_tb = nullptr;
+    cudaError_t e = cudaSuccess;
+#define ALLOC(ptr, bytes) \
+    if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
+    ALLOC(v.bb01, (size_t)N * 16);
+    ALLOC(v.bb23, (size_t)N * 16);
+    ALLOC(v.meta, (size_t)N * 8);
+    ALLOC(v.zkey, (size_t)N * 8);
+    ALLOC(v.episode, (size_t)N * 4);
+    ALLOC(v.legal, (size_t)N * S * 2);
+    ALLOC(v.hist, (size_t)N * H * 8);
+    ALLOC(v.stats, ST_COUNT * 8);
+    ALLOC(env->t_bb01, (size_t)T * 16);
+    ALLOC(env->t_bb23, (size_t)T * 16);
+    ALLOC(env->t_meta, (size_t)T * 8);
+    ALLOC(env->t_zkey, (size_t)T * 8);
+    ALLOC(env->t_legal, (size_t)T * S * 2);
+    ALLOC(env->d_in, (size_t)N * 4);
+    ALLOC(env->d_reward, (size_t)N * 4);
+    ALLOC(env->d_done, (size_t)N);
+    ALLOC(env->d_flags, (size_t)N);
+    ALLOC(d_tb, (size_t)T * 64);
+#undef ALLOC
+    if (e != cudaSuccess) {
+        cudaFree(d_tb);
+        gcb_env_destroy(env);
+        return fail(GCB_E_NOMEM, "cudaMalloc", cudaGetErrorString(e));
+    }
+    v.t_bb01 = env->t_bb01, v.t_bb23 = env->t_bb23, v.t_meta = env->t_meta, v.t_zkey = env->t_zkey, v.t_legal = env->t_legal;
+    v.seed = cfg.seed, v.N = N, v.stride = S, v.hist_mask = H - 1, v.n_templates = T, v.env_offset = cfg.env_id_offset;
+    v.moves_max = cfg.moves_max, v.opponent = cfg.opponent, v.agent_black = cfg.agent_black, v.auto_reset = cfg.auto_reset;
+    v.pps = 1 + (cfg.opponent == 1 ? 1 : 0);  // ring slots per step: agent ply, bot ply (a reset-bot ply reuses the bot slot)
+    int rc = GCB_OK;
+    do {
+        if (cudaMemcpy(d_tb, cfg.n_templates > 0 ? cfg.template_boards : kDefaultBoard, (size_t)T * 64, cudaMemcpyHostToDevice) !=
+                cudaSuccess ||
+            cudaMemset(v.stats, 0, ST_COUNT * 8) != cudaSuccess || cudaMemset(v.episode, 0, (size_t)N * 4) != cudaSuccess ||
+            cudaMemset(v.meta, 0, (size_t)N * 8) != cudaSuccess || cudaMemset(v.bb01, 0, (size_t)N * 16) != cudaSuccess ||
+            cudaMemset(v.bb23, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.zkey, 0, (size_t)N * 8) != cudaSuccess ||
+            cudaMemset(env->t_legal, 0, (size_t)T * S * 2) != cudaSuccess) {
+            rc = fail(GCB_E_CUDA, "cudaMemcpy/cudaMemset", "env init");
+            break;
+        }
+        k_make_templates<<<(T + 63) / 64, 64>>>(T, d_tb, env->t_bb01, env->t_bb23, env->t_meta, env->t_zkey, env->t_legal, S);
+        g_launches.fetch_add(1);
+        // episode 0 starts with a reset that does not advance the episode counter
+        StepIO io;
+        memset(&io, 0, sizeof(io));
+        io.tick = env->tick;
+        k_env_step<MODE_RESET><<<grid_for(N), GCB_BLOCK>>>(v, io);
+        env->tick++;
+        g_launches.fetch_add(1);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        if (e2 != cudaSuccess) rc = fail(GCB_E_CUDA, "env init kernels", cudaGetErrorString(e2));
+    } while (0);
+    cudaFree(d_tb);
+    if (rc) {
+        gcb_env_destroy(env);
+        return rc;
+    }
+    *out = env;
+    return GCB_OK;
+}
+
+#define ENV_CHECK(env)                                               \
+    if (!(env)) return fail(GCB_E_ARG, __func__, "null env");        \
+    CU(cudaSetDevice((env)->cfg.device))
+
+extern "C" int gcb_env_reset(gcb_env* env, const uint8_t* d_mask, void* stream) {
+    ENV_CHECK(env);
+    return launch_step<MODE_RESET>(env, d_mask, nullptr, nullptr, nullptr, nullptr, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gcb_env_step(gcb_env* env, const int32_t* d_actions, int32_t* d_reward, uint8_t* d_done, uint8_t* d_flags,
+                            void* stream) {
+    ENV_CHECK(env);
+    if (!d_actions) return fail(GCB_E_ARG, "gcb_env_step", "null actions");
+    return launch_step<MODE_ACTION>(env, d_actions, d_reward, d_done, d_flags, nullptr, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gcb_env_step_index(gcb_env* env, const uint32_t* d_u32, int32_t* d_reward, uint8_t* d_done, uint8_t* d_flags,
+                                  void* stream) {
+    ENV_CHECK(env);
+    if (!d_u32) return fail(GCB_E_ARG, "gcb_env_step_index", "null random words");
+    return launch_step<MODE_INDEX>(env, d_u32, d_reward, d_done, d_flags, nullptr, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward, uint8_t* d_done, uint8_t* d_flags,
+                                    int32_t* d_actions_out, int32_t* d_bot_out, void* stream) {
+    ENV_CHECK(env);
+    if (nsteps < 0) return fail(GCB_E_ARG, "gcb_env_step_sampled", "nsteps < 0");
+    const size_t N = (size_t)env->v.N;
+    for (int t = 0; t < nsteps; t++) {
+        int rc = launch_step<MODE_SAMPLED>(env, nullptr, d_reward, d_done, d_flags, d_actions_out ? d_actions_out + t * N : nullptr,
+                                           d_bot_out ? d_bot_out + t * N : nullptr, 1, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return GCB_OK;
+}
+
+static int step_host_common(gcb_env* env, int mode, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags) {
+    const size_t N = (size_t)env->v.N;
+    CU(cudaMemcpyAsync(env->d_in, in, N * 4, cudaMemcpyHostToDevice, 0));
+    int rc = mode == MODE_ACTION
+                 ? launch_step<MODE_ACTION>(env, env->d_in, env->d_reward, env->d_done, env->d_flags, nullptr, nullptr, 1, 0)
+                 : launch_step<MODE_INDEX>(env, env->d_in, env->d_reward, env->d_done, env->d_flags, nullptr, nullptr, 1, 0);
+    if (rc) return rc;
+    if (reward) CU(cudaMemcpyAsync(reward, env->d_reward, N * 4, cudaMemcpyDeviceToHost, 0));
+    if (done) CU(cudaMemcpyAsync(done, env->d_done, N, cudaMemcpyDeviceToHost, 0));
+    if (flags) CU(cudaMemcpyAsync(flags, env->d_flags, N, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_step_host(gcb_env* env, const int32_t* actions, int32_t* reward, uint8_t* done, uint8_t* flags) {
+    ENV_CHECK(env);
+    if (!actions) return fail(GCB_E_ARG, "gcb_env_step_host", "null actions");
+    return step_host_common(env, MODE_ACTION, actions, reward, done, flags);
+}
+
+extern "C" int gcb_env_step_index_host(gcb_env* env, const uint32_t* u32, int32_t* reward, uint8_t* done, uint8_t* flags) {
+    ENV_CHECK(env);
+    if (!u32) return fail(GCB_E_ARG, "gcb_env_step_index_host", "null random words");
+    return step_host_common(env, MODE_INDEX, u32, reward, done, flags);
+}
+
+extern "C" int gcb_env_export(gcb_env* env, int8_t* d_boards, int32_t* d_info, void* stream) {
+    ENV_CHECK(env);
+    k_env_export<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, d_boards, d_info);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_legal_mask(gcb_env* env, uint8_t* d_mask, void* stream) {
+    ENV_CHECK(env);
+    if (!d_mask) return fail(GCB_E_ARG, "gcb_env_legal_mask", "null mask");
+    CU(cudaMemsetAsync(d_mask, 0, (size_t)env->v.N * 4101, (cudaStream_t)stream));
+    k_env_legal_mask<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, d_mask);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_legal_ptr(gcb_env* env, uint16_t** d_legal, int32_t* stride) {
+    if (!env) return fail(GCB_E_ARG, "gcb_env_legal_ptr", "null env");
+    if (d_legal) *d_legal = env->v.legal;
+    if (stride) *stride = env->v.stride;
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_positions(gcb_env* env, gcb_positions* out) {
+    if (!env || !out) return fail(GCB_E_ARG, "gcb_env_positions", "null pointer");
+    out->bb01 = reinterpret_cast<uint64_t*>(env->v.bb01);
+    out->bb23 = reinterpret_cast<uint64_t*>(env->v.bb23);
+    out->player = nullptr, out->rights = nullptr;
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_stats(gcb_env* env, uint64_t* out16, void* stream) {
+    ENV_CHECK(env);
+    if (!out16) return fail(GCB_E_ARG, "gcb_env_stats", "null out");
+    CU(cudaMemcpyAsync(out16, env->v.stats, ST_COUNT * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_stats_reset(gcb_env* env, void* stream) {
+    ENV_CHECK(env);
+    CU(cudaMemsetAsync(env->v.stats, 0, ST_COUNT * 8, (cudaStream_t)stream));
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_stats_ptr(gcb_env* env, uint64_t** d_stats) {
+    if (!env || !d_stats) return fail(GCB_E_ARG, "gcb_env_stats_ptr", "null pointer");
+    *d_stats = reinterpret_cast<uint64_t*>(env->v.stats);
+    return GCB_OK;
+}

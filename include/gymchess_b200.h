@@ -1,0 +1,180 @@
+/*
+ * gymchess_b200.h -- C ABI of libgymchess_b200.so, the B200 (sm_100a) drop-in for the
+ * gym-chess v2 env's step / legal-move-generation path.
+ *
+ * Plain pointers and sizes only (no torch / CUDA types): `stream` arguments are a
+ * cudaStream_t passed as void* (NULL = default stream).  Every entry point returns
+ * GCB_OK (0) or a negative GCB_E_* code; gcb_last_error() gives the text.
+ *
+ * What each entry point replaces in the reference (bobu36000/gym-chess):
+ *   engine level  = the 4 methods of the PyO3 class `ChessEngine`, src/lib.rs:1412-1512,
+ *                   batched: one call handles n independent positions;
+ *   env level     = `ChessEnvV2.reset/step` and the random opponent,
+ *                   gym_chess/envs/chess_v2.py:116-127, 183-294, 393-412, batched over N envs
+ *                   held in device memory.
+ * The reference-side bindings a maintainer would add are shown in INTEGRATION.md.
+ *
+ * Wire format (host or device, as stated per function):
+ *   board   int8[64]  row-major, row 0 = rank 8; K1 Q2 R3 B4 N5 P6, black negative
+ *                     (lib.rs:11-17, 41-50)
+ *   player  int8      +1 = "WHITE", -1 = "BLACK"
+ *   rights  uint8[4]  (white_king, white_queen, black_king, black_queen)_castle_is_possible
+ *   action  int32     from*64+to | 4096 KSW | 4097 QSW | 4098 KSB | 4099 QSB | 4100 resign
+ *                     (chess_v2.py:492-506)
+ *   checks  uint8     bit0 white_king_is_checked, bit1 black_king_is_checked
+ */
+#ifndef GYMCHESS_B200_H
+#define GYMCHESS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCB_OK 0
+#define GCB_E_CUDA (-1)    /* a CUDA runtime call failed */
+#define GCB_E_ARG (-2)     /* bad argument */
+#define GCB_E_NOGPU (-3)   /* no CUDA device: there is NO CPU fallback */
+#define GCB_E_NOMEM (-4)
+
+#define GCB_ACT_CASTLE_KS_WHITE 4096
+#define GCB_ACT_CASTLE_QS_WHITE 4097
+#define GCB_ACT_CASTLE_KS_BLACK 4098
+#define GCB_ACT_CASTLE_QS_BLACK 4099
+#define GCB_ACT_RESIGN 4100
+
+/* per-env flags written by the step entry points */
+#define GCB_F_INVALID 1u     /* action not in the legal list: reward -10, done unchanged (chess_v2.py:240-242) */
+#define GCB_F_MATE 2u        /* side to move has no legal move and is in check (chess_v2.py:270-272, 286-288) */
+#define GCB_F_REPETITION 4u  /* pre-move board seen for the 3rd time (chess_v2.py:404-407) */
+#define GCB_F_CAP 8u         /* move_count > 149 early exit (chess_v2.py:252-258) */
+#define GCB_F_WEDGED 16u     /* side to move has no legal move and is NOT in check: the reference never
+                                terminates here (stalemate is not a terminal state; with the random bot it raises
+                                TypeError).  Reported so that callers / auto-reset can act on it. */
+#define GCB_F_RESET 32u      /* the env was auto-reset after this step */
+
+const char *gcb_last_error(void);
+int gcb_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t gcb_launch_count(void);
+int gcb_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Packed device-side position set (structure of arrays; 34 B per position)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t *bb01;  /* [n][2]  piece-code bit-planes t0, t1                (16 B, 16-B aligned) */
+    uint64_t *bb23;  /* [n][2]  piece-code bit-plane t2, colour plane white (16 B, 16-B aligned) */
+    uint8_t *player; /* [n]     0 = white to move, 1 = black to move */
+    uint8_t *rights; /* [n]     bit0 wk, bit1 wq, bit2 bk, bit3 bq */
+} gcb_positions;
+
+/* wire format (device pointers) -> packed; replaces convert_py_state, lib.rs:1246-1276 */
+int gcb_pack(int n, const int8_t *d_boards, const int8_t *d_players, const uint8_t *d_rights4, gcb_positions out,
+             void *stream);
+/* packed -> wire format; replaces State::to_py_object, lib.rs:355-395 */
+int gcb_unpack(int n, gcb_positions in, int8_t *d_boards, int8_t *d_players, uint8_t *d_rights4, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine level, device pointers
+ * ------------------------------------------------------------------------------------------ */
+/* ChessEngine.get_possible_moves(state, player, attack), lib.rs:1454-1480.
+ * d_actions uint16[n][stride] receives the ORDERED move list (normal moves in generation order,
+ * then castles); d_counts int32[n] the true count (entries beyond `stride` are dropped, so
+ * count > stride signals overflow); d_incheck uint8[n] (may be NULL) whether the mover's king square is in
+ * the opponent's attack map.  castles_only != 0 gives ChessEngine.get_castle_moves, lib.rs:1482-1500.
+ * `stride` must be even. */
+int gcb_get_possible_moves(int n, gcb_positions pos, int attack, int castles_only, uint16_t *d_actions, int stride,
+                           int32_t *d_counts, uint8_t *d_incheck, void *stream);
+
+/* ChessEngine.next_state(state, player, move), lib.rs:1422-1452: mask rights by king presence on the input
+ * board, apply, recompute both check flags.  `pos.player` is the mover.  d_status int8[n]: 0 ok, -1 the from
+ * square is empty (the reference panics, lib.rs:693-695), -2 bad action code; on error the position is copied. */
+int gcb_next_state(int n, gcb_positions pos, const int32_t *d_actions, gcb_positions out, uint8_t *d_checks,
+                   int32_t *d_reward, int8_t *d_status, void *stream);
+
+/* ChessEngine.update_state(state), lib.rs:1502-1511: masked rights + both check flags */
+int gcb_update_state(int n, gcb_positions pos, uint8_t *d_rights_out, uint8_t *d_checks, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine level, HOST buffers in the reference's wire format (copies + pack inside the call).
+ * These are what a binding of the reference's `ChessEngine` would call.
+ * ------------------------------------------------------------------------------------------ */
+int gcb_host_get_possible_moves(int n, const int8_t *boards, const int8_t *players, const uint8_t *rights4, int attack,
+                                int castles_only, uint16_t *actions, int stride, int32_t *counts, uint8_t *incheck);
+int gcb_host_next_state(int n, const int8_t *boards, const int8_t *players, const uint8_t *rights4,
+                        const int32_t *actions, int8_t *out_boards, uint8_t *out_rights4, uint8_t *out_checks,
+                        int32_t *out_reward, int8_t *out_status);
+int gcb_host_update_state(int n, const int8_t *boards, const uint8_t *rights4, uint8_t *out_rights4,
+                          uint8_t *out_checks);
+
+/* ------------------------------------------------------------------------------------------
+ * Env level: N envs resident in device memory (ChessEnvV2, chess_v2.py:132-294)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gcb_env gcb_env;
+
+typedef struct {
+    int32_t num_envs;       /* N on this device */
+    uint32_t env_id_offset; /* global id of local env 0 (multi-GPU shards; enters the Philox counter) */
+    uint64_t seed;          /* Philox key */
+    int32_t opponent;       /* 0 = "none" (self-play, one ply per step), 1 = "random" (bot replies inside step) */
+    int32_t agent_black;    /* player_color == "BLACK": the bot opens at reset (chess_v2.py:208-216) */
+    int32_t auto_reset;     /* reset an env in the same step in which it terminates (done | cap | wedged) */
+    int32_t legal_stride;   /* capacity of the per-env legal list (even; default 144 when 0) */
+    int32_t history_cap;    /* slots of the per-env Zobrist ring (power of two; default 512 when 0) */
+    int32_t moves_max;      /* 149 in the reference (chess_v2.py:141); <0 selects 149 */
+    int32_t n_templates;    /* number of initial boards (0 = the default start position) */
+    const int8_t *template_boards; /* HOST int8[n_templates][64]; env i starts from template (global id % n) */
+    int32_t device;         /* CUDA device ordinal */
+} gcb_env_config;
+
+int gcb_env_create(const gcb_env_config *cfg, gcb_env **out);
+int gcb_env_destroy(gcb_env *env);
+
+/* ChessEnvV2.reset, chess_v2.py:183-217.  d_mask uint8[N] selects envs (NULL = all).  A reset starts a new
+ * episode (episode counter + 1, enters the Philox counter). */
+int gcb_env_reset(gcb_env *env, const uint8_t *d_mask, void *stream);
+
+/* ChessEnvV2.step(action), chess_v2.py:219-294, for all N envs.  Outputs (device, any may be NULL):
+ * d_reward int32[N] (the two float 0.0 literals are 0), d_done uint8[N], d_flags uint8[N] (GCB_F_*). */
+int gcb_env_step(gcb_env *env, const int32_t *d_actions, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
+                 void *stream);
+/* same, but env i plays legal[i][(u32[i] * n_legal[i]) >> 32] (RESIGN when it has no legal move): the uniform
+ * draw of make_random_policy (chess_v2.py:116-127) with caller-provided random words */
+int gcb_env_step_index(gcb_env *env, const uint32_t *d_u32, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
+                       void *stream);
+/* same, the word is drawn on the device: Philox4x32-10, counter (global env id, episode, step in episode, 0),
+ * key = seed.  Runs `nsteps` consecutive steps; outputs are those of the LAST step.  d_actions_out int32[nsteps][N]
+ * (may be NULL) records the action each env played, d_bot_out likewise the bot's reply (-1 = none). */
+int gcb_env_step_sampled(gcb_env *env, int nsteps, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
+                         int32_t *d_actions_out, int32_t *d_bot_out, void *stream);
+
+/* HOST-buffer forms (pinned staging + copies inside the call; synchronous) */
+int gcb_env_step_host(gcb_env *env, const int32_t *actions, int32_t *reward, uint8_t *done, uint8_t *flags);
+int gcb_env_step_index_host(gcb_env *env, const uint32_t *u32, int32_t *reward, uint8_t *done, uint8_t *flags);
+
+/* observation / state export (device pointers, any may be NULL):
+ *   d_boards int8[N][64]   -- `state["board"]`, the Box(-6,6,(8,8)) observation
+ *   d_info   int32[N][16]  -- current_player(+1/-1), wk, wq, bk, bq, wchk, bchk, done, move_count, n_legal,
+ *                             episode, step_in_episode, hist_len, 0, 0, 0 */
+int gcb_env_export(gcb_env *env, int8_t *d_boards, int32_t *d_info, void *stream);
+/* legal action mask uint8[N][4101] (possible_actions as a mask) */
+int gcb_env_legal_mask(gcb_env *env, uint8_t *d_mask, void *stream);
+/* zero-copy views of the resident state */
+int gcb_env_legal_ptr(gcb_env *env, uint16_t **d_legal, int32_t *stride);
+int gcb_env_positions(gcb_env *env, gcb_positions *out); /* player/rights pointers are NULL: they live in meta */
+
+/* episode statistics accumulated on the device since the last gcb_env_stats_reset:
+ * out uint64[16] = steps, plies, episodes, mates, repetitions, caps, wedged, invalid, reward_sum (two's complement
+ * int64), legal_sum, in_check, hist_overflow, list_overflow, hist_scanned (ring entries read by the repetition
+ * scans), 0, 0.   Synchronises the stream. */
+int gcb_env_stats(gcb_env *env, uint64_t *out16, void *stream);
+int gcb_env_stats_reset(gcb_env *env, void *stream);
+/* device pointer to the 16 counters (for an NCCL reduce by the caller) */
+int gcb_env_stats_ptr(gcb_env *env, uint64_t **d_stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -433,6 +433,7 @@ void gco_env_init(gco_env *e, const int8_t *initial_board, int agent_black, int 
     memcpy(e->initial_board, initial_board ? initial_board : DEFAULT_BOARD, 64);
     e->agent_black = agent_black, e->opponent = opponent, e->moves_max = 149;
     e->seed = seed, e->env_id = env_id, e->episode = 0;
+    e->forced_bot_action = -1;
     e->hist_cap = 1024;
     e->hist = (int8_t *)malloc((size_t)e->hist_cap * 64);
     gco_env_reset(e);
@@ -485,6 +486,7 @@ void gco_env_reset(gco_env *e) {
         uint32_t u = gco_draw_u32(e->seed, e->env_id, e->episode, 0, GCO_PURPOSE_RESET);
         if (e->n_legal > 0) {
             int a = e->legal[(uint32_t)(((uint64_t)u * (uint32_t)e->n_legal) >> 32)], r, rep;
+            if (e->forced_bot_action >= 0) a = e->forced_bot_action;
             env_player_move(e, a, &r, &rep);
             e->last_bot_action = a;
         } else {
@@ -533,6 +535,7 @@ int gco_env_step(gco_env *e, int action, int *reward, int *done) {
         }
         uint32_t u = gco_draw_u32(e->seed, e->env_id, e->episode, step_idx, GCO_PURPOSE_BOT);
         int a = e->legal[(uint32_t)(((uint64_t)u * (uint32_t)e->n_legal) >> 32)];
+        if (e->forced_bot_action >= 0) a = e->forced_bot_action; /* replay of a recorded bot move (tests) */
         e->last_bot_action = a;
         env_player_move(e, a, &r, &rep);
         e->done = rep;
@@ -653,7 +656,7 @@ void gco_next_state_batch(int n, const int8_t *boards, const int8_t *players, co
         gco_state_new(&s, boards + (size_t)i * 64, players[i], r[0], r[1], r[2], r[3]);
         int rc = gco_next_state(&s, players[i], actions[i], &o, &rew, &both);
         out_status[i] = (int8_t)rc;
-        if (rc) { o = s; rew = 0; }
+        if (rc) { o = s; gco_update_state(&o); rew = 0; } /* reference panics; defined here as: position unchanged */
         memcpy(out_boards + (size_t)i * 64, o.board, 64);
         out_rights[(size_t)i * 4 + 0] = o.wk, out_rights[(size_t)i * 4 + 1] = o.wq;
         out_rights[(size_t)i * 4 + 2] = o.bk, out_rights[(size_t)i * 4 + 3] = o.bq;
@@ -733,3 +736,4 @@ void gco_env_view(const gco_env *e, int8_t *board, int32_t *info, uint16_t *lega
     for (int k = 0; k < e->n_legal && k < legal_cap; k++) legal[k] = e->legal[k];
 }
 void gco_env_set_episode(gco_env *e, uint32_t episode) { e->episode = episode; }
+void gco_env_force_bot(gco_env *e, int action) { e->forced_bot_action = action; }

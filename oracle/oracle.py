@@ -89,6 +89,7 @@ def lib():
         L.gco_env_pick.argtypes = [C.c_void_p, C.c_uint32]
         L.gco_env_view.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gco_env_set_episode.argtypes = [C.c_void_p, C.c_uint32]
+        L.gco_env_force_bot.argtypes = [C.c_void_p, C.c_int]
         L.gco_selfplay.argtypes = [C.c_void_p, C.c_uint64, P(Stats)]
         L.gco_selfplay_mt.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, P(Stats)]
         L.gco_movegen_batch.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -193,12 +194,16 @@ class OracleEngine:
 class OracleEnv:
     """One env of the C restatement of chess_v2.py:183-294 (step / reset / random bot)."""
 
-    def __init__(self, initial_board=None, player_color=WHITE, opponent="none", seed=0, env_id=0):
+    def __init__(self, initial_board=None, player_color=WHITE, opponent="none", seed=0, env_id=0, first_bot_action=-1):
         ib = None
         if initial_board is not None:
             self._ib = np.ascontiguousarray(np.asarray(initial_board, dtype=np.int8).reshape(64))
             ib = self._ib.ctypes.data
         self._h = lib().gco_env_new(ib, int(player_color == BLACK), {"none": 0, "random": 1}[opponent], seed, env_id)
+        if first_bot_action >= 0:  # replay: the reset inside gco_env_new already drew; redo it with the forced move
+            lib().gco_env_force_bot(self._h, first_bot_action)
+            lib().gco_env_reset(self._h)
+            lib().gco_env_force_bot(self._h, -1)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -210,9 +215,12 @@ class OracleEnv:
             lib().gco_env_set_episode(self._h, episode)
         lib().gco_env_reset(self._h)
 
-    def step(self, action):
+    def step(self, action, bot_action=-1):
+        """-> (reward, done, raised).  bot_action >= 0 forces the bot's reply (replay of a recorded game)."""
         r, d = C.c_int(0), C.c_int(0)
+        lib().gco_env_force_bot(self._h, int(bot_action))
         raised = lib().gco_env_step(self._h, int(action), C.byref(r), C.byref(d))
+        lib().gco_env_force_bot(self._h, -1)
         return int(r.value), bool(d.value), bool(raised)
 
     def pick(self, u32):

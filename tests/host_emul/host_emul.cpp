@@ -1,0 +1,151 @@
+// host_emul.cpp -- TEST INFRASTRUCTURE.  Compiles the device rules (gym_chess_b200/csrc/chess_core.cuh,
+// env_core.cuh) with g++ so that `pytest -m "not gpu"` can check the bitboard / step LOGIC against the oracle
+// on a box without a GPU.  It is never loaded by the product package; the product has no CPU path.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../gym_chess_b200/csrc/env_core.cuh"
+
+extern "C" {
+
+void emul_movegen(int n, const int8_t* boards, const int8_t* players, const uint8_t* rights4, int attack, int castles_only,
+                  uint16_t* out, int stride, int32_t* counts, uint8_t* incheck) {
+    for (int i = 0; i < n; i++) {
+        Board b = board_from_mailbox(boards + (size_t)i * 64);
+        const uint8_t* q = rights4 + (size_t)i * 4;
+        u32 rights = (q[0] ? RT_WK : 0) | (q[1] ? RT_WQ : 0) | (q[2] ? RT_BK : 0) | (q[3] ? RT_BQ : 0);
+        rights = mask_rights(b, rights);
+        ListWriter lw(out + (size_t)i * stride, stride);
+        bool chk = false;
+        u64 eatt;
+        if (attack) gen_moves<true>(b, players[i] > 0, rights, lw, &eatt, &chk);
+        else gen_moves<false>(b, players[i] > 0, rights, lw, &eatt, &chk);
+        lw.flush();
+        int cnt = lw.n;
+        if (castles_only) {
+            uint16_t* l = out + (size_t)i * stride;
+            int m = 0, lim = cnt < stride ? cnt : stride;
+            for (int k = 0; k < lim; k++)
+                if (l[k] >= 4096) l[m++] = l[k];
+            cnt = m;
+        }
+        counts[i] = cnt;
+        if (incheck) incheck[i] = chk;
+    }
+}
+
+void emul_next_state(int n, const int8_t* boards, const int8_t* players, const uint8_t* rights4, const int32_t* actions,
+                     int8_t* out_boards, uint8_t* out_rights4, uint8_t* out_checks, int32_t* out_reward, int8_t* out_status) {
+    for (int i = 0; i < n; i++) {
+        Board b = board_from_mailbox(boards + (size_t)i * 64);
+        const uint8_t* q = rights4 + (size_t)i * 4;
+        u32 rights = (q[0] ? RT_WK : 0) | (q[1] ? RT_WQ : 0) | (q[2] ? RT_BK : 0) | (q[3] ? RT_BQ : 0);
+        rights = mask_rights(b, rights);
+        Board nb = b;
+        int st;
+        bool irr;
+        int r = apply_action(nb, rights, players[i] > 0, actions[i], &st, &irr);
+        if (st) nb = b, r = 0;
+        for (int sq = 0; sq < 64; sq++) out_boards[(size_t)i * 64 + sq] = (int8_t)piece_id(nb, sq);
+        out_rights4[4 * i] = rights & RT_WK ? 1 : 0, out_rights4[4 * i + 1] = rights & RT_WQ ? 1 : 0;
+        out_rights4[4 * i + 2] = rights & RT_BK ? 1 : 0, out_rights4[4 * i + 3] = rights & RT_BQ ? 1 : 0;
+        u32 c = check_flags(nb);
+        out_checks[2 * i] = c & 1, out_checks[2 * i + 1] = (c >> 1) & 1;
+        out_reward[i] = r, out_status[i] = (int8_t)st;
+    }
+}
+
+void emul_update_state(int n, const int8_t* boards, const uint8_t* rights4, uint8_t* out_rights4, uint8_t* out_checks) {
+    for (int i = 0; i < n; i++) {
+        Board b = board_from_mailbox(boards + (size_t)i * 64);
+        const uint8_t* q = rights4 + (size_t)i * 4;
+        u32 rights = (q[0] ? RT_WK : 0) | (q[1] ? RT_WQ : 0) | (q[2] ? RT_BK : 0) | (q[3] ? RT_BQ : 0);
+        rights = mask_rights(b, rights);
+        out_rights4[4 * i] = rights & RT_WK ? 1 : 0, out_rights4[4 * i + 1] = rights & RT_WQ ? 1 : 0;
+        out_rights4[4 * i + 2] = rights & RT_BK ? 1 : 0, out_rights4[4 * i + 3] = rights & RT_BQ ? 1 : 0;
+        u32 c = check_flags(b);
+        out_checks[2 * i] = c & 1, out_checks[2 * i + 1] = (c >> 1) & 1;
+    }
+}
+
+uint32_t emul_philox(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step, uint32_t purpose) {
+    return philox_draw(seed, env, episode, step, purpose);
+}
+
+// ---- env emulation: same SoA arrays, host memory, the same env_step_one()
+struct EmulEnv {
+    EnvView v;
+    u64 tick;
+    ulonglong2 *t_bb01, *t_bb23;
+    u64 *t_meta, *t_zkey;
+    uint16_t* t_legal;
+};
+
+void emul_env_destroy(EmulEnv* E) {
+    if (!E) return;
+    free(E->v.bb01), free(E->v.bb23), free(E->v.meta), free(E->v.zkey), free(E->v.episode), free(E->v.legal), free(E->v.hist);
+    free(E->v.stats), free(E->t_bb01), free(E->t_bb23), free(E->t_meta), free(E->t_zkey), free(E->t_legal);
+    free(E);
+}
+
+EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent, int agent_black, int auto_reset, int stride,
+                         int hist_cap, int moves_max, int n_templates, const int8_t* template_boards) {
+    static const int8_t def[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6, -6, -6, -6, -6, -6, -6, 0, 0, 0, 0, 0, 0,
+                                   0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0, 0, 0, 0, 0, 0,
+                                   0,  0,  0,  0,  6,  6,  6,  6,  6,  6,  6,  6,  3,  5,  4,  2,  1, 4, 5, 3};
+    EmulEnv* E = (EmulEnv*)calloc(1, sizeof(EmulEnv));
+    int T = n_templates > 0 ? n_templates : 1;
+    EnvView& v = E->v;
+    v.bb01 = (ulonglong2*)calloc(N, 16), v.bb23 = (ulonglong2*)calloc(N, 16);
+    v.meta = (u64*)calloc(N, 8), v.zkey = (u64*)calloc(N, 8), v.episode = (u32*)calloc(N, 4);
+    v.legal = (uint16_t*)calloc((size_t)N * stride, 2), v.hist = (u64*)calloc((size_t)N * hist_cap, 8);
+    v.stats = (u64*)calloc(ST_COUNT, 8);
+    E->t_bb01 = (ulonglong2*)calloc(T, 16), E->t_bb23 = (ulonglong2*)calloc(T, 16);
+    E->t_meta = (u64*)calloc(T, 8), E->t_zkey = (u64*)calloc(T, 8), E->t_legal = (uint16_t*)calloc((size_t)T * stride, 2);
+    v.t_bb01 = E->t_bb01, v.t_bb23 = E->t_bb23, v.t_meta = E->t_meta, v.t_zkey = E->t_zkey, v.t_legal = E->t_legal;
+    v.seed = seed, v.N = N, v.stride = stride, v.hist_mask = hist_cap - 1, v.n_templates = T, v.env_offset = env_offset;
+    v.moves_max = moves_max, v.opponent = opponent, v.agent_black = agent_black, v.auto_reset = auto_reset;
+    v.pps = 1 + (opponent == 1);
+    for (int i = 0; i < T; i++)
+        make_template_one(i, n_templates > 0 ? template_boards : def, E->t_bb01, E->t_bb23, E->t_meta, E->t_zkey, E->t_legal, stride);
+    StepIO io;
+    memset(&io, 0, sizeof(io));
+    io.tick = E->tick++;
+    StepStats st;
+    for (int e = 0; e < N; e++) env_step_one<MODE_RESET>(v, io, e, st);
+    return E;
+}
+
+// mode: 0 actions, 1 index words, 2 sampled, 3 reset (in = uint8 mask or NULL)
+void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, int32_t* act_out,
+                   int32_t* bot_out) {
+    StepIO io;
+    io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
+    io.tick = E->tick++, io.ep_inc = 1;
+    StepStats st;
+    memset(&st, 0, sizeof(st));
+    for (int e = 0; e < E->v.N; e++) {
+        switch (mode) {
+        case 0: env_step_one<MODE_ACTION>(E->v, io, e, st); break;
+        case 1: env_step_one<MODE_INDEX>(E->v, io, e, st); break;
+        case 2: env_step_one<MODE_SAMPLED>(E->v, io, e, st); break;
+        default:
+            if (!in || ((const uint8_t*)in)[e]) env_step_one<MODE_RESET>(E->v, io, e, st);
+        }
+    }
+    if (mode != 3)
+        for (int k = 0; k < ST_USED; k++) E->v.stats[k] += (u64)(long long)st.v[k];
+}
+
+void emul_env_export(EmulEnv* E, int8_t* boards, int32_t* info, uint16_t* legal, int legal_stride) {
+    for (int e = 0; e < E->v.N; e++) {
+        env_export_one(E->v, e, boards ? boards + (size_t)e * 64 : nullptr, info ? info + (size_t)e * 16 : nullptr);
+        if (legal)
+            for (int k = 0; k < legal_stride && k < E->v.stride; k++) legal[(size_t)e * legal_stride + k] = E->v.legal[(size_t)e * E->v.stride + k];
+    }
+}
+
+void emul_env_stats(EmulEnv* E, uint64_t* out16) { memcpy(out16, E->v.stats, ST_COUNT * 8); }
+
+}  // extern "C"

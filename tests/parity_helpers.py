@@ -1,0 +1,219 @@
+"""Shared parity checks: the same comparisons run against
+   * the oracle itself (pins the oracle to the fixtures made from the real chess_v2.py),
+   * tests/host_emul (the device rules compiled with g++; logic check without a GPU),
+   * the CUDA library through its C ABI (the parity tests proper, -m gpu).
+An "env adapter" offers: N, step(actions), step_index(u32), step_sampled(), reset(mask), export(), stats();
+step* return (reward, done, flags, agent_action, bot_action) as numpy arrays.
+"""
+import gzip
+import json
+import os
+
+import numpy as np
+
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+def load_golden():
+    def gz(name):
+        with gzip.open(os.path.join(GOLD, name)) as f:
+            return json.loads(f.read())
+
+    with open(os.path.join(GOLD, "reference_v2_tests.json")) as f:
+        ref = json.load(f)
+    return dict(reference_tests=ref, trajectories=gz("trajectories.json.gz"), positions=gz("positions.json.gz"))
+
+
+# ------------------------------------------------------------------ engine level
+def check_positions(movegen_fn, update_fn, positions):
+    """movegen_fn(boards, player(+1/-1), rights, attack) -> (actions[n,stride], counts[n], ...)"""
+    boards = np.array([p["board"] for p in positions], np.int8)
+    rights = np.array([p["rights"] for p in positions], np.uint8)
+    for player, pname in ((1, "WHITE"), (-1, "BLACK")):
+        for attack in (0, 1):
+            res = movegen_fn(boards, player, rights, bool(attack))
+            out, cnt = res[0], res[1]
+            for i, p in enumerate(positions):
+                exp = p["lists"]["%s_%d" % (pname, attack)]
+                got = [int(x) for x in out[i, : cnt[i]]]
+                assert got == exp, "position %d %s attack=%d\nboard=%s\nexp=%s\ngot=%s" % (
+                    i, pname, attack, np.array(p["board"]).reshape(8, 8), exp, got)
+    orr, oc = update_fn(boards, rights)
+    exp = np.array([p["update_state"] for p in positions], np.uint8)
+    assert (np.concatenate([orr, oc], 1) == exp).all()
+
+
+def check_reference_test_calls(engine, report):
+    """Replay every engine-visible call the reference's own v2 tests made (logged by make_golden.py)."""
+    ncalls = 0
+    for rec in report:
+        if rec["module"] == "test_benchmark":
+            continue
+        assert rec["passed"], rec
+        for c in rec["calls"]:
+            st = c["state"]
+            state = dict(board=np.array(st["board"], np.int8).reshape(8, 8).tolist(), current_player=st["player"],
+                         white_king_castle_is_possible=bool(st["rights"][0]), white_queen_castle_is_possible=bool(st["rights"][1]),
+                         black_king_castle_is_possible=bool(st["rights"][2]), black_queen_castle_is_possible=bool(st["rights"][3]))
+            if c["kind"] == "get_possible_moves":
+                got = [orc.str_to_action(m) for m in engine.get_possible_moves(state, c["player"], c["attack"])]
+                assert got == c["actions"], (rec["test"], c)
+            elif c["kind"] == "get_castle_moves":
+                got = [orc.str_to_action(m) for m in engine.get_castle_moves(state, c["player"])]
+                assert got == c["actions"], (rec["test"], c)
+            else:  # a step of test_run_moves: the engine part is next_state
+                ns, _ = engine.next_state(state, st["player"], orc.action_to_str(c["action"]))
+                assert [v for row in ns["board"] for v in row] == c["board_after"], (rec["test"], c)
+            ncalls += 1
+    return ncalls
+
+
+def harvest_positions(n_envs=64, steps=400, seed=1, every=3):
+    """positions from oracle random self-play (uniform over the game), both sides to move"""
+    boards, players, rights = [], [], []
+    for i in range(n_envs):
+        e = orc.OracleEnv(seed=seed, env_id=i)
+        for t in range(steps):
+            v = e.view()
+            if t % every == i % every:
+                boards.append(v["board"].copy())
+                players.append(v["current_player"])
+                rights.append([v["wk"], v["wq"], v["bk"], v["bq"]])
+            u = orc.draw_u32(seed, i, v["episode"], v["step_in_episode"], 0)
+            r, d, _ = e.step(e.pick(u))
+            if d or e.view()["n_legal"] == 0:
+                e.reset(v["episode"] + 1)
+    return np.array(boards, np.int8), np.array(players, np.int8), np.array(rights, np.uint8)
+
+
+def crafted_positions(rng, n=2000):
+    """random piece soups: kingless, multi-king, many queens, pawns on last ranks, random rights"""
+    boards = np.zeros((n, 64), np.int8)
+    for i in range(n):
+        k = rng.randint(1, 24)
+        sq = rng.choice(64, size=k, replace=False)
+        kind = rng.randint(4)
+        if kind == 0:    # anything goes
+            boards[i, sq] = rng.choice([-6, -5, -4, -3, -2, -1, 1, 2, 3, 4, 5, 6], size=k)
+        elif kind == 1:  # exactly one king each + soup
+            boards[i, sq] = rng.choice([-6, -5, -4, -3, -2, 2, 3, 4, 5, 6], size=k)
+            boards[i, sq[0]] = 1
+            if k > 1:
+                boards[i, sq[1]] = -1
+        elif kind == 2:  # castle shapes
+            boards[i, sq] = rng.choice([-6, -5, -4, -3, 3, 4, 5, 6], size=k)
+            boards[i, 56:64] = 0
+            boards[i, 0:8] = 0
+            boards[i, 60], boards[i, 56], boards[i, 63] = 1, 3, 3
+            boards[i, 4], boards[i, 0], boards[i, 7] = rng.choice([-1, 1]), rng.choice([-3, 3]), rng.choice([-3, 3])
+            if rng.rand() < 0.5:
+                boards[i, rng.randint(56, 64)] = rng.choice([0, 0, 5, -5, 4])
+        else:            # sliders heavy
+            boards[i, sq] = rng.choice([-4, -3, -2, 2, 3, 4, 1, -1], size=k)
+    players = rng.choice([-1, 1], size=n).astype(np.int8)
+    rights = rng.randint(0, 2, size=(n, 4)).astype(np.uint8)
+    return boards, players, rights
+
+
+def check_movegen_vs_oracle(movegen_fn, boards, players, rights, attack=False, stride=256):
+    res = movegen_fn(boards, players, rights, attack)
+    out, cnt = res[0], res[1]
+    exp, ecnt = orc.movegen_batch(boards, players, rights, attack, stride=stride, threads=os.cpu_count() or 1)
+    assert (np.asarray(cnt) == ecnt).all(), "count mismatch at %s" % np.nonzero(np.asarray(cnt) != ecnt)[0][:10]
+    mask = np.arange(stride)[None, :] < ecnt[:, None]
+    bad = ((np.asarray(out)[:, :stride] != exp) & mask).any(1)
+    assert not bad.any(), "list mismatch at %s" % np.nonzero(bad)[0][:10]
+    return int(ecnt.sum())
+
+
+def check_next_state_vs_oracle(next_state_fn, movegen_out, counts, boards, players, rights, rng):
+    """play one random legal move (and some illegal / empty-square ones) from every position"""
+    n = len(boards)
+    idx = (rng.rand(n) * np.maximum(counts, 1)).astype(np.int64)
+    actions = np.where(counts > 0, movegen_out[np.arange(n), idx], 4100).astype(np.int32)
+    weird = rng.rand(n) < 0.15
+    actions[weird] = rng.randint(0, 4100, size=int(weird.sum()))
+    got = next_state_fn(boards, players, rights, actions)
+    exp = orc.next_state_batch(boards, players, rights, actions)
+    names = ("boards", "rights", "checks", "reward", "status")
+    for g, e_, nm in zip(got, exp, names):
+        assert (np.asarray(g).reshape(np.asarray(e_).shape) == e_).all(), nm
+
+
+# ------------------------------------------------------------------ env level
+def _cmp_export(env, oracles, tag):
+    b, info, legal = env.export()
+    for i, o in enumerate(oracles):
+        v = o.view()
+        mine = dict(board=[int(x) for x in b[i]], cp=int(info[i, 0]), fl=[int(x) for x in info[i, 1:7]], done=int(info[i, 7]),
+                    mc=int(info[i, 8]), n=int(info[i, 9]), ep=int(info[i, 10]), st=int(info[i, 11]),
+                    legal=[int(x) for x in legal[i, : info[i, 9]]])
+        ref = dict(board=[int(x) for x in v["board"]], cp=v["current_player"], fl=[v[k] for k in "wk wq bk bq wchk bchk".split()],
+                   done=v["done"], mc=v["move_count"], n=v["n_legal"], ep=v["episode"], st=v["step_in_episode"],
+                   legal=[int(x) for x in v["legal"]])
+        assert mine == ref, "%s env %d: %s" % (tag, i, {k: (mine[k], ref[k]) for k in mine if mine[k] != ref[k]})
+
+
+def check_sampled_vs_oracle(env, opponent, color, seed, steps, auto_reset=True, boards=None, env_id_offset=0,
+                            compare_every=25, mode="sampled", rng=None):
+    """Run `steps` steps on the device env and replay the SAME draws through N oracle envs; compare every output of
+    every step, the full state every `compare_every` steps, and the statistics at the end."""
+    N = env.N
+    nt = 1 if boards is None else len(boards)
+    O = [orc.OracleEnv(None if boards is None else boards[(env_id_offset + i) % nt], color, opponent, seed, env_id_offset + i)
+         for i in range(N)]
+    _cmp_export(env, O, "reset")
+    tot = dict(steps=0, reward_sum=0, episodes=0)
+    for t in range(steps):
+        words = None
+        if mode == "sampled":
+            r, d, f, a, bot = env.step_sampled()
+        else:
+            words = rng.randint(0, 2 ** 32, size=N, dtype=np.uint64).astype(np.uint32)
+            r, d, f, a, bot = env.step_index(words)
+        for i, o in enumerate(O):
+            v = o.view()
+            u = orc.draw_u32(seed, env_id_offset + i, v["episode"], v["step_in_episode"], 0) if words is None else int(words[i])
+            act = o.pick(u)
+            rr, dd, raised = o.step(act)
+            v2 = o.view()
+            assert (rr, dd) == (int(r[i]), bool(d[i])), "step %d env %d: oracle %s device %s flags %d" % (t, i, (rr, dd), (r[i], d[i]), f[i])
+            if a is not None:
+                assert act == int(a[i]) and v2["last_bot_action"] == int(bot[i]), (t, i, act, a[i], v2["last_bot_action"], bot[i])
+            terminal = dd or v2["n_legal"] == 0
+            assert bool(f[i] & 32) == (terminal and auto_reset), (t, i, int(f[i]), terminal)
+            assert bool(f[i] & 16) == ((not dd) and v2["n_legal"] == 0), (t, i, int(f[i]))
+            tot["steps"] += 1
+            tot["reward_sum"] += rr
+            tot["episodes"] += int(terminal)
+            if terminal and auto_reset:
+                o.reset(v2["episode"] + 1)
+        if t % compare_every == 0 or t == steps - 1:
+            _cmp_export(env, O, "step %d" % t)
+    st = env.stats()
+    assert int(st[0]) == tot["steps"] and int(np.array(st[8:9], np.uint64).view(np.int64)[0]) == tot["reward_sum"] and int(st[2]) == tot["episodes"], (st, tot)
+    return st
+
+
+def check_trajectory_replay(make_env, traj):
+    """Replay a recorded self-play game (opponent none) of the REAL chess_v2.py through a 1-env device env."""
+    assert traj["opponent"] == "none"
+    env = make_env(np.array(traj["initial_board"], np.int8))
+
+    def cmp(s, where):
+        b, info, legal = env.export()
+        assert [int(x) for x in b[0]] == s["board"], where
+        assert [int(x) for x in info[0, 1:7]] == s["flags"], where
+        assert int(info[0, 8]) == s["move_count"], where
+        assert int(info[0, 0]) == (1 if s["current_player"] == "WHITE" else -1), where
+        assert [int(x) for x in legal[0, : info[0, 9]]] == s["legal"], where
+
+    cmp(traj["reset"], (traj["name"], "reset"))
+    for i, s in enumerate(traj["steps"]):
+        r, d, f, _, _ = env.step(np.array([s["action"]], np.int32))
+        assert (int(r[0]), bool(d[0])) == (int(s["reward"]), bool(s["done"])), (traj["name"], traj["seed"], i, r, d, s["reward"], s["done"])
+        cmp(s, (traj["name"], traj["seed"], i))
+    return len(traj["steps"])

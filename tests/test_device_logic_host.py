@@ -1,0 +1,127 @@
+"""The device rules (gym_chess_b200/csrc/chess_core.cuh, env_core.cuh) compiled with g++ (tests/host_emul) and
+checked against the fixtures and the oracle: a LOGIC test for boxes without a GPU.  The parity tests proper, through
+the C ABI on the GPU, are in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import parity_helpers as ph
+from tests.host_emul import emul
+
+
+class EmulAdapter:
+    def __init__(self, N, **kw):
+        self.N = N
+        self.e = emul.EmulEnv(N, **kw)
+
+    def step(self, a):
+        return self.e.step(a)
+
+    def step_index(self, u):
+        return self.e.step_index(u)
+
+    def step_sampled(self):
+        return self.e.step_sampled()
+
+    def export(self):
+        return self.e.export()
+
+    def stats(self):
+        return self.e.stats()
+
+
+def _mg(boards, players, rights, attack):
+    return emul.movegen(boards, players, rights, attack)
+
+
+def test_golden_positions(golden):
+    ph.check_positions(_mg, emul.update_state, golden["positions"])
+
+
+def test_movegen_selfplay_positions_vs_oracle():
+    b, p, r = ph.harvest_positions(n_envs=48, steps=330, seed=1)
+    assert len(b) > 5000
+    total = ph.check_movegen_vs_oracle(_mg, b, p, r, attack=False)
+    assert total > 100000
+    ph.check_movegen_vs_oracle(_mg, b, p, r, attack=True)
+    ph.check_movegen_vs_oracle(_mg, b, -p, r, attack=False)  # the side NOT to move as well
+
+
+def test_movegen_and_next_state_crafted_vs_oracle():
+    rng = np.random.RandomState(3)
+    b, p, r = ph.crafted_positions(rng, 6000)
+    ph.check_movegen_vs_oracle(_mg, b, p, r, attack=False)
+    ph.check_movegen_vs_oracle(_mg, b, p, r, attack=True)
+    out, cnt, _ = emul.movegen(b, p, r)
+    ph.check_next_state_vs_oracle(emul.next_state, out, cnt, b, p, r, rng)
+    hb, hp, hr = ph.harvest_positions(n_envs=16, steps=300, seed=5)
+    out, cnt, _ = emul.movegen(hb, hp, hr)
+    ph.check_next_state_vs_oracle(emul.next_state, out, cnt, hb, hp, hr, rng)
+
+
+def test_castle_only_lists():
+    rng = np.random.RandomState(9)
+    b, p, r = ph.crafted_positions(rng, 3000)
+    out, cnt, _ = emul.movegen(b, p, r, castles_only=True)
+    full, fcnt = orc.movegen_batch(b, p, r, False)
+    n_castles = 0
+    for i in range(len(b)):
+        exp = [int(a) for a in full[i, : fcnt[i]] if a >= 4096]
+        assert [int(a) for a in out[i, : cnt[i]]] == exp
+        n_castles += len(exp)
+    assert n_castles > 100
+
+
+def test_philox_matches_oracle():
+    for args in [(0, 0, 0, 0, 0), (123456789012345, 77, 3, 250, 1), (2 ** 64 - 1, 2 ** 32 - 1, 9, 1, 2)]:
+        assert emul.lib().emul_philox(*args) == orc.draw_u32(*args)
+
+
+@pytest.mark.parametrize("opponent,color", [("none", "WHITE"), ("random", "WHITE"), ("random", "BLACK")])
+def test_env_sampled_vs_oracle(opponent, color):
+    env = EmulAdapter(12, opponent=opponent, player_color=color, seed=21, auto_reset=True)
+    st = ph.check_sampled_vs_oracle(env, opponent, color, 21, 650)
+    assert st[2] > 0  # episodes ended (cap / mate / repetition / wedge all occur in 650 steps x 12 envs)
+
+
+def test_env_index_mode_and_offset_vs_oracle():
+    env = EmulAdapter(8, opponent="none", seed=5, auto_reset=True, env_id_offset=1000)
+    ph.check_sampled_vs_oracle(env, "none", "WHITE", 5, 200, env_id_offset=1000, mode="index", rng=np.random.RandomState(1))
+
+
+def test_env_edge_templates_vs_oracle(golden):
+    boards = []
+    for t in golden["trajectories"]:
+        if t["name"].startswith("selfplay_") and t["initial_board"] not in boards:
+            boards.append(t["initial_board"])
+    boards = np.array(boards, np.int8)
+    assert len(boards) >= 15
+    for opponent, color in (("none", "WHITE"), ("random", "WHITE"), ("random", "BLACK")):
+        env = EmulAdapter(len(boards) * 2, opponent=opponent, player_color=color, seed=8, auto_reset=True, initial_boards=boards)
+        ph.check_sampled_vs_oracle(env, opponent, color, 8, 260, boards=boards)
+
+
+def test_env_no_autoreset_wedge_and_done_behaviour():
+    # stalemate wedge: every further action is invalid (-10, done False); after mate: invalid (-10, True) first (Q16)
+    K, Q = 1, 2
+    b = np.zeros((8, 8), np.int8)
+    b[0, 0], b[3, 1], b[2, 2] = -K, Q, K
+    env = EmulAdapter(1, opponent="none", auto_reset=False, initial_boards=b)
+    r, d, f, _, _ = env.step([orc.str_to_action("b5b6")])
+    assert (r[0], d[0], f[0] & 16) == (-10, 0, 16)
+    r, d, f, _, _ = env.step([0])
+    assert (r[0], d[0], f[0] & 1) == (-10, 0, 1)
+    env = EmulAdapter(1, opponent="none", auto_reset=False, initial_boards=b)
+    r, d, f, _, _ = env.step([orc.str_to_action("b5b7")])
+    assert (r[0], d[0], f[0] & 2) == (90, 1, 2)
+    r, d, f, _, _ = env.step([0])
+    assert (r[0], d[0]) == (-10, 1)
+
+
+def test_env_replays_real_chess_v2_selfplay_games(golden):
+    n = 0
+    for t in golden["trajectories"]:
+        if t["opponent"] != "none":
+            continue
+        n += ph.check_trajectory_replay(lambda ib: EmulAdapter(1, opponent="none", auto_reset=False, initial_boards=ib), t)
+    assert n > 5000

@@ -1,0 +1,213 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libgymchess_b200.so), against the oracle
+and the golden fixtures.  Bit-exact: every comparison is integer equality."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import parity_helpers as ph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from gym_chess_b200 import BatchedChessEngine
+
+    return BatchedChessEngine()
+
+
+class GpuAdapter:
+    def __init__(self, N, **kw):
+        from gym_chess_b200 import BatchedChessEnv
+
+        self.N = N
+        self.env = BatchedChessEnv(N, **kw)
+
+    def _out(self, res):
+        r, d, f = res[:3]
+        a = res[3][-1].cpu().numpy() if len(res) > 3 else None
+        b = res[4][-1].cpu().numpy() if len(res) > 3 else None
+        return r.cpu().numpy(), d.cpu().numpy(), f.cpu().numpy(), a, b
+
+    def step(self, a):
+        return self.env.step_host(np.asarray(a, np.int32)) + (None, None)
+
+    def step_index(self, u):
+        return self.env.step_index_host(u) + (None, None)
+
+    def step_sampled(self):
+        return self._out(self.env.step_sampled(1, record=True))
+
+    def export(self):
+        return self.env.export_numpy()
+
+    def stats(self):
+        s = self.env.stats()
+        from gym_chess_b200.batched_env import STAT_NAMES
+        out = np.zeros(16, np.uint64)
+        for i, k in enumerate(STAT_NAMES):
+            out[i] = np.array(s[k], np.int64).astype(np.uint64) if k == "reward_sum" else s[k]
+        return out
+
+
+def _mg(eng):
+    return lambda b, p, r, attack: eng.get_possible_moves(b, p, r, attack=attack)
+
+
+def test_golden_positions(eng, golden):
+    ph.check_positions(_mg(eng), eng.update_state, golden["positions"])
+
+
+def test_chess_engine_shim_replays_reference_test_calls(golden):
+    from gym_chess_b200 import ChessEngine
+
+    assert ph.check_reference_test_calls(ChessEngine(), golden["reference_tests"]) >= 23
+
+
+def test_movegen_selfplay_positions_vs_oracle(eng):
+    b, p, r = ph.harvest_positions(n_envs=96, steps=330, seed=1)
+    assert len(b) > 10000
+    assert ph.check_movegen_vs_oracle(_mg(eng), b, p, r, attack=False) > 200000
+    ph.check_movegen_vs_oracle(_mg(eng), b, p, r, attack=True)
+    ph.check_movegen_vs_oracle(_mg(eng), b, -p, r, attack=False)
+
+
+def test_movegen_and_next_state_crafted_vs_oracle(eng):
+    rng = np.random.RandomState(3)
+    b, p, r = ph.crafted_positions(rng, 20000)
+    ph.check_movegen_vs_oracle(_mg(eng), b, p, r, attack=False)
+    ph.check_movegen_vs_oracle(_mg(eng), b, p, r, attack=True)
+    out, cnt, _ = eng.get_possible_moves(b, p, r)
+    ph.check_next_state_vs_oracle(eng.next_state, out, cnt, b, p, r, rng)
+    hb, hp, hr = ph.harvest_positions(n_envs=32, steps=300, seed=5)
+    out, cnt, _ = eng.get_possible_moves(hb, hp, hr)
+    ph.check_next_state_vs_oracle(eng.next_state, out, cnt, hb, hp, hr, rng)
+
+
+def test_castle_only_lists(eng):
+    rng = np.random.RandomState(9)
+    b, p, r = ph.crafted_positions(rng, 5000)
+    out, cnt, _ = eng.get_possible_moves(b, p, r, castles_only=True)
+    full, fcnt = orc.movegen_batch(b, p, r, False)
+    for i in range(len(b)):
+        assert [int(a) for a in out[i, : cnt[i]]] == [int(a) for a in full[i, : fcnt[i]] if a >= 4096]
+
+
+def test_empty_and_ragged_batches(eng):
+    out, cnt, chk = eng.get_possible_moves(np.zeros((0, 64), np.int8), np.zeros(0, np.int8), np.zeros((0, 4), np.uint8))
+    assert out.shape[0] == 0 and cnt.shape == (0,)
+    # an empty board, a board with one piece, n not a multiple of the block size
+    b = np.zeros((131, 64), np.int8)
+    b[1:, 27] = 2
+    out, cnt, _ = eng.get_possible_moves(b, 1, np.ones((131, 4), np.uint8))
+    assert cnt[0] == 0 and (cnt[1:] == 27).all()
+    # list overflow is reported through the count: 40 queens, stride 64
+    many = np.zeros((1, 64), np.int8)
+    many[0, ::2] = 2
+    out, cnt, _ = eng.get_possible_moves(many, 1, np.zeros((1, 4), np.uint8), stride=64)
+    exp, ecnt = orc.movegen_batch(many, 1, np.zeros((1, 4), np.uint8), stride=1024)
+    assert cnt[0] == ecnt[0] > 64 and (out[0] == exp[0, :64]).all()
+
+
+@pytest.mark.parametrize("opponent,color", [("none", "WHITE"), ("random", "WHITE"), ("random", "BLACK")])
+def test_env_sampled_vs_oracle(opponent, color):
+    env = GpuAdapter(160, opponent=opponent, player_color=color, seed=21, auto_reset=True)
+    st = ph.check_sampled_vs_oracle(env, opponent, color, 21, 700)
+    assert st[2] > 0
+
+
+def test_env_index_mode_and_offset_vs_oracle():
+    env = GpuAdapter(40, opponent="none", seed=5, auto_reset=True, env_id_offset=1000)
+    ph.check_sampled_vs_oracle(env, "none", "WHITE", 5, 250, env_id_offset=1000, mode="index", rng=np.random.RandomState(1))
+
+
+def test_env_edge_templates_vs_oracle(golden):
+    boards = []
+    for t in golden["trajectories"]:
+        if t["name"].startswith("selfplay_") and t["initial_board"] not in boards:
+            boards.append(t["initial_board"])
+    boards = np.array(boards, np.int8)
+    for opponent, color in (("none", "WHITE"), ("random", "WHITE"), ("random", "BLACK")):
+        env = GpuAdapter(len(boards) * 3, opponent=opponent, player_color=color, seed=8, auto_reset=True, initial_boards=boards)
+        ph.check_sampled_vs_oracle(env, opponent, color, 8, 300, boards=boards)
+
+
+def test_env_replays_real_chess_v2_selfplay_games(golden):
+    n = 0
+    for t in golden["trajectories"]:
+        if t["opponent"] != "none":
+            continue
+        n += ph.check_trajectory_replay(lambda ib: GpuAdapter(1, opponent="none", auto_reset=False, initial_boards=ib), t)
+    assert n > 5000
+
+
+def test_env_sharding_is_invisible():
+    """global env ids make the draws independent of the sharding: 2 shards of 64 == 1 env set of 128"""
+    from gym_chess_b200 import BatchedChessEnv
+
+    whole = BatchedChessEnv(128, opponent="none", seed=3)
+    a = BatchedChessEnv(64, opponent="none", seed=3, env_id_offset=0)
+    b = BatchedChessEnv(64, opponent="none", seed=3, env_id_offset=64)
+    for _ in range(400):
+        rw, dw, _ = whole.step_sampled()
+        ra, da, _ = a.step_sampled()
+        rb, db, _ = b.step_sampled()
+    bw, iw, lw = whole.export_numpy()
+    ba, ia, la = a.export_numpy()
+    bb, ib, lb = b.export_numpy()
+    assert (bw == np.concatenate([ba, bb])).all() and (iw == np.concatenate([ia, ib])).all()
+    sw, sa, sb = whole.stats(), a.stats(), b.stats()
+    assert all(sw[k] == sa[k] + sb[k] for k in sw)
+
+
+def test_full_size_properties():
+    """size-independent properties at BASELINE.json's sizes (1M positions / 65,536 envs): the legal list of a
+    resident env equals a fresh movegen of its exported position; counts agree; statistics add up."""
+    import ctypes as C
+    import torch
+    from gym_chess_b200 import BatchedChessEnv, _lib
+    from gym_chess_b200._lib import Positions, check
+
+    N = 1 << 20
+    env = BatchedChessEnv(N, opponent="none", seed=2)
+    env.step_sampled(64)
+    boards = env.observe().reshape(N, 64)
+    info = env.info_tensor()
+    legal, n_legal = env.legal_actions()
+    dev = boards.device
+    players = info[:, 0].to(torch.int8).contiguous()
+    rights = info[:, 1:5].to(torch.uint8).contiguous()
+    bb01 = torch.empty((N, 2), dtype=torch.int64, device=dev)
+    bb23 = torch.empty((N, 2), dtype=torch.int64, device=dev)
+    pl = torch.empty(N, dtype=torch.uint8, device=dev)
+    rt = torch.empty(N, dtype=torch.uint8, device=dev)
+    pos = Positions(bb01.data_ptr(), bb23.data_ptr(), pl.data_ptr(), rt.data_ptr())
+    L = _lib.lib()
+    check(L.gcb_pack(N, boards.data_ptr(), players.data_ptr(), rights.data_ptr(), pos, None))
+    out = torch.zeros((N, 144), dtype=torch.int16, device=dev)
+    cnt = torch.empty(N, dtype=torch.int32, device=dev)
+    check(L.gcb_get_possible_moves(N, pos, 0, 0, out.data_ptr(), 144, cnt.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    assert torch.equal(cnt, n_legal)
+    mask = torch.arange(144, device=dev)[None, :] < cnt[:, None]
+    assert torch.equal(torch.where(mask, out, 0), torch.where(mask, legal, 0))
+    # pack -> unpack round trip
+    back = torch.empty_like(boards)
+    check(L.gcb_unpack(N, pos, back.data_ptr(), None, None, None))
+    assert torch.equal(back, boards)
+    st = env.stats()
+    assert st["steps"] == N * 64 and st["episodes"] == st["mates"] + st["repetitions"] + st["caps"] + st["wedged"]
+    assert st["hist_overflow"] == 0 and st["list_overflow"] == 0
+    # a sample of the 1M positions against the oracle
+    idx = torch.randint(0, N, (4096,), device=dev)
+    hb, hp, hr = boards[idx].cpu().numpy(), players[idx].cpu().numpy(), rights[idx].cpu().numpy()
+    exp, ecnt = orc.movegen_batch(hb, hp, hr, False, stride=144, threads=8)
+    assert (cnt[idx].cpu().numpy() == ecnt).all()
+    m = np.arange(144)[None, :] < ecnt[:, None]
+    assert ((out[idx].cpu().numpy().view(np.uint16) == exp) | ~m).all()
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()
