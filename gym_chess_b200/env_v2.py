@@ -1,0 +1,316 @@
+"""`ChessEnvV2` -- single-env, gym-style compat class with the reference's surface
+(gym_chess/envs/chess_v2.py:132-602): constructor, reset/step/render/render_moves, `state`, `possible_moves`,
+`possible_actions`, `info`, flags, codec helpers, `get_possible_moves(state, player, attack)`, `get_castle_moves`.
+
+It is a thin host-side view of a `BatchedChessEnv` with one env: `step()` is one launch of the fused CUDA step
+kernel, `get_possible_moves(state=...)` one launch of the batched movegen kernel.  gym itself is not needed (and
+not installed in this image); `observation_space` / `action_space` are minimal stand-ins with `contains`/`sample`.
+"""
+import sys
+from io import StringIO
+
+import numpy as np
+
+from . import codec
+from .batched_env import F_CAP, F_INVALID, BatchedChessEnv
+from .codec import (CASTLE_KING_SIDE_BLACK, CASTLE_KING_SIDE_WHITE, CASTLE_MOVES, CASTLE_QUEEN_SIDE_BLACK,
+                    CASTLE_QUEEN_SIDE_WHITE, RESIGN)
+from .engine import ChessEngine
+
+WHITE, BLACK = "WHITE", "BLACK"
+KING_ID, QUEEN_ID, ROOK_ID, BISHOP_ID, KNIGHT_ID, PAWN_ID = 1, 2, 3, 4, 5, 6
+DEFAULT_BOARD = [
+    [-3, -5, -4, -2, -1, -4, -5, -3],
+    [-6] * 8, [0] * 8, [0] * 8, [0] * 8, [0] * 8,
+    [6] * 8,
+    [3, 5, 4, 2, 1, 4, 5, 3],
+]
+# chess_v2.py:64-84
+ID_TO_ICON = {-6: "♙", -5: "♘", -4: "♗", -3: "♖", -2: "♕", -1: "♔", 0: ".", 1: "♚", 2: "♛", 3: "♜", 4: "♝", 5: "♞", 6: "♟"}
+ID_TO_DESC = {-6: "", -5: "N", -4: "B", -3: "R", -2: "Q", -1: "K", 0: "", 1: "K", 2: "Q", 3: "R", 4: "B", 5: "N", 6: ""}
+
+
+class _Discrete:
+    def __init__(self, n):
+        self.n = n
+
+    def contains(self, x):
+        try:
+            return 0 <= int(x) < self.n and int(x) == x
+        except (TypeError, ValueError):
+            return False
+
+    def sample(self):
+        return int(np.random.randint(self.n))
+
+
+class _Box:
+    def __init__(self, low, high, shape):
+        self.low, self.high, self.shape = low, high, shape
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == tuple(self.shape) and bool((x >= self.low).all() and (x <= self.high).all())
+
+
+def highlight(string, background="white", color="gray"):
+    # gym.utils.colorize stand-in (chess_v2.py:110-111): ANSI colours
+    colors = dict(gray=30, red=31, green=32, yellow=33, blue=34, magenta=35, cyan=36, white=37)
+    return "\x1b[%d;%dm%s\x1b[0m" % (colors[color], colors[background] + 10, string)
+
+
+class ChessEnvV2:
+    def __init__(self, player_color=WHITE, opponent="random", log=True, initial_board=DEFAULT_BOARD, seed=0, device=0):
+        self.moves_max = 149
+        self.log = log
+        self.initial_board = initial_board
+        self.engine = ChessEngine()
+        self.observation_space = _Box(-6, 6, (8, 8))
+        self.action_space = _Discrete(64 * 64 + 4 + 1)
+        self.player = player_color
+        self.player_2 = self.get_other_player(player_color)
+        self.opponent = opponent
+        self._seed, self._device = seed, device
+        if isinstance(opponent, str):
+            if opponent not in ("random", "none"):
+                raise ValueError(f"Unrecognized opponent policy {opponent}")  # gym.error.Error in the reference
+            mode = opponent
+        else:
+            # a callable opponent(env) -> move (chess_v2.py:178-179): the env runs in self-play mode on the device and
+            # the callable's ply is a second kernel step issued from the host
+            if player_color == BLACK:
+                raise NotImplementedError("callable opponents are supported for player_color='WHITE' only")
+            mode = "none"
+        if player_color == BLACK and mode == "none":
+            raise TypeError("'NoneType' object is not callable")  # what the reference does (Q23, chess_v2.py:208-209)
+        self._env = BatchedChessEnv(1, opponent=mode, player_color=player_color, seed=seed, device=device, auto_reset=False,
+                                    initial_boards=np.asarray(initial_board, np.int8))
+        self.opponent_policy = opponent if callable(opponent) else (None if opponent == "none" else "random")
+        self._first = True
+        self.reset()
+
+    def seed(self, seed=None):
+        self._seed = 0 if seed is None else seed
+        return [seed]
+
+    # ------------------------------------------------------------------ state mirror
+    def _pull(self):
+        boards, info, legal = self._env.export_numpy()
+        r = info[0]
+        self.board = boards[0].reshape(8, 8).tolist()
+        self.current_player = WHITE if r[0] > 0 else BLACK
+        self.white_king_castle_is_possible, self.white_queen_castle_is_possible = bool(r[1]), bool(r[2])
+        self.black_king_castle_is_possible, self.black_queen_castle_is_possible = bool(r[3]), bool(r[4])
+        self.white_king_is_checked, self.black_king_is_checked = bool(r[5]), bool(r[6])
+        self.done, self.move_count = bool(r[7]), int(r[8])
+        self._possible_moves = [codec.ACTION_TO_MOVE[a] for a in legal[0, : r[9]]]
+        self._possible_actions = [int(a) for a in legal[0, : r[9]]]
+
+    def reset(self):
+        """chess_v2.py:183-217"""
+        if not self._first:
+            self._env.reset()
+        self._first = False
+        self._pull()
+        self.white_king_on_the_board = self.piece_is_on_board(self.board, KING_ID)    # set here only (Q8)
+        self.black_king_on_the_board = self.piece_is_on_board(self.board, -KING_ID)
+        if self.player == BLACK:  # the board the kings were looked up on is the initial one (chess_v2.py:201-202)
+            ib = np.asarray(self.initial_board).tolist()
+            self.white_king_on_the_board = self.piece_is_on_board(ib, KING_ID)
+            self.black_king_on_the_board = self.piece_is_on_board(ib, -KING_ID)
+        return self.state
+
+    def step(self, action):
+        """chess_v2.py:219-294"""
+        assert self.action_space.contains(action), "ACTION ERROR {}".format(action)
+        was_done, capped = self.done, self.move_count > self.moves_max
+        r, d, f = self._env.step_host(np.array([action], np.int32))
+        reward, done, flags = int(r[0]), bool(d[0]), int(f[0])
+        if not (flags & F_INVALID) and (was_done or (flags & F_CAP) or capped):
+            reward = 0.0  # the two float literals of chess_v2.py:248,255
+        if self.log and not (flags & F_INVALID) and not was_done and not capped:
+            move = self.action_to_move(action)
+            print(" " * 10, ">" * 10, self.current_player)
+            self.render_moves([move], mode="human")
+        self._pull()
+        if callable(self.opponent_policy) and not (flags & F_INVALID) and not was_done and not capped and not done:
+            # bot ply from the host callable (chess_v2.py:277-288)
+            opp_move = self.opponent_policy(self)
+            opp_action = self.move_to_action(opp_move)
+            if opp_action is None or opp_action >= 4100:
+                raise TypeError("'>=' not supported between instances of 'NoneType' and 'int'")  # Q9
+            r2, d2, f2 = self._env.step_host(np.array([opp_action], np.int32))
+            self._pull()
+            # second kernel step returned -10 + capture (+100 if it mated the agent): fold into the agent's reward
+            mated = bool(int(f2[0]) & 2)
+            opp_reward = int(r2[0]) + 10 - (100 if mated else 0)
+            reward = reward - opp_reward + (-100 if mated else 0)
+            done = bool(d2[0])
+        return self.state, reward, done, self.info
+
+    # ------------------------------------------------------------------ properties (chess_v2.py:301-391)
+    @property
+    def state(self):
+        return dict(
+            board=self.board, current_player=self.current_player,
+            white_king_castle_is_possible=self.white_king_castle_is_possible,
+            white_queen_castle_is_possible=self.white_queen_castle_is_possible,
+            black_king_castle_is_possible=self.black_king_castle_is_possible,
+            black_queen_castle_is_possible=self.black_queen_castle_is_possible,
+            white_king_is_checked=self.white_king_is_checked, black_king_is_checked=self.black_king_is_checked)
+
+    @property
+    def possible_moves(self):
+        return self._possible_moves
+
+    @property
+    def possible_actions(self):
+        return list(self._possible_actions)
+
+    @property
+    def info(self):
+        return dict(
+            move_count=self.move_count, current_player=self.current_player, possible_moves=self.possible_moves,
+            white_king_castle_is_possible=self.white_king_castle_is_possible,
+            white_queen_castle_is_possible=self.white_queen_castle_is_possible,
+            black_king_castle_is_possible=self.black_king_castle_is_possible,
+            black_queen_castle_is_possible=self.black_queen_castle_is_possible,
+            white_king_is_checked=self.white_king_is_checked, black_king_is_checked=self.black_king_is_checked,
+            white_king_on_the_board=self.white_king_on_the_board, black_king_on_the_board=self.black_king_on_the_board)
+
+    @property
+    def opponent_player(self):
+        return BLACK if self.current_player == WHITE else WHITE
+
+    @property
+    def current_player_is_white(self):
+        return self.current_player == WHITE
+
+    @property
+    def current_player_is_black(self):
+        return not self.current_player_is_white
+
+    def king_is_checked(self, player):
+        return self.white_king_is_checked if player == WHITE else self.black_king_is_checked
+
+    def piece_is_on_board(self, board, piece_id):
+        return any(sq == piece_id for row in board for sq in row)
+
+    def player_can_castle(self, player):
+        if player == WHITE:
+            return self.white_king_castle_is_possible and self.white_queen_castle_is_possible
+        return self.black_king_castle_is_possible and self.black_queen_castle_is_possible
+
+    def get_other_player(self, player):
+        return BLACK if player == WHITE else WHITE
+
+    # ------------------------------------------------------------------ engine queries (chess_v2.py:414-420, 569-593)
+    def next_state(self, state, player, move):
+        if state is None:
+            state = self.state
+        return self.engine.next_state(state, player, self.move_to_str_code(move))
+
+    def get_possible_actions(self):
+        return [self.move_to_action(m) for m in self.get_possible_moves(player=self.current_player)]
+
+    def get_possible_moves(self, state=None, player=None, attack=False):
+        state = self.state if state is None else state
+        player = self.current_player if player is None else player
+        return [self.rust_move_to_coords(m) for m in self.engine.get_possible_moves(state, player, attack)]
+
+    def get_castle_moves(self, state=None, player=None):
+        state = self.state if state is None else state
+        player = self.current_player if player is None else player
+        return [self.rust_move_to_coords(m) for m in self.engine.get_castle_moves(state, player)]
+
+    def is_resignation(self, action):
+        return False
+
+    def encode_board(self):
+        mapping = "0ABCDEFfedcba"
+        return "".join(mapping[val] for row in self.board for val in row)
+
+    # ------------------------------------------------------------------ codec (chess_v2.py:492-567)
+    def move_to_action(self, move):
+        return codec.move_to_action(move)
+
+    def action_to_move(self, action):
+        return codec.action_to_move(action)
+
+    def action_to_move_str(self, action):
+        # the reference raises NameError here (Q17, chess_v2.py:532); return the intended string instead
+        return codec.ACTION_TO_STR[int(action)]
+
+    def move_to_str_code(self, move):
+        return codec.move_to_str_code(move)
+
+    def rust_move_to_coords(self, move):
+        return codec.str_code_to_move(move)
+
+    def move_to_string(self, move):
+        if move in (CASTLE_KING_SIDE_WHITE, CASTLE_KING_SIDE_BLACK):
+            return "O-O"
+        if move in (CASTLE_QUEEN_SIDE_WHITE, CASTLE_QUEEN_SIDE_BLACK):
+            return "O-O-O"
+        _from, _to = move
+        rows, cols = list(reversed("12345678")), "abcdefgh"
+        desc = ID_TO_DESC[self.board[_from[0]][_from[1]]]
+        capture = self.board[_to[0]][_to[1]] != 0
+        return f"{desc}{cols[_from[1]]}{rows[_from[0]]}{'x' if capture else ''}{cols[_to[1]]}{rows[_to[0]]}"
+
+    # ------------------------------------------------------------------ render (chess_v2.py:422-490)
+    def board_to_grid(self):
+        return [[f" {ID_TO_ICON[sq]} " for sq in row] for row in self.board]
+
+    def render_grid(self, grid, mode="human"):
+        outfile = sys.stdout if mode == "human" else StringIO()
+        outfile.write("    " + "-" * 25 + "\n")
+        rows = "87654321"
+        for i, row in enumerate(grid):
+            outfile.write(f" {rows[i]} | " + "".join(row) + "|\n")
+        outfile.write("    " + "-" * 25 + "\n      a  b  c  d  e  f  g  h \n")
+        if mode == "string":
+            return outfile.getvalue()
+        if mode != "human":
+            return outfile
+
+    def render(self, mode="human"):
+        return self.render_grid(self.board_to_grid(), mode=mode)
+
+    def render_moves(self, moves, mode="human"):
+        grid = self.board_to_grid()
+        for move in moves:
+            if type(move) is str and move in CASTLE_MOVES:
+                row = 7 if move in (CASTLE_QUEEN_SIDE_WHITE, CASTLE_KING_SIDE_WHITE) else 0
+                if move in (CASTLE_QUEEN_SIDE_WHITE, CASTLE_QUEEN_SIDE_BLACK):
+                    grid[row][0] = highlight(grid[row][0], background="white")
+                    grid[row][1] = highlight(" >>", background="green")
+                    grid[row][2] = highlight("> <", background="green")
+                    grid[row][3] = highlight("<< ", background="green")
+                    grid[row][4] = highlight(grid[row][4], background="white")
+                else:
+                    grid[row][4] = highlight(grid[row][4], background="white")
+                    grid[row][5] = highlight(" >>", background="green")
+                    grid[row][6] = highlight("<< ", background="green")
+                    grid[row][7] = highlight(grid[row][7], background="white")
+                continue
+            (x0, y0), (x1, y1) = move
+            if len(grid[x0][y0]) < 4:
+                grid[x0][y0] = highlight(grid[x0][y0], background="white")
+            if len(grid[x1][y1]) < 4:
+                grid[x1][y1] = highlight(grid[x1][y1], background="red" if self.board[x1][y1] else "green")
+        return self.render_grid(grid, mode=mode)
+
+    def close(self):
+        self._env.close()
+
+
+# the two modes the reference registers with gym (gym_chess/__init__.py:32-42)
+REGISTRY = {"ChessVsRandomBot-v2": dict(opponent="random"), "ChessVsSelf-v2": dict(opponent="none")}
+
+
+def make(env_id, **kwargs):
+    """gym.make stand-in for the v2 ids"""
+    kw = dict(REGISTRY[env_id])
+    kw.update(kwargs)
+    return ChessEnvV2(**kw)
