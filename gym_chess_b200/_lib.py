@@ -52,7 +52,7 @@ class EnvConfig(C.Structure):
         ("opponent", C.c_int32),
         ("agent_black", C.c_int32),
         ("auto_reset", C.c_int32),
-        ("legal_stride", C.c_int32),
+        ("piece_slots", C.c_int32),
         ("history_cap", C.c_int32),
         ("moves_max", C.c_int32),
         ("n_templates", C.c_int32),
@@ -86,7 +86,8 @@ SIGNATURES = {
     "gcb_env_step_index_host": (i32, [vp, vp, vp, vp, vp]),
     "gcb_env_export": (i32, [vp, vp, vp, vp]),
     "gcb_env_legal_mask": (i32, [vp, vp, vp]),
-    "gcb_env_legal_ptr": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_int32)]),
+    "gcb_env_legal_actions": (i32, [vp, vp, i32, vp, vp]),
+    "gcb_env_piece_slots": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_int32)]),
     "gcb_env_positions": (i32, [vp, C.POINTER(Positions)]),
     "gcb_env_stats": (i32, [vp, vp, vp]),
     "gcb_env_stats_reset": (i32, [vp, vp]),

@@ -19,10 +19,10 @@ WHITE, BLACK = "WHITE", "BLACK"
 
 F_INVALID, F_MATE, F_REPETITION, F_CAP, F_WEDGED, F_RESET = 1, 2, 4, 8, 16, 32
 STAT_NAMES = ("steps", "plies", "episodes", "mates", "repetitions", "caps", "wedged", "invalid", "reward_sum",
-              "legal_sum", "in_check", "hist_overflow", "list_overflow", "hist_scanned")
+              "legal_sum", "in_check", "hist_overflow", "slot_overflow", "hist_scanned", "hist_window")
 INFO_NAMES = ("current_player", "white_king_castle_is_possible", "white_queen_castle_is_possible",
               "black_king_castle_is_possible", "black_queen_castle_is_possible", "white_king_is_checked",
-              "black_king_is_checked", "done", "move_count", "n_legal", "episode", "step_in_episode", "hist_len")
+              "black_king_is_checked", "done", "move_count", "n_legal", "episode", "step_in_episode", "hist_len", "castles")
 
 
 class _DevArray:
@@ -38,7 +38,7 @@ def _stream_ptr():
 
 class BatchedChessEnv:
     def __init__(self, num_envs, opponent="random", player_color=WHITE, seed=0, device=0, auto_reset=True,
-                 initial_boards=None, env_id_offset=0, legal_stride=144, history_cap=512, moves_max=149):
+                 initial_boards=None, env_id_offset=0, legal_stride=144, history_cap=512, moves_max=149, piece_slots=0):
         """
         opponent      "random" (the bot replies inside step, chess_v2.py:277-288) or "none" (self-play)
         player_color  "WHITE" | "BLACK" (BLACK needs opponent="random", like the reference: Q23)
@@ -56,7 +56,7 @@ class BatchedChessEnv:
         cfg = EnvConfig()
         cfg.num_envs, cfg.env_id_offset, cfg.seed = self.num_envs, self.env_id_offset, self.seed
         cfg.opponent, cfg.agent_black, cfg.auto_reset = int(opponent == "random"), int(player_color == BLACK), int(auto_reset)
-        cfg.legal_stride, cfg.history_cap, cfg.moves_max = legal_stride, history_cap, moves_max
+        cfg.piece_slots, cfg.history_cap, cfg.moves_max = piece_slots, history_cap, moves_max
         self._templates = None
         if initial_boards is not None:
             tb = np.ascontiguousarray(np.asarray(initial_boards, dtype=np.int8).reshape(-1, 64))
@@ -158,13 +158,23 @@ class BatchedChessEnv:
             check(_lib.lib().gcb_env_export(self._h, None, C.c_void_p(t.data_ptr()), _stream_ptr()))
         return t
 
-    def legal_actions(self):
-        """(legal uint16-as-int16 [N, stride] zero-copy view, n_legal int32 [N]) = possible_actions, reference order."""
-        ptr, stride = C.c_void_p(), C.c_int32()
-        check(_lib.lib().gcb_env_legal_ptr(self._h, C.byref(ptr), C.byref(stride)))
+    def legal_actions(self, stride=None):
+        """(legal int16-viewed uint16 [N, stride], n_legal int32 [N]) = possible_actions in the reference's order,
+        decoded on access from the resident piece slots (like the reference's property, chess_v2.py:333-335)."""
+        stride = int(stride or self.legal_stride)
         with torch.cuda.device(self.device):
-            view = torch.as_tensor(_DevArray(ptr.value, (self.num_envs, stride.value), "<i2"), device=self.device)
-        return view, self.info_tensor()[:, 9].contiguous()
+            out = torch.zeros((self.num_envs, stride), dtype=torch.int16, device=self.device)
+            cnt = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            check(_lib.lib().gcb_env_legal_actions(self._h, C.c_void_p(out.data_ptr()), stride, C.c_void_p(cnt.data_ptr()),
+                                                   _stream_ptr()))
+        return out, cnt
+
+    def piece_slots(self):
+        """zero-copy int64 [S, N] view of the resident legal set (slot r = legal targets of the r-th own piece)."""
+        ptr, n = C.c_void_p(), C.c_int32()
+        check(_lib.lib().gcb_env_piece_slots(self._h, C.byref(ptr), C.byref(n)))
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_DevArray(ptr.value, (n.value, self.num_envs), "<i8"), device=self.device)
 
     def legal_mask(self):
         """uint8 [N, 4101] mask of possible_actions."""

@@ -50,6 +50,13 @@ GCB_HD int gcb_msb(u64 x) {  // index of the highest set bit, x != 0
     return 63 - __builtin_clzll(x);
 #endif
 }
+GCB_HD int gcb_popc(u64 x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
 GCB_HD u32 gcb_umulhi(u32 a, u32 b) {
 #if defined(__CUDA_ARCH__)
     return __umulhi(a, b);
@@ -228,260 +235,395 @@ GCB_HD u32 mask_rights(const Board& b, u32 rights) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Ordered legal move generation (lib.rs:460-610).  Emit must provide  void push(int action).
-// Returns nothing; the caller reads the count from its Emit.  Outputs:
-//   *in_check : mover's (reference) king square is in the opponent attack map
-// ATTACK = true reproduces get_possible_moves(attack=True): defended squares included, pawn
-// diagonals only, no legality filter, no castles, king sees an empty attack map.
+// Legal move generation (lib.rs:460-610), B200 formulation.
+//
+// The reference simulates every candidate move and recomputes the whole opponent attack map
+// (move_leaves_king_checked, lib.rs:612-626).  Here the legal set of a position is produced as ONE
+// 64-bit target set per own piece ("piece slots", own pieces in ascending square order = the
+// reference's row-major scan, lib.rs:510-511) plus two castle bits:
+//   gen_prepare()  -- per position: opponent attack map, checkers of the (reference-rule, Q15) king
+//                     square, the check mask (capture the single checker / block its ray) and the
+//                     set of pinned pieces with their pin rays.  Exactly equivalent to simulate-and-
+//                     recompute for NON-king moves because there is no en passant and a non-king move
+//                     changes the attack on the king square only through (a) capturing an attacker,
+//                     (b) blocking a ray, (c) vacating a ray through the king square.
+//   gen_targets()  -- per own piece, TYPE-MAJOR (all rooks, then bishops, queens, knights, kings,
+//                     pawns) so that the 32 envs of a warp execute the same code; the slot index is
+//                     the piece's rank among the own pieces, so slots come out in reference order.
+//   emit_piece_moves() / nth_target() -- the reference's per-piece move ORDER (direction order of
+//                     lib.rs:797-806, 824-851, 891-900, 935-959; rays by increasing distance) is a
+//                     pure function of (piece type, colour, square, target set): the ordered list
+//                     is decoded from the slots only where a caller asks for it.
+// ATTACK lists (get_possible_moves(attack=True)) keep a direct ordered generator (gen_attack_moves).
 // ---------------------------------------------------------------------------------------------
-struct KingSafety {
-    u64 occ, eRQ, eBQ, leapers;  // leapers = enemy N/K/P that attack the king square right now
-    u64 klines;                  // queen lines through the king square (incl. it)
+GCB_HD u64 sq_bit_safe(int sq) { return (unsigned)sq < 64u ? (1ULL << sq) : 0ULL; }
+
+// the queen line through both squares (0 when they are not aligned); a != b
+GCB_HD u64 line_through(int a, int b) {
+    const int ra = a >> 3, ca = a & 7, rb = b >> 3, cb = b & 7;
+    u64 m = 0;
+    if (ca == cb) m = mask_file(a);
+    else if (ra == rb) m = mask_rank(a);
+    else if (ra - ca == rb - cb) m = mask_diag(a);
+    else if (ra + ca == rb + cb) m = mask_anti(a);
+    return m;
+}
+// squares strictly between two aligned squares (0 when not aligned or adjacent)
+GCB_HD u64 between_excl(int a, int b) {
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    const u64 span = (1ULL << hi) - (2ULL << lo);  // bits lo+1 .. hi-1
+    return span & line_through(a, b);
+}
+
+struct GenCtx {
+    u64 occ, own, enemy;
+    u64 kings, queens, rooks, bishops, knights, pawns;
+    u64 eatt;     // opponent attack map on the CURRENT board, own king left on it (lib.rs:466-470; Q6)
+    u64 satt;     // attack map of the side to move, accumulated by gen_targets (check flag of the other side)
+    u64 cm;       // targets that resolve the check for a non-king piece (all ones when not in check / no king)
+    u64 pinned;   // own pieces whose removal opens a slider line onto the king square
+    u64 pinrays;  // union of (between(king, pinner) | pinner)
     int ksq;
     bool has_king, in_check;
+    int white;
 };
 
-// Would the mover's king square be attacked after moving a NON-king piece from->to ?
-// Equals lib.rs:612-626 (simulate with next_state, recompute the opponent attack map, look the
-// king square up): attack sets are symmetric, the captured piece (if any) stops attacking.
-GCB_HD bool king_attacked_after(const KingSafety& ks, u64 fbit, u64 tbit) {
-    u64 keep = ~tbit;
-    if (ks.leapers & keep) return true;
-    u64 occ2 = (ks.occ & ~fbit) | tbit;
-    if (rook_att(ks.ksq, occ2) & ks.eRQ & keep) return true;
-    if (bishop_att(ks.ksq, occ2) & ks.eBQ & keep) return true;
-    return false;
-}
+GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
+    g.white = white_to_move;
+    g.occ = bb_occ(b);
+    g.own = white_to_move ? b.w : (g.occ & ~b.w);
+    g.enemy = g.occ & ~g.own;
+    g.kings = bb_kings(b), g.queens = bb_queens(b), g.rooks = bb_rooks(b), g.bishops = bb_bishops(b);
+    g.knights = bb_knights(b), g.pawns = bb_pawns(b);
+    const u64 occ = g.occ, enemy = g.enemy;
+    const u64 ekings = g.kings & enemy;
+    const u64 eRQ = (g.rooks | g.queens) & enemy, eBQ = (g.bishops | g.queens) & enemy;
 
-GCB_HD bool nonking_move_legal(const KingSafety& ks, u64 fbit, u64 tbit) {
-    if (!ks.has_king) return true;  // lib.rs:655-658: no king -> nothing is filtered
-    // exact fast path: king not attacked now and the moved piece is not on a line through the
-    // king square -> vacating `from` cannot open a slider line, placing on `to` can only block,
-    // a capture only removes attackers.
-    if (!ks.in_check && !(ks.klines & fbit)) return true;
-    return !king_attacked_after(ks, fbit, tbit);
-}
+    // opponent attack map (lib.rs:669-677): pawns minus squares holding the attacker's OWN king (Q14)
+    u64 eatt = pawn_set_att(g.pawns & enemy, !white_to_move) & ~ekings;
+    eatt |= knight_set_att(g.knights & enemy) | king_set_att(ekings);
+    for (u64 s = eRQ; s; s &= s - 1) eatt |= rook_att(gcb_lsb(s), occ);
+    for (u64 s = eBQ; s; s &= s - 1) eatt |= bishop_att(gcb_lsb(s), occ);
+    g.eatt = eatt;
 
-template <bool ATTACK, class Emit>
-GCB_HD void emit_targets_desc(Emit& em, const KingSafety& ks, int from, u64 fbit, u64 m) {
-    while (m) {  // nearest first on a ray that runs towards lower square indices
-        int to = gcb_msb(m);
-        u64 tbit = 1ULL << to;
-        m ^= tbit;
-        if (ATTACK || nonking_move_legal(ks, fbit, tbit)) em.push(from * 64 + to);
+    g.satt = 0, g.cm = ~0ULL, g.pinned = 0, g.pinrays = 0, g.ksq = 0, g.in_check = false;
+    const u64 ownk = g.kings & g.own;
+    g.has_king = ownk != 0;
+    if (!g.has_king) return;  // lib.rs:655-658: no king -> nothing is filtered
+    const int ksq = ref_king_square(ownk);
+    const u64 kbit = 1ULL << ksq;
+    g.ksq = ksq;
+    const u64 rk = rook_att(ksq, occ), bk = bishop_att(ksq, occ);
+    // pieces that attack the king square right now (attack sets are symmetric; an enemy pawn attacks ksq
+    // iff it stands where a pawn of the MOVER's colour on ksq would attack; enemy kings count, Q22)
+    const u64 chk = (knight_set_att(kbit) & g.knights & enemy) | (king_set_att(kbit) & ekings) |
+                    (pawn_set_att(kbit, white_to_move) & g.pawns & enemy) | (rk & eRQ) | (bk & eBQ);
+    g.in_check = chk != 0;
+    if (chk) {
+        if (chk & (chk - 1)) g.cm = 0;  // two or more attackers: no non-king move can remove both
+        else g.cm = chk | between_excl(ksq, gcb_lsb(chk));
+    }
+    // pins: drop the own pieces the king "sees" first on each ray and look again
+    const u64 xr = rook_att(ksq, occ ^ (rk & g.own)) & ~rk & eRQ;
+    const u64 xb = bishop_att(ksq, occ ^ (bk & g.own)) & ~bk & eBQ;
+    for (u64 p = xr | xb; p; p &= p - 1) {
+        const int psq = gcb_lsb(p);
+        const u64 btw = between_excl(ksq, psq);
+        g.pinned |= btw & g.own;
+        g.pinrays |= btw | (1ULL << psq);
     }
 }
-template <bool ATTACK, class Emit>
-GCB_HD void emit_targets_asc(Emit& em, const KingSafety& ks, int from, u64 fbit, u64 m) {
-    while (m) {  // nearest first on a ray that runs towards higher square indices
-        int to = gcb_lsb(m);
-        u64 tbit = 1ULL << to;
-        m ^= tbit;
-        if (ATTACK || nonking_move_legal(ks, fbit, tbit)) em.push(from * 64 + to);
+
+// legality mask of a NON-king piece standing on `sq`
+GCB_HD u64 nonking_mask(const GenCtx& g, int sq, u64 bit) {
+    u64 m = g.cm;
+    if (g.pinned & bit) {
+        const u64 kbit = 1ULL << g.ksq;
+        const u64 side = sq > g.ksq ? ~(kbit | (kbit - 1)) : (kbit - 1);
+        m &= g.pinrays & line_through(g.ksq, sq) & side;
     }
+    return m;
 }
 
-template <bool ATTACK, class Emit>
-GCB_HD void gen_moves(const Board& b, int white_to_move, u32 rights, Emit& em, u64* eatt_out,
-                                          bool* in_check_out) {
-    const u64 occ = bb_occ(b);
-    const u64 own = white_to_move ? b.w : (occ & ~b.w);
-    const u64 enemy = occ & ~own;
-    const u64 kings = bb_kings(b), queens = bb_queens(b), rooks = bb_rooks(b), bishops = bb_bishops(b),
-              knights = bb_knights(b), pawns = bb_pawns(b);
-
-    // opponent attack map on the CURRENT board, own king left on it (lib.rs:466-470; Q6)
-    u64 eatt = 0;
-    if (!ATTACK) eatt = side_attack_map(b, enemy, !white_to_move);
-
-    KingSafety ks;
-    ks.occ = occ;
-    ks.has_king = (kings & own) != 0;
-    ks.ksq = 0, ks.in_check = false, ks.klines = 0, ks.leapers = 0;
-    ks.eRQ = (rooks | queens) & enemy, ks.eBQ = (bishops | queens) & enemy;
-    if (!ATTACK && ks.has_king) {
-        int ksq = ref_king_square(kings & own);
-        u64 kbit = 1ULL << ksq;
-        ks.ksq = ksq;
-        ks.in_check = (eatt >> ksq) & 1;
-        ks.klines = mask_file(ksq) | mask_rank(ksq) | mask_diag(ksq) | mask_anti(ksq);
-        // enemy pawns that attack ksq stand where a pawn of the MOVER's colour on ksq would attack
-        ks.leapers = (knight_set_att(kbit) & knights & enemy) | (king_set_att(kbit) & kings & enemy) |
-                     (pawn_set_att(kbit, white_to_move) & pawns & enemy);
+// Targets of every own piece in `subset` (a set of squares; the caller passes all own pieces, or a
+// chunk of them when there are more pieces than slots).  sink.put(rank, targets): rank = index of the
+// piece among the own pieces of `subset` in ascending square order.  Returns the number of targets.
+template <class Sink>
+GCB_HD int gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
+    const u64 occ = g.occ, own = g.own, notown = ~g.own;
+    const u64 mine = own & subset;
+    int total = 0;
+#define GCB_PUT(sq_, bit_, T_)                                         \
+    do {                                                               \
+        const u64 t__ = (T_);                                          \
+        sink.put(gcb_popc(mine & ((bit_) - 1)), t__);                  \
+        total += gcb_popc(t__);                                        \
+    } while (0)
+    // rooks
+    for (u64 s = g.rooks & mine; s; s &= s - 1) {
+        const int sq = gcb_lsb(s);
+        const u64 bit = 1ULL << sq, a = rook_att(sq, occ);
+        g.satt |= a;
+        GCB_PUT(sq, bit, a & notown & nonking_mask(g, sq, bit));
     }
-    if (eatt_out) *eatt_out = eatt;
-    if (in_check_out) *in_check_out = ks.in_check;
-
-    // row-major scan of own pieces (lib.rs:510-553)
-    u64 todo = own;
-    while (todo) {
-        const int sq = gcb_lsb(todo);
-        const u64 bit = 1ULL << sq;
-        todo &= todo - 1;
-        const int code = piece_code(b, sq);
-        if (code == PC_PAWN) {
-            // lib.rs:918-964
-            const int col = sq & 7, row = sq >> 3;
-            if (ATTACK) {
-                // (row-p, col+1) then (row-p, col-1), skipped when it holds the OWN king (Q14)
-                if (white_to_move) {
-                    if (row > 0 && col < 7 && !((kings & own) >> (sq - 7) & 1)) em.push(sq * 64 + sq - 7);
-                    if (row > 0 && col > 0 && !((kings & own) >> (sq - 9) & 1)) em.push(sq * 64 + sq - 9);
-                } else {
-                    if (row < 7 && col < 7 && !((kings & own) >> (sq + 9) & 1)) em.push(sq * 64 + sq + 9);
-                    if (row < 7 && col > 0 && !((kings & own) >> (sq + 7) & 1)) em.push(sq * 64 + sq + 7);
-                }
+    // bishops
+    for (u64 s = g.bishops & mine; s; s &= s - 1) {
+        const int sq = gcb_lsb(s);
+        const u64 bit = 1ULL << sq, a = bishop_att(sq, occ);
+        g.satt |= a;
+        GCB_PUT(sq, bit, a & notown & nonking_mask(g, sq, bit));
+    }
+    // queens
+    for (u64 s = g.queens & mine; s; s &= s - 1) {
+        const int sq = gcb_lsb(s);
+        const u64 bit = 1ULL << sq, a = rook_att(sq, occ) | bishop_att(sq, occ);
+        g.satt |= a;
+        GCB_PUT(sq, bit, a & notown & nonking_mask(g, sq, bit));
+    }
+    // knights
+    for (u64 s = g.knights & mine; s; s &= s - 1) {
+        const int sq = gcb_lsb(s);
+        const u64 bit = 1ULL << sq, a = knight_set_att(bit);
+        g.satt |= a;
+        GCB_PUT(sq, bit, a & notown & nonking_mask(g, sq, bit));
+    }
+    // kings: never passed through the legality filter (lib.rs:615-619); attack map with the king on it (Q6)
+    for (u64 s = g.kings & mine; s; s &= s - 1) {
+        const int sq = gcb_lsb(s);
+        const u64 bit = 1ULL << sq, a = king_set_att(bit);
+        g.satt |= a;
+        GCB_PUT(sq, bit, a & notown & ~g.eatt);
+    }
+    // pawns (lib.rs:918-964): one step if empty; two steps from the start row if the TARGET is empty (the
+    // jumped square is not tested, Q13); diagonals onto enemy pieces incl. the king; no en passant
+    {
+        const u64 pw = g.pawns & mine, allp = g.pawns & own;
+        g.satt |= pawn_set_att(pw, g.white) & ~(g.kings & own);  // Q14
+        (void)allp;
+        for (u64 s = pw; s; s &= s - 1) {
+            const int sq = gcb_lsb(s);
+            const u64 bit = 1ULL << sq;
+            u64 push, cap;
+            if (g.white) {
+                push = (bit >> 8) | ((bit & 0x00FF000000000000ULL) >> 16);
+                cap = ((bit & ~GCB_FILE_H) >> 7) | ((bit & ~GCB_FILE_A) >> 9);
             } else {
-                int one, two, capr, capl;
-                bool can_one, can_two;
-                if (white_to_move) {
-                    one = sq - 8, two = sq - 16, capr = sq - 7, capl = sq - 9;
-                    can_one = row > 0, can_two = row == 6;
-                } else {
-                    one = sq + 8, two = sq + 16, capr = sq + 9, capl = sq + 7;
-                    can_one = row < 7, can_two = row == 1;
-                }
-                if (can_one && !((occ >> one) & 1) && nonking_move_legal(ks, bit, 1ULL << one)) em.push(sq * 64 + one);
-                // double step tests only the TARGET square (lib.rs:942-954, Q13)
-                if (can_two && !((occ >> two) & 1) && nonking_move_legal(ks, bit, 1ULL << two)) em.push(sq * 64 + two);
-                if (can_one && col < 7 && ((enemy >> capr) & 1) && nonking_move_legal(ks, bit, 1ULL << capr))
-                    em.push(sq * 64 + capr);
-                if (can_one && col > 0 && ((enemy >> capl) & 1) && nonking_move_legal(ks, bit, 1ULL << capl))
-                    em.push(sq * 64 + capl);
+                push = (bit << 8) | ((bit & 0x000000000000FF00ULL) << 16);
+                cap = ((bit & ~GCB_FILE_H) << 9) | ((bit & ~GCB_FILE_A) << 7);
             }
-        } else if (code == PC_KNIGHT) {
-            // lib.rs:889-916, order (-2,-1)(-2,1)(2,-1)(2,1)(-1,-2)(-1,2)(1,-2)(1,2)
-            u64 t = knight_set_att(bit);
-            if (!ATTACK) t &= ~own;
-            const int d[8] = {-17, -15, 15, 17, -10, -6, 6, 10};
+            GCB_PUT(sq, bit, ((push & ~occ) | (cap & g.enemy)) & nonking_mask(g, sq, bit));
+        }
+    }
+#undef GCB_PUT
+    return total;
+}
+
+// castles, lib.rs:578-610 + 966-1056: needs the mover's king on the board and K-right OR Q-right (Q4).
+// The black branch tests WHITE ids (+ROOK on a8/h8, +KING on e8) exactly like lib.rs:1023-1046 (Q3) -- never
+// true in play.  bit0 = queen side (listed first, lib.rs:992), bit1 = king side.
+GCB_HD u32 gen_castles(const Board& b, const GenCtx& g, u32 rights) {
+    if (!g.has_king) return 0;
+    const u64 wR = g.rooks & b.w, wK = g.kings & b.w, occ = g.occ, eatt = g.eatt;
+    u32 c = 0;
+    if (g.white) {
+        if (!(rights & (RT_WK | RT_WQ))) return 0;
+        const u64 e1 = 1ULL << 60;
+        if ((wR >> 56 & 1) && !(occ & (7ULL << 57)) && (wK & e1) && !(eatt & (7ULL << 58))) c |= 1u;
+        if ((wR >> 63 & 1) && !(occ & (3ULL << 61)) && (wK & e1) && !(eatt & (7ULL << 60))) c |= 2u;
+    } else {
+        if (!(rights & (RT_BK | RT_BQ))) return 0;
+        const u64 e8 = 1ULL << 4;
+        if ((wR & 1) && !(occ & (7ULL << 1)) && (wK & e8) && !(eatt & (7ULL << 2))) c |= 1u;
+        if ((wR >> 7 & 1) && !(occ & (3ULL << 5)) && (wK & e8) && !(eatt & (7ULL << 4))) c |= 2u;
+    }
+    return c;
+}
+GCB_HD int castle_action(int white, int king_side) {
+    return white ? (king_side ? ACT_CASTLE_KS_WHITE : ACT_CASTLE_QS_WHITE) : (king_side ? ACT_CASTLE_KS_BLACK : ACT_CASTLE_QS_BLACK);
+}
+
+// ---- the reference's move ORDER inside one piece, as a function of (code, colour, square, targets)
+// direction tables, 8 signed bytes packed little-endian in a u64 (entry k = (int8)(pack >> 8k))
+#define GCB_PACK8(a, b, c, d, e, f, g, h)                                                              \
+    (((u64)(uint8_t)(int8_t)(a)) | ((u64)(uint8_t)(int8_t)(b) << 8) | ((u64)(uint8_t)(int8_t)(c) << 16) | \
+     ((u64)(uint8_t)(int8_t)(d) << 24) | ((u64)(uint8_t)(int8_t)(e) << 32) | ((u64)(uint8_t)(int8_t)(f) << 40) | \
+     ((u64)(uint8_t)(int8_t)(g) << 48) | ((u64)(uint8_t)(int8_t)(h) << 56))
+// king (lib.rs:797-806): (1,0)(-1,0)(0,1)(0,-1)(1,1)(1,-1)(-1,1)(-1,-1)
+#define GCB_DELTAS_KING GCB_PACK8(8, -8, 1, -1, 9, 7, -7, -9)
+// knight (lib.rs:891-900): (-2,-1)(-2,1)(2,-1)(2,1)(-1,-2)(-1,2)(1,-2)(1,2)
+#define GCB_DELTAS_KNIGHT GCB_PACK8(-17, -15, 15, 17, -10, -6, 6, 10)
+// pawn (lib.rs:935-959): one step, two steps, (row-p, col+1), (row-p, col-1); white then black; rest unused (0)
+#define GCB_DELTAS_WPAWN GCB_PACK8(-8, -16, -7, -9, 0, 0, 0, 0)
+#define GCB_DELTAS_BPAWN GCB_PACK8(8, 16, 9, 7, 0, 0, 0, 0)
+
+GCB_HD u64 leaper_deltas(int code, int white) {
+    return code == PC_KING ? GCB_DELTAS_KING : code == PC_KNIGHT ? GCB_DELTAS_KNIGHT : white ? GCB_DELTAS_WPAWN : GCB_DELTAS_BPAWN;
+}
+GCB_HD int delta_at(u64 pack, int k) { return (int)(int8_t)(uint8_t)(pack >> (8 * k)); }
+
+// ray k (0..7) of a slider on sq in the reference's order: rook dirs (-1,0)(1,0)(0,-1)(0,1) then bishop dirs
+// (-1,-1)(-1,1)(1,-1)(1,1) (lib.rs:824-851).  Rays 0,2,4,5 run towards lower square indices.
+GCB_HD u64 slider_ray(int sq, int k) {
+    const u64 bit = 1ULL << sq, below = bit - 1, above = ~(bit | below);
+    switch (k) {
+    case 0: return mask_file(sq) & below;
+    case 1: return mask_file(sq) & above;
+    case 2: return mask_rank(sq) & below;
+    case 3: return mask_rank(sq) & above;
+    case 4: return mask_diag(sq) & below;
+    case 5: return mask_anti(sq) & below;
+    case 6: return mask_anti(sq) & above;
+    default: return mask_diag(sq) & above;
+    }
+}
+#define GCB_RAY_DESC_MASK 0x35u  // rays 0,2,4,5: nearest square first = highest bit first
+
+template <class Emit>
+GCB_HD void emit_piece_moves(Emit& em, int code, int white, int sq, u64 T) {
+    if (!T) return;
+    const int base = sq * 64;
+    if (code == PC_KING || code == PC_KNIGHT || code == PC_PAWN) {
+        const u64 d = leaper_deltas(code, white);
+#if defined(__CUDA_ARCH__)
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                int to = sq + d[k];
-                if (to >= 0 && to < 64 && ((t >> to) & 1)) {
-                    if (ATTACK || nonking_move_legal(ks, bit, 1ULL << to)) em.push(sq * 64 + to);
-                }
-            }
-        } else if (code == PC_KING) {
-            // lib.rs:789-822 + 1113-1174, order (1,0)(-1,0)(0,1)(0,-1)(1,1)(1,-1)(-1,1)(-1,-1).
-            // King moves are never passed through the legality filter (lib.rs:615-619).
-            u64 t = king_set_att(bit);
-            if (!ATTACK) t &= ~eatt & ~own;
-            const int d[8] = {8, -8, 1, -1, 9, 7, -7, -9};
+#endif
+        for (int k = 0; k < 8; k++) {
+            const int to = sq + delta_at(d, k);
+            if (T & sq_bit_safe(to)) em.push(base + to);
+        }
+        return;
+    }
+    // sliders: rook uses rays 0-3, bishop 4-7, queen all eight
+    const int k0 = code == PC_BISHOP ? 4 : 0, k1 = code == PC_ROOK ? 4 : 8;
+#if defined(__CUDA_ARCH__)
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                int to = sq + d[k];
-                if (to >= 0 && to < 64 && ((t >> to) & 1)) em.push(sq * 64 + to);
+#endif
+    for (int k = 0; k < 8; k++) {
+        if (k < k0 || k >= k1) continue;
+        u64 m = T & slider_ray(sq, k);
+        if ((GCB_RAY_DESC_MASK >> k) & 1) {
+            while (m) {
+                const int to = gcb_msb(m);
+                m ^= 1ULL << to;
+                em.push(base + to);
             }
         } else {
-            // sliders, lib.rs:824-887: rook dirs (-1,0)(1,0)(0,-1)(0,1), bishop dirs
-            // (-1,-1)(-1,1)(1,-1)(1,1); queen = rook dirs then bishop dirs; increasing distance
-            const u64 rbit = 1ULL << (63 - sq);
-            const u64 below = bit - 1, above = ~(bit | below);
-            const u64 keepmask = ATTACK ? ~0ULL : ~own;
-            if (code == PC_ROOK || code == PC_QUEEN) {
-                u64 f = hq_line(occ, mask_file(sq) ^ bit, bit, rbit) & keepmask;
-                u64 r = hq_line(occ, mask_rank(sq) ^ bit, bit, rbit) & keepmask;
-                emit_targets_desc<ATTACK>(em, ks, sq, bit, f & below);
-                emit_targets_asc<ATTACK>(em, ks, sq, bit, f & above);
-                emit_targets_desc<ATTACK>(em, ks, sq, bit, r & below);
-                emit_targets_asc<ATTACK>(em, ks, sq, bit, r & above);
-            }
-            if (code == PC_BISHOP || code == PC_QUEEN) {
-                u64 dg = hq_line(occ, mask_diag(sq) ^ bit, bit, rbit) & keepmask;
-                u64 an = hq_line(occ, mask_anti(sq) ^ bit, bit, rbit) & keepmask;
-                emit_targets_desc<ATTACK>(em, ks, sq, bit, dg & below);  // (-1,-1)
-                emit_targets_desc<ATTACK>(em, ks, sq, bit, an & below);  // (-1,+1)
-                emit_targets_asc<ATTACK>(em, ks, sq, bit, an & above);   // (+1,-1)
-                emit_targets_asc<ATTACK>(em, ks, sq, bit, dg & above);   // (+1,+1)
+            while (m) {
+                const int to = gcb_lsb(m);
+                m &= m - 1;
+                em.push(base + to);
             }
         }
     }
+}
 
-    if (ATTACK) return;
-    // castles, lib.rs:578-610 + 966-1056: needs the mover's king on the board and K-right OR
-    // Q-right (Q4); queen side is listed before king side.  The black branch tests WHITE ids
-    // (+ROOK on a8/h8, +KING on e8) exactly like lib.rs:1023-1046 (Q3) -- never true in play.
-    if (!ks.has_king) return;
-    const u64 wR = rooks & b.w, wK = kings & b.w;
-    if (white_to_move) {
-        if (!(rights & (RT_WK | RT_WQ))) return;
-        const u64 e1 = 1ULL << 60;
-        if ((wR >> 56 & 1) && !(occ & (7ULL << 57)) && (wK & e1) && !(eatt & (7ULL << 58))) em.push(ACT_CASTLE_QS_WHITE);
-        if ((wR >> 63 & 1) && !(occ & (3ULL << 61)) && (wK & e1) && !(eatt & (7ULL << 60))) em.push(ACT_CASTLE_KS_WHITE);
-    } else {
-        if (!(rights & (RT_BK | RT_BQ))) return;
-        const u64 e8 = 1ULL << 4;
-        if ((wR & 1) && !(occ & (7ULL << 1)) && (wK & e8) && !(eatt & (7ULL << 2))) em.push(ACT_CASTLE_QS_BLACK);
-        if ((wR >> 7 & 1) && !(occ & (3ULL << 5)) && (wK & e8) && !(eatt & (7ULL << 4))) em.push(ACT_CASTLE_KS_BLACK);
+// the idx-th (0-based) target of one piece in the reference's order; idx < popc(T)
+GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
+    if (code == PC_KING || code == PC_KNIGHT || code == PC_PAWN) {
+        const u64 d = leaper_deltas(code, white);
+        int res = sq;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 8; k++) {
+            const int to = sq + delta_at(d, k);
+            if (T & sq_bit_safe(to)) {
+                if (idx == 0) res = to;
+                idx--;
+            }
+        }
+        return res;
+    }
+    // sliders: find the ray that holds the idx-th target, then walk idx squares along it (nearest first)
+    const int k0 = code == PC_BISHOP ? 4 : 0, k1 = code == PC_ROOK ? 4 : 8;
+    u64 mf = 0;
+    bool found = false, desc = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; k++) {
+        if (k < k0 || k >= k1 || found) continue;
+        const u64 m = T & slider_ray(sq, k);
+        const int c = gcb_popc(m);
+        if (idx < c) found = true, mf = m, desc = (GCB_RAY_DESC_MASK >> k) & 1;
+        else idx -= c;
+    }
+    if (!mf) return sq;
+    if (desc) mf = gcb_brev64(mf);  // nearest first = lowest bit first in both cases
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < idx; j++) mf &= mf - 1;
+    const int t = gcb_lsb(mf);
+    return desc ? 63 - t : t;
+}
+
+// ---- attack=True lists (get_possible_moves(attack=True), lib.rs:928-933, 1089-1104, 1147-1174): defended
+// squares included, pawn diagonals only (minus squares holding the mover's own king, Q14), no legality filter,
+// no castles; ordered, straight from the board.
+template <class Emit>
+GCB_HD void gen_attack_moves(const Board& b, int white_to_move, Emit& em) {
+    const u64 occ = bb_occ(b);
+    const u64 own = white_to_move ? b.w : (occ & ~b.w);
+    const u64 ownk = bb_kings(b) & own;
+    for (u64 todo = own; todo; todo &= todo - 1) {
+        const int sq = gcb_lsb(todo);
+        const u64 bit = 1ULL << sq;
+        const int code = piece_code(b, sq);
+        u64 T;
+        if (code == PC_PAWN) T = pawn_set_att(bit, white_to_move) & ~ownk;
+        else if (code == PC_KNIGHT) T = knight_set_att(bit);
+        else if (code == PC_KING) T = king_set_att(bit);
+        else {
+            T = 0;
+            if (code == PC_ROOK || code == PC_QUEEN) T |= rook_att(sq, occ);
+            if (code == PC_BISHOP || code == PC_QUEEN) T |= bishop_att(sq, occ);
+        }
+        if (code == PC_PAWN) {  // (row-p, col+1) then (row-p, col-1)
+            const int d1 = white_to_move ? -7 : 9, d2 = white_to_move ? -9 : 7;
+            if (T & sq_bit_safe(sq + d1)) em.push(sq * 64 + sq + d1);
+            if (T & sq_bit_safe(sq + d2)) em.push(sq * 64 + sq + d2);
+        } else {
+            emit_piece_moves(em, code, white_to_move, sq, T);
+        }
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// next_state (lib.rs:679-784) on planes.  `rights` must already be masked (mask_rights).
-// Returns the reward; *status = 0 ok, -1 empty from-square (reference panics), -2 bad action.
-// *irreversible is set for pawn moves and captures (board-only repetition key can never recur).
-// ---------------------------------------------------------------------------------------------
-GCB_HD int piece_value(int code) {
-    // P1 N3 B3 R5 Q10 K0 (lib.rs:19-25), indexed by code 0..7, 4 bits each
-    return (int)((0x01335A00u >> (code * 4)) & 15u);
-}
-
-GCB_HD int apply_action(Board& b, u32& rights, int white_to_move, int action, int* status,
-                                            bool* irreversible) {
-    *status = 0;
-    *irreversible = false;
-    int reward = 0;
-    if (action < 4096) {
-        if (action < 0) { *status = -2; return 0; }
-        const int from = action >> 6, to = action & 63;
-        const int pid = piece_id(b, from);
-        if (pid == 0) { *status = -1; return 0; }
-        const int cap = piece_code(b, to);
-        const int code = pid < 0 ? -pid : pid;
-        int newcode = code, newwhite = pid > 0;
-        reward += piece_value(cap);
-        // "pawn becomes queen" tests the WRONG ends (lib.rs:703-704, Q1); colour = the MOVER's
-        if (code == PC_PAWN && ((white_to_move && (to >> 3) == 7) || (!white_to_move && (to >> 3) == 0))) {
-            newcode = PC_QUEEN, newwhite = white_to_move;
-            reward += 10;
+// Whole ordered legal list of one position through a small slot buffer (any number of own pieces): the
+// engine-level get_possible_moves.  Slots must offer put(r, T) / get(r) for r < GCB_SLOTS.
+#define GCB_SLOTS 16
+template <class Slots, class Emit>
+GCB_HD void gen_legal_list(const Board& b, int white_to_move, u32 rights, Slots& slots, Emit& em, bool* in_check_out) {
+    GenCtx g;
+    gen_prepare(b, white_to_move, g);
+    if (in_check_out) *in_check_out = g.in_check;
+    u64 rem = g.own;
+    while (rem) {
+        // next chunk of at most GCB_SLOTS own pieces in square order
+        u64 chunk = rem;
+        if (gcb_popc(rem) > GCB_SLOTS) {
+            u64 t = rem;
+            for (int i = 0; i < GCB_SLOTS; i++) t &= t - 1;
+            chunk = rem ^ t;
         }
-        clear_sq(b, 1ULL << from);
-        put_sq(b, to, newcode, newwhite);
-        // rights react only to WHITE ids, column of the from-square only (lib.rs:711-734, Q5)
-        if (pid == PC_KING) rights &= white_to_move ? ~(RT_WK | RT_WQ) : ~(RT_BK | RT_BQ);
-        else if (pid == PC_ROOK) {
-            if ((from & 7) == 0) rights &= white_to_move ? ~RT_WQ : ~RT_BQ;
-            else if ((from & 7) == 7) rights &= white_to_move ? ~RT_WK : ~RT_BK;
-        }
-        *irreversible = (code == PC_PAWN) || (cap != 0);
-    } else {
-        switch (action) {  // literal square writes, lib.rs:739-774
-        case ACT_CASTLE_KS_WHITE:
-            put_sq(b, 60, 0, 0), put_sq(b, 61, PC_ROOK, 1), put_sq(b, 62, PC_KING, 1), put_sq(b, 63, 0, 0);
-            rights &= ~(RT_WK | RT_WQ);
-            break;
-        case ACT_CASTLE_QS_WHITE:
-            put_sq(b, 56, 0, 0), put_sq(b, 57, 0, 0), put_sq(b, 58, PC_KING, 1), put_sq(b, 59, PC_ROOK, 1), put_sq(b, 60, 0, 0);
-            rights &= ~(RT_WK | RT_WQ);
-            break;
-        case ACT_CASTLE_KS_BLACK:
-            put_sq(b, 4, 0, 0), put_sq(b, 5, PC_ROOK, 0), put_sq(b, 6, PC_KING, 0), put_sq(b, 7, 0, 0);
-            rights &= ~(RT_BK | RT_BQ);
-            break;
-        case ACT_CASTLE_QS_BLACK:
-            put_sq(b, 0, 0, 0), put_sq(b, 1, 0, 0), put_sq(b, 2, PC_KING, 0), put_sq(b, 3, PC_ROOK, 0), put_sq(b, 4, 0, 0);
-            rights &= ~(RT_BK | RT_BQ);
-            break;
-        default: *status = -2; return 0;
+        rem ^= chunk;
+        gen_targets(b, g, chunk, slots);
+        int r = 0;
+        for (u64 s = chunk; s; s &= s - 1, r++) {
+            const int sq = gcb_lsb(s);
+            emit_piece_moves(em, piece_code(b, sq), white_to_move, sq, slots.get(r));
         }
     }
-    return reward;
+    const u32 c = gen_castles(b, g, rights);
+    if (c & 1u) em.push(castle_action(white_to_move, 0));
+    if (c & 2u) em.push(castle_action(white_to_move, 1));
 }
 
 // ---------------------------------------------------------------------------------------------
 // Zobrist key of the board only (the reference's repetition key is the 64-char board string,
 // chess_v2.py:404-407, 599-602: no side to move, no rights).  Keys are splitmix64 of
-// (piece index, square); piece index = id + 6 in 0..12.
+// (piece index, square); piece index = id + 6 in 0..12.  The env kernels read them from a
+// 13*64-entry table in global memory (fill_zobrist_table), three L1-resident loads per ply.
 // ---------------------------------------------------------------------------------------------
 GCB_HD u64 gcb_splitmix64(u64 x) {
     x += 0x9E3779B97F4A7C15ULL;
@@ -489,8 +631,17 @@ GCB_HD u64 gcb_splitmix64(u64 x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
+#define GCB_ZOB_ENTRIES (13 * 64)
 GCB_HD u64 zobrist_piece(int pid /* signed id != 0 */, int sq) {
     return gcb_splitmix64((u64)((pid + 6) * 64 + sq) + 0x6A09E667F3BCC908ULL);
+}
+GCB_HD void fill_zobrist_entry(u64* tab, int i) { tab[i] = (i >> 6) == 6 ? 0ULL : zobrist_piece((i >> 6) - 6, i & 63); }
+GCB_HD u64 zob_at(const u64* tab, int pid, int sq) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(tab + (pid + 6) * 64 + sq);
+#else
+    return tab[(pid + 6) * 64 + sq];
+#endif
 }
 GCB_HD u64 zobrist_full(const Board& b) {
     u64 occ = bb_occ(b), k = 0;
@@ -503,6 +654,91 @@ GCB_HD u64 zobrist_full(const Board& b) {
 }
 // what the history ring stores / compares: never 0, which marks "no ply in this slot"
 GCB_HD u64 hist_key(u64 zkey) { return zkey | 1ULL; }
+
+// ---------------------------------------------------------------------------------------------
+// next_state (lib.rs:679-784) on planes.  `rights` must already be masked (mask_rights).
+// Returns the reward; *status = 0 ok, -1 empty from-square (reference panics), -2 bad action.
+// *irreversible is set for pawn moves and captures (board-only repetition key can never recur).
+// ztab != NULL: *zk (Zobrist key of the board) is updated incrementally.
+// ---------------------------------------------------------------------------------------------
+GCB_HD int piece_value(int code) {
+    // P1 N3 B3 R5 Q10 K0 (lib.rs:19-25), indexed by code 0..7, 4 bits each
+    return (int)((0x01335A00u >> (code * 4)) & 15u);
+}
+GCB_HD void set_code(Board& b, u64 bit, int code, int white) {  // the square must be clear
+    if (code & 1) b.t0 |= bit;
+    if (code & 2) b.t1 |= bit;
+    if (code & 4) b.t2 |= bit;
+    if (white && code) b.w |= bit;
+}
+
+GCB_HD int apply_action(Board& b, u32& rights, int white_to_move, int action, int* status, bool* irreversible,
+                        u64* zk = nullptr, const u64* ztab = nullptr) {
+    *status = 0;
+    *irreversible = false;
+    int reward = 0;
+    if (action < 4096) {
+        if (action < 0) { *status = -2; return 0; }
+        const int from = action >> 6, to = action & 63;
+        const u64 fbit = 1ULL << from, tbit = 1ULL << to;
+        const int code = piece_code(b, from);
+        if (code == 0) { *status = -1; return 0; }
+        const int fw = (int)((b.w >> from) & 1);
+        const int cap = piece_code(b, to), capw = (int)((b.w >> to) & 1);
+        int newcode = code, newwhite = fw;
+        reward += piece_value(cap);
+        // "pawn becomes queen" tests the WRONG ends (lib.rs:703-704, Q1); colour = the MOVER's
+        if (code == PC_PAWN && ((white_to_move && (to >> 3) == 7) || (!white_to_move && (to >> 3) == 0))) {
+            newcode = PC_QUEEN, newwhite = white_to_move;
+            reward += 10;
+        }
+        clear_sq(b, fbit | tbit);
+        set_code(b, tbit, newcode, newwhite);
+        if (ztab) {
+            u64 z = zob_at(ztab, fw ? code : -code, from) ^ zob_at(ztab, newwhite ? newcode : -newcode, to);
+            if (cap) z ^= zob_at(ztab, capw ? cap : -cap, to);  // (from == to: the "captured" piece is the mover itself)
+            *zk ^= z;
+        }
+        // rights react only to WHITE ids, column of the from-square only (lib.rs:711-734, Q5)
+        if (fw && code == PC_KING) rights &= white_to_move ? ~(RT_WK | RT_WQ) : ~(RT_BK | RT_BQ);
+        else if (fw && code == PC_ROOK) {
+            if ((from & 7) == 0) rights &= white_to_move ? ~RT_WQ : ~RT_BQ;
+            else if ((from & 7) == 7) rights &= white_to_move ? ~RT_WK : ~RT_BK;
+        }
+        *irreversible = (code == PC_PAWN) || (cap != 0);
+    } else {
+        const Board old = b;
+        switch (action) {  // literal square writes, lib.rs:739-774
+        case ACT_CASTLE_KS_WHITE:
+            clear_sq(b, 15ULL << 60), set_code(b, 1ULL << 61, PC_ROOK, 1), set_code(b, 1ULL << 62, PC_KING, 1);
+            rights &= ~(RT_WK | RT_WQ);
+            break;
+        case ACT_CASTLE_QS_WHITE:
+            clear_sq(b, 31ULL << 56), set_code(b, 1ULL << 58, PC_KING, 1), set_code(b, 1ULL << 59, PC_ROOK, 1);
+            rights &= ~(RT_WK | RT_WQ);
+            break;
+        case ACT_CASTLE_KS_BLACK:
+            clear_sq(b, 15ULL << 4), set_code(b, 1ULL << 5, PC_ROOK, 0), set_code(b, 1ULL << 6, PC_KING, 0);
+            rights &= ~(RT_BK | RT_BQ);
+            break;
+        case ACT_CASTLE_QS_BLACK:
+            clear_sq(b, 31ULL), set_code(b, 1ULL << 2, PC_KING, 0), set_code(b, 1ULL << 3, PC_ROOK, 0);
+            rights &= ~(RT_BK | RT_BQ);
+            break;
+        default: *status = -2; return 0;
+        }
+        if (ztab) {  // rare: key over the squares that changed
+            u64 diff = (old.t0 ^ b.t0) | (old.t1 ^ b.t1) | (old.t2 ^ b.t2) | (old.w ^ b.w);
+            for (; diff; diff &= diff - 1) {
+                const int sq = gcb_lsb(diff);
+                const int po = piece_id(old, sq), pn = piece_id(b, sq);
+                if (po) *zk ^= zob_at(ztab, po, sq);
+                if (pn) *zk ^= zob_at(ztab, pn, sq);
+            }
+        }
+    }
+    return reward;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  draw = word 0 of ctr=(env, episode, step, purpose),

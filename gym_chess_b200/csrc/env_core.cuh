@@ -5,11 +5,16 @@
 // Layout in HBM (structure of arrays):
 //   bb01[N]  ulonglong2 {t0,t1}       16 B   piece-code bit-planes
 //   bb23[N]  ulonglong2 {t2,white}    16 B
-//   meta[N]  u64                       8 B   stm | rights | check flags | done | n_legal | move_count |
-//                                            step_in_episode | hist_len
+//   meta[N]  u64                       8 B   stm | rights | check flags | done | castle bits | n_legal |
+//                                            move_count | step_in_episode | hist_len
 //   zkey[N]  u64                       8 B   Zobrist key of the current board (board only)
+//   bloom[N] ulonglong2               16 B   two 64-bit Bloom words over the repetition window: key seen once /
+//                                            seen twice; the ring is only scanned when the second one hits
 //   episode[N] u32                     4 B
-//   legal[N][stride] u16                     cached ordered legal list = ChessEnvV2.possible_moves
+//   tgt[S][N] u64                            the cached legal set = ChessEnvV2.possible_moves: slot r = legal
+//                                            targets of the r-th own piece of the side to move (ascending square
+//                                            order = the reference's scan order); castles are two bits of meta.
+//                                            The ordered action list is a pure decode of (board, slots).
 //   hist[H][N] u64                           Zobrist ring; slot = global tick * plies-per-step + k, so that
 //                                            appends and window scans are coalesced across envs
 #pragma once
@@ -52,40 +57,43 @@ struct ListWriter {
     }
 };
 
-// meta word
+// meta word: bit 0 stm, 1-4 rights, 5-6 check flags, 7 done, 8-9 castle (queen side, king side)
 #define M_RIGHTS_SHIFT 1
-#define M_NLEGAL_SHIFT 8
-#define M_MOVECOUNT_SHIFT 20
-#define M_STEP_SHIFT 36
-#define M_HIST_SHIFT 52
+#define M_CASTLE_SHIFT 8
+#define M_NLEGAL_SHIFT 10
+#define M_MOVECOUNT_SHIFT 22
+#define M_STEP_SHIFT 38
+#define M_HIST_SHIFT 54
 
 enum { ST_STEPS = 0, ST_PLIES, ST_EPISODES, ST_MATES, ST_REPS, ST_CAPS, ST_WEDGED, ST_INVALID, ST_REWARD, ST_LEGAL,
-       ST_INCHECK, ST_HISTOVF, ST_LISTOVF, ST_HISTSCAN, ST_USED, ST_COUNT = 16 };
+       ST_INCHECK, ST_HISTOVF, ST_SLOTOVF, ST_HISTSCAN, ST_WINDOW, ST_USED, ST_COUNT = 16 };
 
 struct EnvView {
     ulonglong2* bb01;
     ulonglong2* bb23;
     u64* meta;
     u64* zkey;
+    ulonglong2* bloom;
     u32* episode;
-    uint16_t* legal;
+    u64* tgt;
     u64* hist;
     const ulonglong2* t_bb01;
     const ulonglong2* t_bb23;
     const u64* t_meta;
     const u64* t_zkey;
-    const uint16_t* t_legal;
+    const u64* t_tgt;
+    const u64* zob;
     u64* stats;
     u64 seed;
-    int N, stride, hist_mask, n_templates;
+    int N, slots, hist_mask, n_templates;
     u32 env_offset;
     int moves_max, opponent, agent_black, auto_reset, pps;
 };
 
 struct EnvRegs {
     Board b;
-    u64 zk;
-    u32 rights, chk;  // chk bit0 white checked, bit1 black checked
+    u64 zk, seen1, seen2;
+    u32 rights, chk, castle;  // chk bit0 white checked, bit1 black checked; castle bit0 queen side, bit1 king side
     int stm_black, done, n_legal, move_count, step, hist_len;
 };
 
@@ -94,6 +102,7 @@ GCB_HD void unpack_meta(u64 m, EnvRegs& s) {
     s.rights = (u32)(m >> M_RIGHTS_SHIFT) & 15u;
     s.chk = (u32)(m >> 5) & 3u;
     s.done = (int)(m >> 7) & 1;
+    s.castle = (u32)(m >> M_CASTLE_SHIFT) & 3u;
     s.n_legal = (int)(m >> M_NLEGAL_SHIFT) & 0xFFF;
     s.move_count = (int)(m >> M_MOVECOUNT_SHIFT) & 0xFFFF;
     s.step = (int)(m >> M_STEP_SHIFT) & 0xFFFF;
@@ -101,12 +110,26 @@ GCB_HD void unpack_meta(u64 m, EnvRegs& s) {
 }
 GCB_HD u64 pack_meta(const EnvRegs& s) {
     return (u64)(s.stm_black & 1) | ((u64)(s.rights & 15u) << M_RIGHTS_SHIFT) | ((u64)(s.chk & 3u) << 5) |
-           ((u64)(s.done & 1) << 7) | ((u64)(s.n_legal & 0xFFF) << M_NLEGAL_SHIFT) |
+           ((u64)(s.done & 1) << 7) | ((u64)(s.castle & 3u) << M_CASTLE_SHIFT) | ((u64)(s.n_legal & 0xFFF) << M_NLEGAL_SHIFT) |
            ((u64)(s.move_count & 0xFFFF) << M_MOVECOUNT_SHIFT) | ((u64)(s.step & 0xFFFF) << M_STEP_SHIFT) |
            ((u64)(s.hist_len & 0x3FF) << M_HIST_SHIFT);
 }
 
 GCB_HD bool stm_checked(const EnvRegs& s) { return (s.chk >> s.stm_black) & 1u; }
+GCB_HD u64 stm_pieces(const EnvRegs& s) { return s.stm_black ? (bb_occ(s.b) & ~s.b.w) : s.b.w; }
+
+// piece slots of env e in the resident array (slot r of env e at tgt[r*N + e]: coalesced when a warp reads slot r)
+struct TgtSink {
+    u64* base;
+    size_t N;
+    int slots, dropped;
+    GCB_HD TgtSink(u64* tgt, int n, int e, int s) : base(tgt + e), N((size_t)n), slots(s), dropped(0) {}
+    GCB_HD void put(int r, u64 t) {
+        if (r < slots) base[(size_t)r * N] = t;
+        else dropped++;
+    }
+    GCB_HD u64 get(int r) const { return r < slots ? base[(size_t)r * N] : 0ULL; }
+};
 
 // history ring bookkeeping: `cursor` = next slot of this tick; hist_len = length of the contiguous
 // window of slots behind the cursor that may hold an equal board (reset by irreversible plies)
@@ -126,60 +149,93 @@ GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, in
     }
 }
 
+// The action `possible_moves[idx]` of the reference-ordered list, decoded from the slots (chess_v2.py:116-127:
+// the uniform draw indexes the ORDERED list).  idx < n_legal.
+GCB_HD int action_at(const EnvView& v, int e, const EnvRegs& s, int idx) {
+    TgtSink slots(v.tgt, v.N, e, v.slots);
+    int r = 0;
+    for (u64 rem = stm_pieces(s); rem; rem &= rem - 1, r++) {
+        const u64 T = slots.get(r);
+        const int c = gcb_popc(T);
+        if (idx < c) {
+            const int sq = gcb_lsb(rem);
+            return sq * 64 + nth_target(piece_code(s.b, sq), !s.stm_black, sq, T, idx);
+        }
+        idx -= c;
+    }
+    // castles come last, queen side first (lib.rs:1473-1479, 992, 1011)
+    const int king_side = (s.castle & 1u) ? (idx != 0) : 1;
+    return castle_action(!s.stm_black, king_side);
+}
+
+// action in possible_actions ? (chess_v2.py:240)
+GCB_HD bool action_is_legal(const EnvView& v, int e, const EnvRegs& s, int action) {
+    if (action < 0) return false;
+    if (action < 4096) {
+        const int from = action >> 6, to = action & 63;
+        const u64 own = stm_pieces(s), fbit = 1ULL << from;
+        if (!(own & fbit)) return false;
+        TgtSink slots(v.tgt, v.N, e, v.slots);
+        return (slots.get(gcb_popc(own & (fbit - 1))) >> to) & 1ULL;
+    }
+    if (action == castle_action(!s.stm_black, 0)) return s.castle & 1u;
+    if (action == castle_action(!s.stm_black, 1)) return (s.castle >> 1) & 1u;
+    return false;
+}
+
+struct StepStats {
+    int v[ST_USED];
+};
+
 // One ply = player_move (chess_v2.py:393-412: engine.next_state + repetition count on the PRE-move
 // board) + the state setter (315-323) + switch_player (296-299) + get_possible_moves for the new
 // side to move (573-582).  apply=false only switches the side and regenerates (BLACK-agent reset
 // when White has no move).  Returns the ply reward.
 GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int slot, int action, bool apply, bool* rep,
-                           int* hist_ovf, int* hist_scanned) {
+                           StepStats& st) {
     int r = 0;
     *rep = false;
     if (apply) {
-        hist_skip_to(v, e, s, hc, slot, hist_ovf);
+        hist_skip_to(v, e, s, hc, slot, &st.v[ST_HISTOVF]);
         const u64 key = hist_key(s.zk);
         const u64 cur = hc.base + slot;
+        // repetition count of the pre-move board over the reversible window.  The ring is read only when the
+        // "seen twice" Bloom word says this key may already have occurred twice (no false negatives).
+        const u64 bbit = 1ULL << (key >> 58);
         int cnt = 0;
-        for (int j = 1; j <= s.hist_len; j++) cnt += (v.hist[((cur - j) & (u64)v.hist_mask) * (u64)v.N + e] == key);
+        if (s.seen2 & bbit) {
+            for (int j = 1; j <= s.hist_len; j++) cnt += (v.hist[((cur - j) & (u64)v.hist_mask) * (u64)v.N + e] == key);
+            st.v[ST_HISTSCAN] += s.hist_len;
+        }
+        st.v[ST_WINDOW] += s.hist_len;
         *rep = cnt >= 2;  // saved_boards[key] reaches 3 with this ply
-        *hist_scanned += s.hist_len;
         v.hist[(cur & (u64)v.hist_mask) * (u64)v.N + e] = key;
         hc.cursor = slot + 1;
+        if (s.seen1 & bbit) s.seen2 |= bbit;
+        s.seen1 |= bbit;
 
-        const Board old = s.b;
         u32 rights = mask_rights(s.b, s.rights);  // engine entry masks by the INPUT board (Q21)
-        int st;
+        int status;
         bool irr;
-        r = apply_action(s.b, rights, !s.stm_black, action, &st, &irr);
+        r = apply_action(s.b, rights, !s.stm_black, action, &status, &irr, &s.zk, v.zob);
         s.rights = rights;
-        // incremental Zobrist over the squares that changed
-        u64 diff = (old.t0 ^ s.b.t0) | (old.t1 ^ s.b.t1) | (old.t2 ^ s.b.t2) | (old.w ^ s.b.w);
-        while (diff) {
-            int sq = gcb_lsb(diff);
-            diff &= diff - 1;
-            int po = piece_id(old, sq), pn = piece_id(s.b, sq);
-            if (po) s.zk ^= zobrist_piece(po, sq);
-            if (pn) s.zk ^= zobrist_piece(pn, sq);
-        }
-        if (irr) s.hist_len = 0;
+        if (irr) s.hist_len = 0, s.seen1 = 0, s.seen2 = 0;
         else if (s.hist_len < v.hist_mask) s.hist_len++;
-        else (*hist_ovf)++;
+        else st.v[ST_HISTOVF]++;
     }
     s.stm_black ^= 1;
-    ListWriter lw(v.legal + (size_t)e * v.stride, v.stride);
-    bool inchk = false;
-    u64 eatt;
-    gen_moves<false>(s.b, !s.stm_black, mask_rights(s.b, s.rights), lw, &eatt, &inchk);
-    lw.flush();
-    s.n_legal = lw.n;
-    // both check flags (update_state, lib.rs:1386-1393): the side to move from its movegen attack map,
-    // the side that just moved by the symmetric single-square test
-    u32 chk = inchk ? (1u << s.stm_black) : 0u;
-    {
-        const u64 occ = bb_occ(s.b);
-        const u64 stm_side = s.stm_black ? (occ & ~s.b.w) : s.b.w;
-        const u64 mk = bb_kings(s.b) & occ & ~stm_side;
-        if (mk && square_attacked_by(s.b, ref_king_square(mk), stm_side, !s.stm_black)) chk |= 1u << (s.stm_black ^ 1);
-    }
+    GenCtx g;
+    gen_prepare(s.b, !s.stm_black, g);
+    TgtSink sink(v.tgt, v.N, e, v.slots);
+    const int n = gen_targets(s.b, g, g.own, sink);
+    if (sink.dropped) st.v[ST_SLOTOVF] += 1;
+    s.castle = gen_castles(s.b, g, mask_rights(s.b, s.rights));
+    s.n_legal = n + (int)(s.castle & 1u) + (int)(s.castle >> 1);
+    // both check flags (update_state, lib.rs:1386-1393): the side to move from the attackers of its king
+    // square, the side that just moved from the attack map the generation accumulated
+    u32 chk = g.in_check ? (1u << s.stm_black) : 0u;
+    const u64 mk = g.kings & g.enemy;
+    if (mk && ((g.satt >> ref_king_square(mk)) & 1ULL)) chk |= 1u << (s.stm_black ^ 1);
     s.chk = chk;
     return r;
 }
@@ -198,10 +254,6 @@ struct StepIO {
     int ep_inc;
 };
 
-struct StepStats {
-    int v[ST_USED];
-};
-
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step)
 template <int MODE>
 GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& st) {
@@ -209,12 +261,13 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     {
         ulonglong2 a = v.bb01[e], c = v.bb23[e];
         s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
+        ulonglong2 bl = v.bloom[e];
+        s.seen1 = bl.x, s.seen2 = bl.y;
     }
     unpack_meta(v.meta[e], s);
     s.zk = v.zkey[e];
     u32 ep = v.episode[e];
     const u32 genv = v.env_offset + (u32)e;
-    uint16_t* mylist = v.legal + (size_t)e * v.stride;
     HistCursor hc;
     hc.base = io.tick * (u64)v.pps, hc.cursor = 0;
 
@@ -229,15 +282,13 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
         phase = PH_FINAL;
     } else {
         bool valid = false;
-        const int nread = n0 < v.stride ? n0 : v.stride;  // entries beyond the stride were dropped (list_overflow)
         if (MODE == MODE_ACTION) {
             action = reinterpret_cast<const int32_t*>(io.in)[e];
-            for (int k = 0; k < nread; k++) valid |= (mylist[k] == action);  // action in possible_actions
+            valid = action_is_legal(v, e, s, action);  // action in possible_actions
         } else {
             u32 u = (MODE == MODE_INDEX) ? reinterpret_cast<const u32*>(io.in)[e] : philox_draw(v.seed, genv, ep, step_idx, 0u);
             if (n0 > 0) {
-                int idx = (int)gcb_umulhi(u, (u32)n0);
-                action = mylist[idx < nread ? idx : nread - 1];
+                action = action_at(v, e, s, (int)gcb_umulhi(u, (u32)n0));
                 valid = true;
             }
         }
@@ -293,16 +344,16 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
                 s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
                 unpack_meta(v.t_meta[t], s);
                 s.zk = v.t_zkey[t];
-                const uint16_t* tl = v.t_legal + (size_t)t * v.stride;
-                const int lim = s.n_legal < v.stride ? s.n_legal : v.stride;
-                for (int k = 0; k < lim; k += 2) *reinterpret_cast<u32*>(mylist + k) = *reinterpret_cast<const u32*>(tl + k);
+                s.seen1 = 0, s.seen2 = 0;
+                const int np = gcb_popc(s.b.w);  // White is to move in every initial state
+                const u64* ts = v.t_tgt + (size_t)t * v.slots;
+                for (int r = 0; r < np && r < v.slots; r++) v.tgt[(size_t)r * v.N + e] = ts[r];
                 ep += (u32)io.ep_inc;
                 if (v.agent_black) {
                     // the bot opens for White (chess_v2.py:208-216)
                     if (s.n_legal > 0) {
                         u32 u = philox_draw(v.seed, genv, ep, 0u, 2u);
-                        int idx = (int)gcb_umulhi(u, (u32)s.n_legal);
-                        cur = mylist[idx < v.stride ? idx : v.stride - 1];
+                        cur = action_at(v, e, s, (int)gcb_umulhi(u, (u32)s.n_legal));
                         do_apply = true;
                     } else {
                         do_apply = false;
@@ -316,9 +367,8 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
             continue;
         }
         bool rep;
-        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, &st.v[ST_HISTOVF], &st.v[ST_HISTSCAN]);
+        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st);
         if (do_apply) st.v[ST_PLIES] += 1;
-        if (s.n_legal > v.stride) st.v[ST_LISTOVF] += 1;
         const bool mate = s.n_legal == 0 && stm_checked(s);
         if (phase == PH_AGENT) {
             agent_ply = true;
@@ -329,8 +379,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
             if (!s.done && v.opponent == 1) {
                 if (s.n_legal > 0) {  // chess_v2.py:277-288
                     u32 u = philox_draw(v.seed, genv, ep, step_idx, 1u);
-                    int idx = (int)gcb_umulhi(u, (u32)s.n_legal);
-                    bot_action = mylist[idx < v.stride ? idx : v.stride - 1];
+                    bot_action = action_at(v, e, s, (int)gcb_umulhi(u, (u32)s.n_legal));
                     cur = bot_action, slot = 1, phase = PH_BOT;
                     continue;
                 }
@@ -357,6 +406,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
 
     v.bb01[e] = make_ulonglong2(s.b.t0, s.b.t1);
     v.bb23[e] = make_ulonglong2(s.b.t2, s.b.w);
+    v.bloom[e] = make_ulonglong2(s.seen1, s.seen2);
     v.meta[e] = pack_meta(s);
     v.zkey[e] = s.zk;
     v.episode[e] = ep;
@@ -364,24 +414,42 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
 
 // initial state of one template board (ChessEnvV2.reset up to the first movegen, chess_v2.py:188-206)
 GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulonglong2* bb23, u64* meta, u64* zkey,
-                              uint16_t* legal, int stride) {
+                              u64* tgt, int slots) {
     Board b = board_from_mailbox(boards + (size_t)i * 64);
     EnvRegs s;
     s.b = b;
     s.zk = zobrist_full(b);
+    s.seen1 = s.seen2 = 0;
     s.rights = mask_rights(b, 15u);  // all four True, then engine.update_state masks them (chess_v2.py:195-204)
     s.chk = check_flags(b);
     s.stm_black = 0, s.done = 0, s.move_count = 0, s.step = 0, s.hist_len = 0;
-    ListWriter lw(legal + (size_t)i * stride, stride);
-    u64 eatt;
-    bool chk;
-    gen_moves<false>(b, 1, s.rights, lw, &eatt, &chk);
-    lw.flush();
-    s.n_legal = lw.n;
+    GenCtx g;
+    gen_prepare(b, 1, g);
+    TgtSink sink(tgt + (size_t)i * slots, 1, 0, slots);
+    const int n = gen_targets(b, g, g.own, sink);
+    s.castle = gen_castles(b, g, s.rights);
+    s.n_legal = n + (int)(s.castle & 1u) + (int)(s.castle >> 1);
     bb01[i] = make_ulonglong2(b.t0, b.t1);
     bb23[i] = make_ulonglong2(b.t2, b.w);
     meta[i] = pack_meta(s);
     zkey[i] = s.zk;
+}
+
+// ChessEnvV2.possible_actions (chess_v2.py:333-335) of env e: decode the slots into the reference-ordered list
+template <class Emit>
+GCB_HD void env_legal_list_one(const EnvView& v, int e, Emit& em) {
+    EnvRegs s;
+    ulonglong2 a = v.bb01[e], c = v.bb23[e];
+    s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
+    unpack_meta(v.meta[e], s);
+    TgtSink slots(v.tgt, v.N, e, v.slots);
+    int r = 0;
+    for (u64 rem = stm_pieces(s); rem; rem &= rem - 1, r++) {
+        const int sq = gcb_lsb(rem);
+        emit_piece_moves(em, piece_code(s.b, sq), !s.stm_black, sq, slots.get(r));
+    }
+    if (s.castle & 1u) em.push(castle_action(!s.stm_black, 0));
+    if (s.castle & 2u) em.push(castle_action(!s.stm_black, 1));
 }
 
 // unpacked view of one env for export: board int8[64] (may be NULL) and info int32[16]
@@ -396,6 +464,6 @@ GCB_HD void env_export_one(const EnvView& v, int e, int8_t* board, int32_t* info
         info[0] = s.stm_black ? -1 : 1, info[1] = s.rights & RT_WK ? 1 : 0, info[2] = s.rights & RT_WQ ? 1 : 0;
         info[3] = s.rights & RT_BK ? 1 : 0, info[4] = s.rights & RT_BQ ? 1 : 0, info[5] = s.chk & 1, info[6] = (s.chk >> 1) & 1;
         info[7] = s.done, info[8] = s.move_count, info[9] = s.n_legal, info[10] = (int)v.episode[e], info[11] = s.step;
-        info[12] = s.hist_len, info[13] = 0, info[14] = 0, info[15] = 0;
+        info[12] = s.hist_len, info[13] = (int)s.castle, info[14] = 0, info[15] = 0;
     }
 }

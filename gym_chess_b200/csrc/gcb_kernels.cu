@@ -95,10 +95,18 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_unpack(int n, gcb_positions in, i
 }
 
 // ------------------------------------------------------------------------------------------------ engine kernels
+// piece slots of one thread in shared memory: slot r of thread t at base[r * GCB_BLOCK + t]
+struct SmemSlots {
+    u64* base;
+    __device__ __forceinline__ void put(int r, u64 t) { base[r * GCB_BLOCK] = t; }
+    __device__ __forceinline__ u64 get(int r) const { return base[r * GCB_BLOCK]; }
+};
+
 template <bool ATTACK>
 __global__ void __launch_bounds__(GCB_BLOCK) k_movegen(int n, gcb_positions pos, int castles_only,
                                                        uint16_t* __restrict__ actions, int stride,
                                                        int32_t* __restrict__ counts, uint8_t* __restrict__ incheck) {
+    __shared__ u64 s_slots[ATTACK ? 1 : GCB_SLOTS * GCB_BLOCK];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     ulonglong2 a = reinterpret_cast<const ulonglong2*>(pos.bb01)[i], c = reinterpret_cast<const ulonglong2*>(pos.bb23)[i];
@@ -107,8 +115,12 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_movegen(int n, gcb_positions pos,
     const u32 rights = mask_rights(b, pos.rights[i]);  // convert_py_state -> State::new, lib.rs:1267-1274
     ListWriter lw(actions + (size_t)i * stride, stride);
     bool chk = false;
-    u64 eatt;
-    gen_moves<ATTACK>(b, white, rights, lw, &eatt, &chk);
+    if (ATTACK) {
+        gen_attack_moves(b, white, lw);
+    } else {
+        SmemSlots slots = {s_slots + threadIdx.x};
+        gen_legal_list(b, white, rights, slots, lw, &chk);
+    }
     lw.flush();
     int cnt = lw.n;
     if (castles_only) {  // get_castle_moves, lib.rs:1482-1500: the castle tail of the same list
@@ -184,10 +196,15 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_step(EnvView v, StepIO io) {
 }
 
 __global__ void k_make_templates(int n, const int8_t* __restrict__ boards, ulonglong2* bb01, ulonglong2* bb23, u64* meta,
-                                 u64* zkey, uint16_t* legal, int stride) {
+                                 u64* zkey, u64* tgt, int slots) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    make_template_one(i, boards, bb01, bb23, meta, zkey, legal, stride);
+    make_template_one(i, boards, bb01, bb23, meta, zkey, tgt, slots);
+}
+
+__global__ void k_init_zobrist(u64* tab) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < GCB_ZOB_ENTRIES) fill_zobrist_entry(tab, i);
 }
 
 __global__ void __launch_bounds__(GCB_BLOCK) k_env_export(EnvView v, int8_t* __restrict__ boards, int32_t* __restrict__ info) {
@@ -208,14 +225,26 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_export(EnvView v, int8_t* __r
     }
 }
 
+// ChessEnvV2.possible_actions for every env: the reference-ordered list decoded from the resident piece slots
+__global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_list(EnvView v, uint16_t* __restrict__ actions, int stride,
+                                                              int32_t* __restrict__ counts) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.N) return;
+    ListWriter lw(actions + (size_t)e * stride, stride);
+    env_legal_list_one(v, e, lw);
+    lw.flush();
+    if (counts) counts[e] = lw.n;
+}
+
+struct MaskWriter {
+    uint8_t* m;
+    __device__ __forceinline__ void push(int action) { m[action] = 1; }
+};
 __global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_mask(EnvView v, uint8_t* __restrict__ mask) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= v.N) return;
-    int n = (int)(v.meta[e] >> M_NLEGAL_SHIFT) & 0xFFF;
-    if (n > v.stride) n = v.stride;
-    const uint16_t* l = v.legal + (size_t)e * v.stride;
-    uint8_t* m = mask + (size_t)e * 4101;
-    for (int k = 0; k < n; k++) m[l[k]] = 1;
+    MaskWriter mw = {mask + (size_t)e * 4101};
+    env_legal_list_one(v, e, mw);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -415,8 +444,7 @@ struct gcb_env {
     gcb_env_config cfg;
     EnvView v;
     ulonglong2 *t_bb01 = nullptr, *t_bb23 = nullptr;
-    u64 *t_meta = nullptr, *t_zkey = nullptr;
-    uint16_t* t_legal = nullptr;
+    u64 *t_meta = nullptr, *t_zkey = nullptr, *t_tgt = nullptr, *zob = nullptr;
     u64 tick = 0;
     // staging for the host-buffer step calls
     int32_t *d_in = nullptr, *d_reward = nullptr;
@@ -442,9 +470,9 @@ static int launch_step(gcb_env* env, const void* in, int32_t* reward, uint8_t* d
 extern "C" int gcb_env_destroy(gcb_env* env) {
     if (!env) return GCB_OK;
     cudaSetDevice(env->cfg.device);
-    cudaFree(env->v.bb01), cudaFree(env->v.bb23), cudaFree(env->v.meta), cudaFree(env->v.zkey), cudaFree(env->v.episode);
-    cudaFree(env->v.legal), cudaFree(env->v.hist), cudaFree(env->v.stats);
-    cudaFree(env->t_bb01), cudaFree(env->t_bb23), cudaFree(env->t_meta), cudaFree(env->t_zkey), cudaFree(env->t_legal);
+    cudaFree(env->v.bb01), cudaFree(env->v.bb23), cudaFree(env->v.meta), cudaFree(env->v.zkey), cudaFree(env->v.bloom);
+    cudaFree(env->v.episode), cudaFree(env->v.tgt), cudaFree(env->v.hist), cudaFree(env->v.stats);
+    cudaFree(env->t_bb01), cudaFree(env->t_bb23), cudaFree(env->t_meta), cudaFree(env->t_zkey), cudaFree(env->t_tgt), cudaFree(env->zob);
     cudaFree(env->d_in), cudaFree(env->d_reward), cudaFree(env->d_done), cudaFree(env->d_flags);
     delete env;
     return GCB_OK;
@@ -455,11 +483,24 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     if (int rc = need_gpu()) return rc;
     gcb_env_config cfg = *cfg_in;
     if (cfg.num_envs <= 0) return fail(GCB_E_ARG, "gcb_env_create", "num_envs <= 0");
-    if (cfg.legal_stride == 0) cfg.legal_stride = 144;
+    // piece slots: one per own piece of the side to move; piece counts never grow (no promotion in play, Q1)
+    {
+        int need = 16;
+        for (int t = 0; t < cfg.n_templates && cfg.template_boards; t++) {
+            int w = 0, bl = 0;
+            for (int sq = 0; sq < 64; sq++) {
+                int8_t p = cfg.template_boards[(size_t)t * 64 + sq];
+                w += p > 0, bl += p < 0;
+            }
+            need = need < w ? w : need;
+            need = need < bl ? bl : need;
+        }
+        if (cfg.piece_slots == 0) cfg.piece_slots = need;
+        if (cfg.piece_slots < need || cfg.piece_slots > 64)
+            return fail(GCB_E_ARG, "gcb_env_create", "piece_slots must be 0 (auto) or in [max pieces per side, 64]");
+    }
     if (cfg.history_cap == 0) cfg.history_cap = 512;
     if (cfg.moves_max < 0) cfg.moves_max = 149;
-    if (cfg.legal_stride < 2 || (cfg.legal_stride & 1) || cfg.legal_stride > 4094)
-        return fail(GCB_E_ARG, "gcb_env_create", "legal_stride must be even and in [2, 4094]");
     if (cfg.history_cap < 8 || cfg.history_cap > 1024 || (cfg.history_cap & (cfg.history_cap - 1)))
         return fail(GCB_E_ARG, "gcb_env_create", "history_cap must be a power of two in [8, 1024]");
     if (cfg.opponent != 0 && cfg.opponent != 1) return fail(GCB_E_ARG, "gcb_env_create", "opponent must be 0 or 1");
@@ -470,7 +511,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     CU(cudaSetDevice(cfg.device));
     gcb_env* env = new (std::nothrow) gcb_env();
     if (!env) return fail(GCB_E_NOMEM, "new", "gcb_env");
-    const int N = cfg.num_envs, T = cfg.n_templates > 0 ? cfg.n_templates : 1, S = cfg.legal_stride, H = cfg.history_cap;
+    const int N = cfg.num_envs, T = cfg.n_templates > 0 ? cfg.n_templates : 1, S = cfg.piece_slots, H = cfg.history_cap;
     env->cfg = cfg;
     env->cfg.template_boards = nullptr;
     EnvView& v = env->v;
@@ -483,15 +524,17 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     ALLOC(v.bb23, (size_t)N * 16);
     ALLOC(v.meta, (size_t)N * 8);
     ALLOC(v.zkey, (size_t)N * 8);
+    ALLOC(v.bloom, (size_t)N * 16);
     ALLOC(v.episode, (size_t)N * 4);
-    ALLOC(v.legal, (size_t)N * S * 2);
+    ALLOC(v.tgt, (size_t)N * S * 8);
     ALLOC(v.hist, (size_t)N * H * 8);
     ALLOC(v.stats, ST_COUNT * 8);
     ALLOC(env->t_bb01, (size_t)T * 16);
     ALLOC(env->t_bb23, (size_t)T * 16);
     ALLOC(env->t_meta, (size_t)T * 8);
     ALLOC(env->t_zkey, (size_t)T * 8);
-    ALLOC(env->t_legal, (size_t)T * S * 2);
+    ALLOC(env->t_tgt, (size_t)T * S * 8);
+    ALLOC(env->zob, (size_t)GCB_ZOB_ENTRIES * 8);
     ALLOC(env->d_in, (size_t)N * 4);
     ALLOC(env->d_reward, (size_t)N * 4);
     ALLOC(env->d_done, (size_t)N);
@@ -503,8 +546,9 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
         gcb_env_destroy(env);
         return fail(GCB_E_NOMEM, "cudaMalloc", cudaGetErrorString(e));
     }
-    v.t_bb01 = env->t_bb01, v.t_bb23 = env->t_bb23, v.t_meta = env->t_meta, v.t_zkey = env->t_zkey, v.t_legal = env->t_legal;
-    v.seed = cfg.seed, v.N = N, v.stride = S, v.hist_mask = H - 1, v.n_templates = T, v.env_offset = cfg.env_id_offset;
+    v.t_bb01 = env->t_bb01, v.t_bb23 = env->t_bb23, v.t_meta = env->t_meta, v.t_zkey = env->t_zkey, v.t_tgt = env->t_tgt;
+    v.zob = env->zob;
+    v.seed = cfg.seed, v.N = N, v.slots = S, v.hist_mask = H - 1, v.n_templates = T, v.env_offset = cfg.env_id_offset;
     v.moves_max = cfg.moves_max, v.opponent = cfg.opponent, v.agent_black = cfg.agent_black, v.auto_reset = cfg.auto_reset;
     v.pps = 1 + (cfg.opponent == 1 ? 1 : 0);  // ring slots per step: agent ply, bot ply (a reset-bot ply reuses the bot slot)
     int rc = GCB_OK;
@@ -514,12 +558,14 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
             cudaMemset(v.stats, 0, ST_COUNT * 8) != cudaSuccess || cudaMemset(v.episode, 0, (size_t)N * 4) != cudaSuccess ||
             cudaMemset(v.meta, 0, (size_t)N * 8) != cudaSuccess || cudaMemset(v.bb01, 0, (size_t)N * 16) != cudaSuccess ||
             cudaMemset(v.bb23, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.zkey, 0, (size_t)N * 8) != cudaSuccess ||
-            cudaMemset(env->t_legal, 0, (size_t)T * S * 2) != cudaSuccess) {
+            cudaMemset(v.bloom, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
+            cudaMemset(env->t_tgt, 0, (size_t)T * S * 8) != cudaSuccess) {
             rc = fail(GCB_E_CUDA, "cudaMemcpy/cudaMemset", "env init");
             break;
         }
-        k_make_templates<<<(T + 63) / 64, 64>>>(T, d_tb, env->t_bb01, env->t_bb23, env->t_meta, env->t_zkey, env->t_legal, S);
-        g_launches.fetch_add(1);
+        k_init_zobrist<<<(GCB_ZOB_ENTRIES + 127) / 128, 128>>>(env->zob);
+        k_make_templates<<<(T + 63) / 64, 64>>>(T, d_tb, env->t_bb01, env->t_bb23, env->t_meta, env->t_zkey, env->t_tgt, S);
+        g_launches.fetch_add(2);
         // episode 0 starts with a reset that does not advance the episode counter
         StepIO io;
         memset(&io, 0, sizeof(io));
@@ -617,10 +663,18 @@ extern "C" int gcb_env_legal_mask(gcb_env* env, uint8_t* d_mask, void* stream) {
     return GCB_OK;
 }
 
-extern "C" int gcb_env_legal_ptr(gcb_env* env, uint16_t** d_legal, int32_t* stride) {
-    if (!env) return fail(GCB_E_ARG, "gcb_env_legal_ptr", "null env");
-    if (d_legal) *d_legal = env->v.legal;
-    if (stride) *stride = env->v.stride;
+extern "C" int gcb_env_legal_actions(gcb_env* env, uint16_t* d_actions, int stride, int32_t* d_counts, void* stream) {
+    ENV_CHECK(env);
+    if (!d_actions || stride <= 0 || (stride & 1)) return fail(GCB_E_ARG, "gcb_env_legal_actions", "null pointer or odd stride");
+    k_env_legal_list<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, d_actions, stride, d_counts);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_piece_slots(gcb_env* env, uint64_t** d_slots, int32_t* n_slots) {
+    if (!env) return fail(GCB_E_ARG, "gcb_env_piece_slots", "null env");
+    if (d_slots) *d_slots = reinterpret_cast<uint64_t*>(env->v.tgt);
+    if (n_slots) *n_slots = env->v.slots;
     return GCB_OK;
 }
 

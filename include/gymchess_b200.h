@@ -121,7 +121,8 @@ typedef struct {
     int32_t opponent;       /* 0 = "none" (self-play, one ply per step), 1 = "random" (bot replies inside step) */
     int32_t agent_black;    /* player_color == "BLACK": the bot opens at reset (chess_v2.py:208-216) */
     int32_t auto_reset;     /* reset an env in the same step in which it terminates (done | cap | wedged) */
-    int32_t legal_stride;   /* capacity of the per-env legal list (even; default 144 when 0) */
+    int32_t piece_slots;    /* slots of the per-env legal set (one 64-bit target set per own piece of the side to
+                               move); 0 = auto = max(16, most pieces of one colour on any initial board) */
     int32_t history_cap;    /* slots of the per-env Zobrist ring (power of two; default 512 when 0) */
     int32_t moves_max;      /* 149 in the reference (chess_v2.py:141); <0 selects 149 */
     int32_t n_templates;    /* number of initial boards (0 = the default start position) */
@@ -140,7 +141,7 @@ int gcb_env_reset(gcb_env *env, const uint8_t *d_mask, void *stream);
  * d_reward int32[N] (the two float 0.0 literals are 0), d_done uint8[N], d_flags uint8[N] (GCB_F_*). */
 int gcb_env_step(gcb_env *env, const int32_t *d_actions, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
                  void *stream);
-/* same, but env i plays legal[i][(u32[i] * n_legal[i]) >> 32] (RESIGN when it has no legal move): the uniform
+/* same, but env i plays possible_actions[i][(u32[i] * n_legal[i]) >> 32] (RESIGN when it has no legal move): the uniform
  * draw of make_random_policy (chess_v2.py:116-127) with caller-provided random words */
 int gcb_env_step_index(gcb_env *env, const uint32_t *d_u32, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
                        void *stream);
@@ -157,18 +158,24 @@ int gcb_env_step_index_host(gcb_env *env, const uint32_t *u32, int32_t *reward, 
 /* observation / state export (device pointers, any may be NULL):
  *   d_boards int8[N][64]   -- `state["board"]`, the Box(-6,6,(8,8)) observation
  *   d_info   int32[N][16]  -- current_player(+1/-1), wk, wq, bk, bq, wchk, bchk, done, move_count, n_legal,
- *                             episode, step_in_episode, hist_len, 0, 0, 0 */
+ *                             episode, step_in_episode, hist_len, castle bits (1 queen side | 2 king side), 0, 0 */
 int gcb_env_export(gcb_env *env, int8_t *d_boards, int32_t *d_info, void *stream);
 /* legal action mask uint8[N][4101] (possible_actions as a mask) */
 int gcb_env_legal_mask(gcb_env *env, uint8_t *d_mask, void *stream);
-/* zero-copy views of the resident state */
-int gcb_env_legal_ptr(gcb_env *env, uint16_t **d_legal, int32_t *stride);
-int gcb_env_positions(gcb_env *env, gcb_positions *out); /* player/rights pointers are NULL: they live in meta */
+/* ChessEnvV2.possible_actions (chess_v2.py:333-335) of every env: d_actions uint16[N][stride] receives the list in
+ * the reference's order (normal moves in generation order, then castles), d_counts int32[N] (may be NULL) the true
+ * count.  Like the reference's property, the list is DERIVED on access: the resident form of possible_moves is one
+ * 64-bit legal-target set per own piece (gcb_env_piece_slots) and the list is a pure decode of (board, slots). */
+int gcb_env_legal_actions(gcb_env *env, uint16_t *d_actions, int stride, int32_t *d_counts, void *stream);
+/* zero-copy views of the resident state: slots uint64[n_slots][N] (slot r of env e at [r][e] = legal targets of the
+ * r-th piece, in ascending square order, of the side to move); positions (player/rights are NULL: they live in meta) */
+int gcb_env_piece_slots(gcb_env *env, uint64_t **d_slots, int32_t *n_slots);
+int gcb_env_positions(gcb_env *env, gcb_positions *out);
 
 /* episode statistics accumulated on the device since the last gcb_env_stats_reset:
  * out uint64[16] = steps, plies, episodes, mates, repetitions, caps, wedged, invalid, reward_sum (two's complement
- * int64), legal_sum, in_check, hist_overflow, list_overflow, hist_scanned (ring entries read by the repetition
- * scans), 0, 0.   Synchronises the stream. */
+ * int64), legal_sum, in_check, hist_overflow, slot_overflow, hist_scanned (ring entries actually read by the
+ * repetition scans), hist_window (sum over plies of the repetition window length), 0.   Synchronises the stream. */
 int gcb_env_stats(gcb_env *env, uint64_t *out16, void *stream);
 int gcb_env_stats_reset(gcb_env *env, void *stream);
 /* device pointer to the 16 counters (for an NCCL reduce by the caller) */

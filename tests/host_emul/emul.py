@@ -91,8 +91,11 @@ class EmulEnv:
             nt = len(tb)
         self._tb = tb
         self.N, self.stride = num_envs, legal_stride
+        slots = 16
+        if tb is not None:
+            slots = max(16, int(max((tb > 0).sum(1).max(), (tb < 0).sum(1).max())))
         self._h = lib().emul_env_create(num_envs, env_id_offset, seed, {"none": 0, "random": 1}[opponent],
-                                        int(player_color == "BLACK"), int(auto_reset), legal_stride, history_cap, moves_max,
+                                        int(player_color == "BLACK"), int(auto_reset), slots, history_cap, moves_max,
                                         nt, _p(tb))
 
     def __del__(self):

@@ -9,6 +9,12 @@
 
 extern "C" {
 
+struct LocalSlots {
+    u64 t[GCB_SLOTS];
+    void put(int r, u64 v) { t[r] = v; }
+    u64 get(int r) const { return t[r]; }
+};
+
 void emul_movegen(int n, const int8_t* boards, const int8_t* players, const uint8_t* rights4, int attack, int castles_only,
                   uint16_t* out, int stride, int32_t* counts, uint8_t* incheck) {
     for (int i = 0; i < n; i++) {
@@ -18,9 +24,9 @@ void emul_movegen(int n, const int8_t* boards, const int8_t* players, const uint
         rights = mask_rights(b, rights);
         ListWriter lw(out + (size_t)i * stride, stride);
         bool chk = false;
-        u64 eatt;
-        if (attack) gen_moves<true>(b, players[i] > 0, rights, lw, &eatt, &chk);
-        else gen_moves<false>(b, players[i] > 0, rights, lw, &eatt, &chk);
+        LocalSlots slots;
+        if (attack) gen_attack_moves(b, players[i] > 0, lw);
+        else gen_legal_list(b, players[i] > 0, rights, slots, lw, &chk);
         lw.flush();
         int cnt = lw.n;
         if (castles_only) {
@@ -78,18 +84,17 @@ struct EmulEnv {
     EnvView v;
     u64 tick;
     ulonglong2 *t_bb01, *t_bb23;
-    u64 *t_meta, *t_zkey;
-    uint16_t* t_legal;
+    u64 *t_meta, *t_zkey, *t_tgt, *zob;
 };
 
 void emul_env_destroy(EmulEnv* E) {
     if (!E) return;
-    free(E->v.bb01), free(E->v.bb23), free(E->v.meta), free(E->v.zkey), free(E->v.episode), free(E->v.legal), free(E->v.hist);
-    free(E->v.stats), free(E->t_bb01), free(E->t_bb23), free(E->t_meta), free(E->t_zkey), free(E->t_legal);
+    free(E->v.bb01), free(E->v.bb23), free(E->v.meta), free(E->v.zkey), free(E->v.bloom), free(E->v.episode), free(E->v.tgt);
+    free(E->v.hist), free(E->v.stats), free(E->t_bb01), free(E->t_bb23), free(E->t_meta), free(E->t_zkey), free(E->t_tgt), free(E->zob);
     free(E);
 }
 
-EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent, int agent_black, int auto_reset, int stride,
+EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent, int agent_black, int auto_reset, int slots,
                          int hist_cap, int moves_max, int n_templates, const int8_t* template_boards) {
     static const int8_t def[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6, -6, -6, -6, -6, -6, -6, 0, 0, 0, 0, 0, 0,
                                    0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0, 0, 0, 0, 0, 0,
@@ -99,20 +104,24 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
     EnvView& v = E->v;
     v.bb01 = (ulonglong2*)calloc(N, 16), v.bb23 = (ulonglong2*)calloc(N, 16);
     v.meta = (u64*)calloc(N, 8), v.zkey = (u64*)calloc(N, 8), v.episode = (u32*)calloc(N, 4);
-    v.legal = (uint16_t*)calloc((size_t)N * stride, 2), v.hist = (u64*)calloc((size_t)N * hist_cap, 8);
+    v.bloom = (ulonglong2*)calloc(N, 16);
+    v.tgt = (u64*)calloc((size_t)N * slots, 8), v.hist = (u64*)calloc((size_t)N * hist_cap, 8);
     v.stats = (u64*)calloc(ST_COUNT, 8);
     E->t_bb01 = (ulonglong2*)calloc(T, 16), E->t_bb23 = (ulonglong2*)calloc(T, 16);
-    E->t_meta = (u64*)calloc(T, 8), E->t_zkey = (u64*)calloc(T, 8), E->t_legal = (uint16_t*)calloc((size_t)T * stride, 2);
-    v.t_bb01 = E->t_bb01, v.t_bb23 = E->t_bb23, v.t_meta = E->t_meta, v.t_zkey = E->t_zkey, v.t_legal = E->t_legal;
-    v.seed = seed, v.N = N, v.stride = stride, v.hist_mask = hist_cap - 1, v.n_templates = T, v.env_offset = env_offset;
+    E->t_meta = (u64*)calloc(T, 8), E->t_zkey = (u64*)calloc(T, 8), E->t_tgt = (u64*)calloc((size_t)T * slots, 8);
+    E->zob = (u64*)calloc(GCB_ZOB_ENTRIES, 8);
+    for (int i = 0; i < GCB_ZOB_ENTRIES; i++) fill_zobrist_entry(E->zob, i);
+    v.t_bb01 = E->t_bb01, v.t_bb23 = E->t_bb23, v.t_meta = E->t_meta, v.t_zkey = E->t_zkey, v.t_tgt = E->t_tgt, v.zob = E->zob;
+    v.seed = seed, v.N = N, v.slots = slots, v.hist_mask = hist_cap - 1, v.n_templates = T, v.env_offset = env_offset;
     v.moves_max = moves_max, v.opponent = opponent, v.agent_black = agent_black, v.auto_reset = auto_reset;
     v.pps = 1 + (opponent == 1);
     for (int i = 0; i < T; i++)
-        make_template_one(i, n_templates > 0 ? template_boards : def, E->t_bb01, E->t_bb23, E->t_meta, E->t_zkey, E->t_legal, stride);
+        make_template_one(i, n_templates > 0 ? template_boards : def, E->t_bb01, E->t_bb23, E->t_meta, E->t_zkey, E->t_tgt, slots);
     StepIO io;
     memset(&io, 0, sizeof(io));
     io.tick = E->tick++;
     StepStats st;
+    memset(&st, 0, sizeof(st));
     for (int e = 0; e < N; e++) env_step_one<MODE_RESET>(v, io, e, st);
     return E;
 }
@@ -141,8 +150,11 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
 void emul_env_export(EmulEnv* E, int8_t* boards, int32_t* info, uint16_t* legal, int legal_stride) {
     for (int e = 0; e < E->v.N; e++) {
         env_export_one(E->v, e, boards ? boards + (size_t)e * 64 : nullptr, info ? info + (size_t)e * 16 : nullptr);
-        if (legal)
-            for (int k = 0; k < legal_stride && k < E->v.stride; k++) legal[(size_t)e * legal_stride + k] = E->v.legal[(size_t)e * E->v.stride + k];
+        if (legal) {  // possible_actions: decode of the piece slots
+            ListWriter lw(legal + (size_t)e * legal_stride, legal_stride);
+            env_legal_list_one(E->v, e, lw);
+            lw.flush();
+        }
     }
 }
 

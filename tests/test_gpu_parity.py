@@ -197,7 +197,7 @@ def test_full_size_properties():
     assert torch.equal(back, boards)
     st = env.stats()
     assert st["steps"] == N * 64 and st["episodes"] == st["mates"] + st["repetitions"] + st["caps"] + st["wedged"]
-    assert st["hist_overflow"] == 0 and st["list_overflow"] == 0
+    assert st["hist_overflow"] == 0 and st["slot_overflow"] == 0
     # a sample of the 1M positions against the oracle
     idx = torch.randint(0, N, (4096,), device=dev)
     hb, hp, hr = boards[idx].cpu().numpy(), players[idx].cpu().numpy(), rights[idx].cpu().numpy()
