@@ -10,7 +10,8 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SO_PATH = os.path.join(_PKG, "libgymchess_b200.so")
+# GYMCHESS_B200_LIB selects another build of the same library (used to A/B kernel variants on the GPU box)
+SO_PATH = os.environ.get("GYMCHESS_B200_LIB") or os.path.join(_PKG, "libgymchess_b200.so")
 _CSRC = os.path.join(_PKG, "csrc")
 
 NVCC_FLAGS = [
@@ -91,7 +92,7 @@ SIGNATURES = {
     "gcb_env_positions": (i32, [vp, C.POINTER(Positions)]),
     "gcb_env_stats": (i32, [vp, vp, vp]),
     "gcb_env_stats_reset": (i32, [vp, vp]),
-    "gcb_env_stats_ptr": (i32, [vp, C.POINTER(vp)]),
+    "gcb_env_stats_ptr": (i32, [vp, C.POINTER(vp), vp]),
 }
 
 _lib = None

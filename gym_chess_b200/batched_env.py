@@ -211,8 +211,8 @@ class BatchedChessEnv:
     def stats_tensor(self):
         """zero-copy int64 [16] view of the device counters (for an NCCL reduce)."""
         ptr = C.c_void_p()
-        check(_lib.lib().gcb_env_stats_ptr(self._h, C.byref(ptr)))
         with torch.cuda.device(self.device):
+            check(_lib.lib().gcb_env_stats_ptr(self._h, C.byref(ptr), _stream_ptr()))
             return torch.as_tensor(_DevArray(ptr.value, (16,), "<i8"), device=self.device)
 
     def reset_stats(self):

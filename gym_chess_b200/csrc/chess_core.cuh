@@ -57,6 +57,7 @@ GCB_HD int gcb_popc(u64 x) {
     return __builtin_popcountll(x);
 #endif
 }
+GCB_HD u64 gcb_rotl64(u64 x, int k) { return (x << (k & 63)) | (x >> ((64 - k) & 63)); }  // 0 < k < 64
 GCB_HD u32 gcb_umulhi(u32 a, u32 b) {
 #if defined(__CUDA_ARCH__)
     return __umulhi(a, b);
@@ -334,15 +335,11 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     }
 }
 
-// legality mask of a NON-king piece standing on `sq`
-GCB_HD u64 nonking_mask(const GenCtx& g, int sq, u64 bit) {
-    u64 m = g.cm;
-    if (g.pinned & bit) {
-        const u64 kbit = 1ULL << g.ksq;
-        const u64 side = sq > g.ksq ? ~(kbit | (kbit - 1)) : (kbit - 1);
-        m &= g.pinrays & line_through(g.ksq, sq) & side;
-    }
-    return m;
+// the squares a pinned piece on `sq` may move to: its own pin ray (between(king, pinner) | pinner)
+GCB_HD u64 pin_mask(const GenCtx& g, int sq) {
+    const u64 kbit = 1ULL << g.ksq;
+    const u64 side = sq > g.ksq ? ~(kbit | (kbit - 1)) : (kbit - 1);
+    return g.pinrays & line_through(g.ksq, sq) & side;
 }
 
 // Targets of every own piece in `subset` (a set of squares; the caller passes all own pieces, or a
@@ -364,28 +361,28 @@ GCB_HD int gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         const int sq = gcb_lsb(s);
         const u64 bit = 1ULL << sq, a = rook_att(sq, occ);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & nonking_mask(g, sq, bit));
+        GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // bishops
     for (u64 s = g.bishops & mine; s; s &= s - 1) {
         const int sq = gcb_lsb(s);
         const u64 bit = 1ULL << sq, a = bishop_att(sq, occ);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & nonking_mask(g, sq, bit));
+        GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // queens
     for (u64 s = g.queens & mine; s; s &= s - 1) {
         const int sq = gcb_lsb(s);
         const u64 bit = 1ULL << sq, a = rook_att(sq, occ) | bishop_att(sq, occ);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & nonking_mask(g, sq, bit));
+        GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // knights
     for (u64 s = g.knights & mine; s; s &= s - 1) {
         const int sq = gcb_lsb(s);
         const u64 bit = 1ULL << sq, a = knight_set_att(bit);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & nonking_mask(g, sq, bit));
+        GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // kings: never passed through the legality filter (lib.rs:615-619); attack map with the king on it (Q6)
     for (u64 s = g.kings & mine; s; s &= s - 1) {
@@ -403,18 +400,26 @@ GCB_HD int gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         for (u64 s = pw; s; s &= s - 1) {
             const int sq = gcb_lsb(s);
             const u64 bit = 1ULL << sq;
-            u64 push, cap;
-            if (g.white) {
-                push = (bit >> 8) | ((bit & 0x00FF000000000000ULL) >> 16);
-                cap = ((bit & ~GCB_FILE_H) >> 7) | ((bit & ~GCB_FILE_A) >> 9);
-            } else {
-                push = (bit << 8) | ((bit & 0x000000000000FF00ULL) << 16);
-                cap = ((bit & ~GCB_FILE_H) << 9) | ((bit & ~GCB_FILE_A) << 7);
-            }
-            GCB_PUT(sq, bit, ((push & ~occ) | (cap & g.enemy)) & nonking_mask(g, sq, bit));
+            // colour-agnostic: a rotation by 56 is a shift down by 8 for every row but row 0 (masked out), so the
+            // white and black pawns of a warp run the same instructions
+            const int fwd = g.white ? 56 : 8;
+            const u64 last = g.white ? 0x00000000000000FFULL : 0xFF00000000000000ULL;   // no step from the last row
+            const u64 start = g.white ? 0x00FF000000000000ULL : 0x000000000000FF00ULL;  // two steps from here
+            const u64 one = gcb_rotl64(bit & ~last, fwd);
+            const u64 push = one | gcb_rotl64(gcb_rotl64(bit & start, fwd), fwd);
+            const u64 cap = ((one & ~GCB_FILE_H) << 1) | ((one & ~GCB_FILE_A) >> 1);
+            GCB_PUT(sq, bit, ((push & ~occ) | (cap & g.enemy)) & g.cm);
         }
     }
 #undef GCB_PUT
+    // pinned pieces (rare per position, but some env of a warp nearly always has one): one fix-up pass over the
+    // slots instead of a pin test at every generation site
+    for (u64 p = g.pinned & mine & ~g.kings; p; p &= p - 1) {
+        const int sq = gcb_lsb(p), r = gcb_popc(mine & ((1ULL << sq) - 1));
+        const u64 t = sink.get(r), t2 = t & pin_mask(g, sq);
+        sink.replace(r, t, t2);
+        total -= gcb_popc(t ^ t2);
+    }
     return total;
 }
 

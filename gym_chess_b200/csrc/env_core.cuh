@@ -11,6 +11,9 @@
 //   bloom[N] ulonglong2               16 B   two 64-bit Bloom words over the repetition window: key seen once /
 //                                            seen twice; the ring is only scanned when the second one hits
 //   episode[N] u32                     4 B
+//   cnt[N]   ulonglong2               16 B   byte r = number of legal targets of the r-th own piece (r < 16): the
+//                                            uniform draw over the ordered list finds its piece from this one record
+//                                            and then reads a single slot
 //   tgt[S][N] u64                            the cached legal set = ChessEnvV2.possible_moves: slot r = legal
 //                                            targets of the r-th own piece of the side to move (ascending square
 //                                            order = the reference's scan order); castles are two bits of meta.
@@ -75,6 +78,7 @@ struct EnvView {
     u64* zkey;
     ulonglong2* bloom;
     u32* episode;
+    ulonglong2* cnt;
     u64* tgt;
     u64* hist;
     const ulonglong2* t_bb01;
@@ -82,8 +86,10 @@ struct EnvView {
     const u64* t_meta;
     const u64* t_zkey;
     const u64* t_tgt;
+    const ulonglong2* t_cnt;
     const u64* zob;
-    u64* stats;
+    u64* stats;      // [ST_COUNT] totals (written by the reduction of stat_rows)
+    u64* stat_rows;  // [ceil(N/32)][ST_COUNT] per-warp accumulators: no atomics, no block barrier in the step kernel
     u64 seed;
     int N, slots, hist_mask, n_templates;
     u32 env_offset;
@@ -92,7 +98,7 @@ struct EnvView {
 
 struct EnvRegs {
     Board b;
-    u64 zk, seen1, seen2;
+    u64 zk, seen1, seen2, cnt_lo, cnt_hi;
     u32 rights, chk, castle;  // chk bit0 white checked, bit1 black checked; castle bit0 queen side, bit1 king side
     int stm_black, done, n_legal, move_count, step, hist_len;
 };
@@ -119,16 +125,27 @@ GCB_HD bool stm_checked(const EnvRegs& s) { return (s.chk >> s.stm_black) & 1u; 
 GCB_HD u64 stm_pieces(const EnvRegs& s) { return s.stm_black ? (bb_occ(s.b) & ~s.b.w) : s.b.w; }
 
 // piece slots of env e in the resident array (slot r of env e at tgt[r*N + e]: coalesced when a warp reads slot r)
+// plus the per-piece target counts of the first 16 slots, one byte each
 struct TgtSink {
     u64* base;
     size_t N;
     int slots, dropped;
-    GCB_HD TgtSink(u64* tgt, int n, int e, int s) : base(tgt + e), N((size_t)n), slots(s), dropped(0) {}
+    u64 cnt_lo, cnt_hi;
+    GCB_HD TgtSink(u64* tgt, int n, int e, int s) : base(tgt + e), N((size_t)n), slots(s), dropped(0), cnt_lo(0), cnt_hi(0) {}
+    GCB_HD void add_count(int r, u64 c) {
+        if (r < 8) cnt_lo += c << (8 * r);
+        else if (r < 16) cnt_hi += c << (8 * (r - 8));
+    }
     GCB_HD void put(int r, u64 t) {
         if (r < slots) base[(size_t)r * N] = t;
         else dropped++;
+        add_count(r, (u64)gcb_popc(t));
     }
     GCB_HD u64 get(int r) const { return r < slots ? base[(size_t)r * N] : 0ULL; }
+    GCB_HD void replace(int r, u64 told, u64 tnew) {  // tnew is a subset of told
+        if (r < slots) base[(size_t)r * N] = tnew;
+        add_count(r, (u64)0 - (u64)gcb_popc(told ^ tnew));  // the byte never underflows: no borrow leaves it
+    }
 };
 
 // history ring bookkeeping: `cursor` = next slot of this tick; hist_len = length of the contiguous
@@ -152,19 +169,38 @@ GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, in
 // The action `possible_moves[idx]` of the reference-ordered list, decoded from the slots (chess_v2.py:116-127:
 // the uniform draw indexes the ORDERED list).  idx < n_legal.
 GCB_HD int action_at(const EnvView& v, int e, const EnvRegs& s, int idx) {
+    // which piece: prefix scan over the 16 count bytes (registers only); pieces beyond 16 (only on crafted initial
+    // boards) by reading their slots
+    int acc = 0, hit_r = -1, hit_idx = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 16; r++) {
+        const int c = (int)(((r < 8 ? s.cnt_lo : s.cnt_hi) >> (8 * (r & 7))) & 0xFF);
+        if (hit_r < 0 && idx - acc < c) hit_r = r, hit_idx = idx - acc;
+        acc += c;
+    }
     TgtSink slots(v.tgt, v.N, e, v.slots);
-    int r = 0;
-    for (u64 rem = stm_pieces(s); rem; rem &= rem - 1, r++) {
-        const u64 T = slots.get(r);
-        const int c = gcb_popc(T);
-        if (idx < c) {
-            const int sq = gcb_lsb(rem);
-            return sq * 64 + nth_target(piece_code(s.b, sq), !s.stm_black, sq, T, idx);
+    u64 own = stm_pieces(s);
+    if (v.slots > 16 && hit_r < 0) {
+        const int np = gcb_popc(own);
+        for (int r = 16; r < np && hit_r < 0; r++) {
+            const int c = gcb_popc(slots.get(r));
+            if (idx - acc < c) hit_r = r, hit_idx = idx - acc;
+            else acc += c;
         }
-        idx -= c;
+    }
+    if (hit_r >= 0) {
+        const u64 T = slots.get(hit_r);  // the one slot this draw needs
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int i = 0; i < hit_r; i++) own &= own - 1;
+        const int sq = gcb_lsb(own);
+        return sq * 64 + nth_target(piece_code(s.b, sq), !s.stm_black, sq, T, hit_idx);
     }
     // castles come last, queen side first (lib.rs:1473-1479, 992, 1011)
-    const int king_side = (s.castle & 1u) ? (idx != 0) : 1;
+    const int king_side = (s.castle & 1u) ? (idx - acc != 0) : 1;
     return castle_action(!s.stm_black, king_side);
 }
 
@@ -204,7 +240,21 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
         const u64 bbit = 1ULL << (key >> 58);
         int cnt = 0;
         if (s.seen2 & bbit) {
-            for (int j = 1; j <= s.hist_len; j++) cnt += (v.hist[((cur - j) & (u64)v.hist_mask) * (u64)v.N + e] == key);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j0 = 1; j0 <= s.hist_len; j0 += 8) {  // 8 independent loads in flight
+                u64 h[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int i = 0; i < 8; i++)
+                    h[i] = (j0 + i <= s.hist_len) ? v.hist[((cur - (u64)(j0 + i)) & (u64)v.hist_mask) * (u64)v.N + e] : 0ULL;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int i = 0; i < 8; i++) cnt += (h[i] == key);
+            }
             st.v[ST_HISTSCAN] += s.hist_len;
         }
         st.v[ST_WINDOW] += s.hist_len;
@@ -229,6 +279,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
     TgtSink sink(v.tgt, v.N, e, v.slots);
     const int n = gen_targets(s.b, g, g.own, sink);
     if (sink.dropped) st.v[ST_SLOTOVF] += 1;
+    s.cnt_lo = sink.cnt_lo, s.cnt_hi = sink.cnt_hi;
     s.castle = gen_castles(s.b, g, mask_rights(s.b, s.rights));
     s.n_legal = n + (int)(s.castle & 1u) + (int)(s.castle >> 1);
     // both check flags (update_state, lib.rs:1386-1393): the side to move from the attackers of its king
@@ -261,8 +312,8 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     {
         ulonglong2 a = v.bb01[e], c = v.bb23[e];
         s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
-        ulonglong2 bl = v.bloom[e];
-        s.seen1 = bl.x, s.seen2 = bl.y;
+        ulonglong2 bl = v.bloom[e], ct = v.cnt[e];
+        s.seen1 = bl.x, s.seen2 = bl.y, s.cnt_lo = ct.x, s.cnt_hi = ct.y;
     }
     unpack_meta(v.meta[e], s);
     s.zk = v.zkey[e];
@@ -345,6 +396,10 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
                 unpack_meta(v.t_meta[t], s);
                 s.zk = v.t_zkey[t];
                 s.seen1 = 0, s.seen2 = 0;
+                {
+                    ulonglong2 ct = v.t_cnt[t];
+                    s.cnt_lo = ct.x, s.cnt_hi = ct.y;
+                }
                 const int np = gcb_popc(s.b.w);  // White is to move in every initial state
                 const u64* ts = v.t_tgt + (size_t)t * v.slots;
                 for (int r = 0; r < np && r < v.slots; r++) v.tgt[(size_t)r * v.N + e] = ts[r];
@@ -407,6 +462,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     v.bb01[e] = make_ulonglong2(s.b.t0, s.b.t1);
     v.bb23[e] = make_ulonglong2(s.b.t2, s.b.w);
     v.bloom[e] = make_ulonglong2(s.seen1, s.seen2);
+    v.cnt[e] = make_ulonglong2(s.cnt_lo, s.cnt_hi);
     v.meta[e] = pack_meta(s);
     v.zkey[e] = s.zk;
     v.episode[e] = ep;
@@ -414,7 +470,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
 
 // initial state of one template board (ChessEnvV2.reset up to the first movegen, chess_v2.py:188-206)
 GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulonglong2* bb23, u64* meta, u64* zkey,
-                              u64* tgt, int slots) {
+                              u64* tgt, ulonglong2* cnt, int slots) {
     Board b = board_from_mailbox(boards + (size_t)i * 64);
     EnvRegs s;
     s.b = b;
@@ -429,6 +485,7 @@ GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulo
     const int n = gen_targets(b, g, g.own, sink);
     s.castle = gen_castles(b, g, s.rights);
     s.n_legal = n + (int)(s.castle & 1u) + (int)(s.castle >> 1);
+    cnt[i] = make_ulonglong2(sink.cnt_lo, sink.cnt_hi);
     bb01[i] = make_ulonglong2(b.t0, b.t1);
     bb23[i] = make_ulonglong2(b.t2, b.w);
     meta[i] = pack_meta(s);

@@ -43,6 +43,9 @@ extern "C" int gcb_device_count(void) {
 }
 
 #define GCB_BLOCK 128
+#ifndef GCB_STEP_MIN_BLOCKS
+#define GCB_STEP_MIN_BLOCKS 5
+#endif
 static inline int grid_for(int n) { return (n + GCB_BLOCK - 1) / GCB_BLOCK; }
 
 // ------------------------------------------------------------------------------------------------ pack / unpack
@@ -100,6 +103,7 @@ struct SmemSlots {
     u64* base;
     __device__ __forceinline__ void put(int r, u64 t) { base[r * GCB_BLOCK] = t; }
     __device__ __forceinline__ u64 get(int r) const { return base[r * GCB_BLOCK]; }
+    __device__ __forceinline__ void replace(int r, u64, u64 t) { base[r * GCB_BLOCK] = t; }
 };
 
 template <bool ATTACK>
@@ -170,12 +174,7 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(GCB_BLOCK) k_env_step(EnvView v, StepIO io) {
-    __shared__ unsigned long long s_stats[ST_COUNT];
-    if (MODE != MODE_RESET) {
-        if (threadIdx.x < ST_COUNT) s_stats[threadIdx.x] = 0;
-        __syncthreads();
-    }
+__global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     StepStats st;
 #pragma unroll
@@ -184,22 +183,39 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_step(EnvView v, StepIO io) {
     if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;
     if (active) env_step_one<MODE>(v, io, e, st);
     if (MODE != MODE_RESET) {
-        // episode statistics: warp reduce -> shared atomics -> one global atomic per counter per block
+        // episode statistics: warp reduce (REDUX), lane k keeps counter k, one coalesced read-modify-write of the
+        // warp's own row -- no atomics and no block barrier
+        const int lane = threadIdx.x & 31;
+        long long mine = 0;
 #pragma unroll
         for (int k = 0; k < ST_USED; k++) {
-            int t = __reduce_add_sync(0xffffffffu, st.v[k]);
-            if ((threadIdx.x & 31) == 0 && t) atomicAdd(&s_stats[k], (unsigned long long)(long long)t);
+            const int t = __reduce_add_sync(0xffffffffu, st.v[k]);
+            if (lane == k) mine = t;
         }
-        __syncthreads();
-        if (threadIdx.x < ST_USED && s_stats[threadIdx.x]) atomicAdd((unsigned long long*)&v.stats[threadIdx.x], s_stats[threadIdx.x]);
+        if (lane < ST_USED) v.stat_rows[(size_t)(e >> 5) * ST_COUNT + lane] += (u64)mine;
+    }
+}
+
+// totals = column sums of the per-warp rows (one block; deterministic order)
+__global__ void k_stats_reduce(const u64* __restrict__ rows, int nrows, u64* __restrict__ out) {
+    __shared__ u64 s[32][ST_COUNT + 1];
+    const int k = threadIdx.x & 15, part = threadIdx.x >> 4;  // 512 threads: 32 partial sums per counter
+    u64 acc = 0;
+    for (int r = part; r < nrows; r += 32) acc += rows[(size_t)r * ST_COUNT + k];
+    s[part][k] = acc;
+    __syncthreads();
+    if (threadIdx.x < ST_COUNT) {
+        u64 t = 0;
+        for (int p = 0; p < 32; p++) t += s[p][threadIdx.x];
+        out[threadIdx.x] = t;
     }
 }
 
 __global__ void k_make_templates(int n, const int8_t* __restrict__ boards, ulonglong2* bb01, ulonglong2* bb23, u64* meta,
-                                 u64* zkey, u64* tgt, int slots) {
+                                 u64* zkey, u64* tgt, ulonglong2* cnt, int slots) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    make_template_one(i, boards, bb01, bb23, meta, zkey, tgt, slots);
+    make_template_one(i, boards, bb01, bb23, meta, zkey, tgt, cnt, slots);
 }
 
 __global__ void k_init_zobrist(u64* tab) {
@@ -445,6 +461,7 @@ struct gcb_env {
     EnvView v;
     ulonglong2 *t_bb01 = nullptr, *t_bb23 = nullptr;
     u64 *t_meta = nullptr, *t_zkey = nullptr, *t_tgt = nullptr, *zob = nullptr;
+    ulonglong2* t_cnt = nullptr;
     u64 tick = 0;
     // staging for the host-buffer step calls
     int32_t *d_in = nullptr, *d_reward = nullptr;
@@ -470,8 +487,8 @@ static int launch_step(gcb_env* env, const void* in, int32_t* reward, uint8_t* d
 extern "C" int gcb_env_destroy(gcb_env* env) {
     if (!env) return GCB_OK;
     cudaSetDevice(env->cfg.device);
-    cudaFree(env->v.bb01), cudaFree(env->v.bb23), cudaFree(env->v.meta), cudaFree(env->v.zkey), cudaFree(env->v.bloom);
-    cudaFree(env->v.episode), cudaFree(env->v.tgt), cudaFree(env->v.hist), cudaFree(env->v.stats);
+    cudaFree(env->v.bb01), cudaFree(env->v.bb23), cudaFree(env->v.meta), cudaFree(env->v.zkey), cudaFree(env->v.bloom), cudaFree(env->v.cnt), cudaFree(env->t_cnt);
+    cudaFree(env->v.episode), cudaFree(env->v.tgt), cudaFree(env->v.hist), cudaFree(env->v.stats), cudaFree(env->v.stat_rows);
     cudaFree(env->t_bb01), cudaFree(env->t_bb23), cudaFree(env->t_meta), cudaFree(env->t_zkey), cudaFree(env->t_tgt), cudaFree(env->zob);
     cudaFree(env->d_in), cudaFree(env->d_reward), cudaFree(env->d_done), cudaFree(env->d_flags);
     delete env;
@@ -525,10 +542,13 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     ALLOC(v.meta, (size_t)N * 8);
     ALLOC(v.zkey, (size_t)N * 8);
     ALLOC(v.bloom, (size_t)N * 16);
+    ALLOC(v.cnt, (size_t)N * 16);
+    ALLOC(env->t_cnt, (size_t)T * 16);
     ALLOC(v.episode, (size_t)N * 4);
     ALLOC(v.tgt, (size_t)N * S * 8);
     ALLOC(v.hist, (size_t)N * H * 8);
     ALLOC(v.stats, ST_COUNT * 8);
+    ALLOC(v.stat_rows, (size_t)((N + 31) / 32) * ST_COUNT * 8);
     ALLOC(env->t_bb01, (size_t)T * 16);
     ALLOC(env->t_bb23, (size_t)T * 16);
     ALLOC(env->t_meta, (size_t)T * 8);
@@ -547,7 +567,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
         return fail(GCB_E_NOMEM, "cudaMalloc", cudaGetErrorString(e));
     }
     v.t_bb01 = env->t_bb01, v.t_bb23 = env->t_bb23, v.t_meta = env->t_meta, v.t_zkey = env->t_zkey, v.t_tgt = env->t_tgt;
-    v.zob = env->zob;
+    v.zob = env->zob, v.t_cnt = env->t_cnt;
     v.seed = cfg.seed, v.N = N, v.slots = S, v.hist_mask = H - 1, v.n_templates = T, v.env_offset = cfg.env_id_offset;
     v.moves_max = cfg.moves_max, v.opponent = cfg.opponent, v.agent_black = cfg.agent_black, v.auto_reset = cfg.auto_reset;
     v.pps = 1 + (cfg.opponent == 1 ? 1 : 0);  // ring slots per step: agent ply, bot ply (a reset-bot ply reuses the bot slot)
@@ -555,16 +575,17 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     do {
         if (cudaMemcpy(d_tb, cfg.n_templates > 0 ? cfg.template_boards : kDefaultBoard, (size_t)T * 64, cudaMemcpyHostToDevice) !=
                 cudaSuccess ||
-            cudaMemset(v.stats, 0, ST_COUNT * 8) != cudaSuccess || cudaMemset(v.episode, 0, (size_t)N * 4) != cudaSuccess ||
+            cudaMemset(v.stats, 0, ST_COUNT * 8) != cudaSuccess ||
+            cudaMemset(v.stat_rows, 0, (size_t)((N + 31) / 32) * ST_COUNT * 8) != cudaSuccess || cudaMemset(v.episode, 0, (size_t)N * 4) != cudaSuccess ||
             cudaMemset(v.meta, 0, (size_t)N * 8) != cudaSuccess || cudaMemset(v.bb01, 0, (size_t)N * 16) != cudaSuccess ||
             cudaMemset(v.bb23, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.zkey, 0, (size_t)N * 8) != cudaSuccess ||
-            cudaMemset(v.bloom, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
+            cudaMemset(v.bloom, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.cnt, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
             cudaMemset(env->t_tgt, 0, (size_t)T * S * 8) != cudaSuccess) {
             rc = fail(GCB_E_CUDA, "cudaMemcpy/cudaMemset", "env init");
             break;
         }
         k_init_zobrist<<<(GCB_ZOB_ENTRIES + 127) / 128, 128>>>(env->zob);
-        k_make_templates<<<(T + 63) / 64, 64>>>(T, d_tb, env->t_bb01, env->t_bb23, env->t_meta, env->t_zkey, env->t_tgt, S);
+        k_make_templates<<<(T + 63) / 64, 64>>>(T, d_tb, env->t_bb01, env->t_bb23, env->t_meta, env->t_zkey, env->t_tgt, env->t_cnt, S);
         g_launches.fetch_add(2);
         // episode 0 starts with a reset that does not advance the episode counter
         StepIO io;
@@ -686,9 +707,16 @@ extern "C" int gcb_env_positions(gcb_env* env, gcb_positions* out) {
     return GCB_OK;
 }
 
+static int stats_reduce(gcb_env* env, cudaStream_t s) {
+    k_stats_reduce<<<1, 512, 0, s>>>(env->v.stat_rows, (env->v.N + 31) / 32, env->v.stats);
+    LAUNCHED();
+    return GCB_OK;
+}
+
 extern "C" int gcb_env_stats(gcb_env* env, uint64_t* out16, void* stream) {
     ENV_CHECK(env);
     if (!out16) return fail(GCB_E_ARG, "gcb_env_stats", "null out");
+    if (int rc = stats_reduce(env, (cudaStream_t)stream)) return rc;
     CU(cudaMemcpyAsync(out16, env->v.stats, ST_COUNT * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     return GCB_OK;
@@ -697,11 +725,14 @@ extern "C" int gcb_env_stats(gcb_env* env, uint64_t* out16, void* stream) {
 extern "C" int gcb_env_stats_reset(gcb_env* env, void* stream) {
     ENV_CHECK(env);
     CU(cudaMemsetAsync(env->v.stats, 0, ST_COUNT * 8, (cudaStream_t)stream));
+    CU(cudaMemsetAsync(env->v.stat_rows, 0, (size_t)((env->v.N + 31) / 32) * ST_COUNT * 8, (cudaStream_t)stream));
     return GCB_OK;
 }
 
-extern "C" int gcb_env_stats_ptr(gcb_env* env, uint64_t** d_stats) {
+extern "C" int gcb_env_stats_ptr(gcb_env* env, uint64_t** d_stats, void* stream) {
     if (!env || !d_stats) return fail(GCB_E_ARG, "gcb_env_stats_ptr", "null pointer");
+    CU(cudaSetDevice(env->cfg.device));
+    if (int rc = stats_reduce(env, (cudaStream_t)stream)) return rc;  // totals are current once `stream` reaches here
     *d_stats = reinterpret_cast<uint64_t*>(env->v.stats);
     return GCB_OK;
 }

@@ -178,8 +178,9 @@ int gcb_env_positions(gcb_env *env, gcb_positions *out);
  * repetition scans), hist_window (sum over plies of the repetition window length), 0.   Synchronises the stream. */
 int gcb_env_stats(gcb_env *env, uint64_t *out16, void *stream);
 int gcb_env_stats_reset(gcb_env *env, void *stream);
-/* device pointer to the 16 counters (for an NCCL reduce by the caller) */
-int gcb_env_stats_ptr(gcb_env *env, uint64_t **d_stats);
+/* device pointer to the 16 counters (for an NCCL reduce by the caller); the totals are brought up to date by a small
+ * reduction kernel enqueued on `stream` */
+int gcb_env_stats_ptr(gcb_env *env, uint64_t **d_stats, void *stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@ struct LocalSlots {
     u64 t[GCB_SLOTS];
     void put(int r, u64 v) { t[r] = v; }
     u64 get(int r) const { return t[r]; }
+    void replace(int r, u64, u64 v) { t[r] = v; }
 };
 
 void emul_movegen(int n, const int8_t* boards, const int8_t* players, const uint8_t* rights4, int attack, int castles_only,
@@ -85,11 +86,12 @@ struct EmulEnv {
     u64 tick;
     ulonglong2 *t_bb01, *t_bb23;
     u64 *t_meta, *t_zkey, *t_tgt, *zob;
+    ulonglong2* t_cnt;
 };
 
 void emul_env_destroy(EmulEnv* E) {
     if (!E) return;
-    free(E->v.bb01), free(E->v.bb23), free(E->v.meta), free(E->v.zkey), free(E->v.bloom), free(E->v.episode), free(E->v.tgt);
+    free(E->v.bb01), free(E->v.bb23), free(E->v.meta), free(E->v.zkey), free(E->v.bloom), free(E->v.cnt), free(E->t_cnt), free(E->v.episode), free(E->v.tgt);
     free(E->v.hist), free(E->v.stats), free(E->t_bb01), free(E->t_bb23), free(E->t_meta), free(E->t_zkey), free(E->t_tgt), free(E->zob);
     free(E);
 }
@@ -104,19 +106,19 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
     EnvView& v = E->v;
     v.bb01 = (ulonglong2*)calloc(N, 16), v.bb23 = (ulonglong2*)calloc(N, 16);
     v.meta = (u64*)calloc(N, 8), v.zkey = (u64*)calloc(N, 8), v.episode = (u32*)calloc(N, 4);
-    v.bloom = (ulonglong2*)calloc(N, 16);
+    v.bloom = (ulonglong2*)calloc(N, 16), v.cnt = (ulonglong2*)calloc(N, 16), E->t_cnt = (ulonglong2*)calloc(T, 16);
     v.tgt = (u64*)calloc((size_t)N * slots, 8), v.hist = (u64*)calloc((size_t)N * hist_cap, 8);
     v.stats = (u64*)calloc(ST_COUNT, 8);
     E->t_bb01 = (ulonglong2*)calloc(T, 16), E->t_bb23 = (ulonglong2*)calloc(T, 16);
     E->t_meta = (u64*)calloc(T, 8), E->t_zkey = (u64*)calloc(T, 8), E->t_tgt = (u64*)calloc((size_t)T * slots, 8);
     E->zob = (u64*)calloc(GCB_ZOB_ENTRIES, 8);
     for (int i = 0; i < GCB_ZOB_ENTRIES; i++) fill_zobrist_entry(E->zob, i);
-    v.t_bb01 = E->t_bb01, v.t_bb23 = E->t_bb23, v.t_meta = E->t_meta, v.t_zkey = E->t_zkey, v.t_tgt = E->t_tgt, v.zob = E->zob;
+    v.t_bb01 = E->t_bb01, v.t_bb23 = E->t_bb23, v.t_meta = E->t_meta, v.t_zkey = E->t_zkey, v.t_tgt = E->t_tgt, v.zob = E->zob, v.t_cnt = E->t_cnt;
     v.seed = seed, v.N = N, v.slots = slots, v.hist_mask = hist_cap - 1, v.n_templates = T, v.env_offset = env_offset;
     v.moves_max = moves_max, v.opponent = opponent, v.agent_black = agent_black, v.auto_reset = auto_reset;
     v.pps = 1 + (opponent == 1);
     for (int i = 0; i < T; i++)
-        make_template_one(i, n_templates > 0 ? template_boards : def, E->t_bb01, E->t_bb23, E->t_meta, E->t_zkey, E->t_tgt, slots);
+        make_template_one(i, n_templates > 0 ? template_boards : def, E->t_bb01, E->t_bb23, E->t_meta, E->t_zkey, E->t_tgt, E->t_cnt, slots);
     StepIO io;
     memset(&io, 0, sizeof(io));
     io.tick = E->tick++;

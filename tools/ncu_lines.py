@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Join an ncu SASS-level source page with nvdisasm line info of the SAME build:
+tools/ncu_lines.py <rep> <so> <kernel substring> [top] -> per source line: stall samples, warp instructions executed,
+lane efficiency.  Also aggregates by the outermost inlined-at frame (function-level view)."""
+import collections, csv, io, os, re, subprocess, sys, tempfile
+
+rep, so, pat = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+blocks, cur = [], None
+for row in csv.reader(io.StringIO(raw)):
+    if row and row[0] == "Kernel Name":
+        cur = {"name": row[1], "rows": []}
+        blocks.append(cur)
+    elif row and row[0] == "Address":
+        cur["hdr"] = row
+    elif row and cur is not None and "hdr" in cur:
+        cur["rows"].append(row)
+blk = [b for b in blocks if pat in b["name"].replace("(int)", "")][0]
+h = {n: i for i, n in enumerate(blk["hdr"])}
+d = tempfile.mkdtemp()
+subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=d, stdout=subprocess.DEVNULL)
+cub = [os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cubin")][0]
+lines = subprocess.run(["nvdisasm", "--print-line-info-inline", cub], capture_output=True, text=True).stdout.split("\n")
+starts = [i for i, l in enumerate(lines) if l.startswith("//--------------------- .text.")]
+mang = {"k_env_step<2>": "k_env_stepILi2E", "k_env_step<0>": "k_env_stepILi0E", "k_env_step<1>": "k_env_stepILi1E",
+        "k_movegen<false>": "k_movegenILb0E", "k_movegen<0>": "k_movegenILb0E"}.get(pat, pat)
+locs = []
+for si, st in enumerate(starts):
+    if mang not in lines[st]:
+        continue
+    en = starts[si + 1] if si + 1 < len(starts) else len(lines)
+    frames = []
+    fresh = True
+    for l in lines[st:en]:
+        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+        if m:
+            if fresh:
+                frames, fresh = [], False
+            frames.append((m.group(1).split("/")[-1], int(m.group(2))))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l):
+            locs.append(tuple(frames))
+            fresh = True
+    break
+rows = blk["rows"]
+assert len(rows) == len(locs), (len(rows), len(locs))
+by_line, by_outer = collections.defaultdict(lambda: [0, 0, 0]), collections.defaultdict(lambda: [0, 0, 0])
+tot = [0, 0, 0]
+for r, frames in zip(rows, locs):
+    s, wi, ti = int(r[h["# Samples"]]), int(r[h["Instructions Executed"]]), int(r[h["Thread Instructions Executed"]])
+    loc = frames[0] if frames else ("?", 0)
+    # function-level view: the frame one below the outermost two (kernel line -> env_step_one line -> ...)
+    outer = frames[-2] if len(frames) >= 2 else loc
+    if len(frames) >= 3 and frames[-2][0] == "env_core.cuh":
+        outer = frames[-3] if frames[-3][0] == "env_core.cuh" else frames[-2]
+    for dct, k in ((by_line, loc), (by_outer, outer)):
+        dct[k][0] += s; dct[k][1] += wi; dct[k][2] += ti
+    tot[0] += s; tot[1] += wi; tot[2] += ti
+print("total samples %d warp-inst %d lane-eff %.1f" % (tot[0], tot[1], tot[2] / max(1, tot[1])))
+for title, dct in (("by innermost line", by_line), ("by env_core-level frame", by_outer)):
+    print("==", title)
+    for k, (s, wi, ti) in sorted(dct.items(), key=lambda x: -x[1][0])[:top]:
+        print("  %-24s %5d  samples %6d (%4.1f%%)  warp-inst %9d (%4.1f%%)  lanes %.1f" % (k[0], k[1], s, 100.0 * s / tot[0], wi, 100.0 * wi / tot[1], ti / max(1, wi)))
+if len(sys.argv) > 5:  # annotated listing: file:lo-hi
+    f, rng = sys.argv[5].split(":")
+    lo, hi = map(int, rng.split("-"))
+    path = [p for p in ("gym_chess_b200/csrc/" + f, f) if os.path.exists(p)][0]
+    src = open(path).read().split("\n")
+    for ln in range(lo, hi + 1):
+        s, wi, ti = by_line.get((f, ln), (0, 0, 0))
+        print("%5d %6d %9d %5.1f | %s" % (ln, s, wi, ti / max(1, wi), src[ln - 1][:110]))
