@@ -50,6 +50,12 @@ GCB_HD int gcb_msb(u64 x) {  // index of the highest set bit, x != 0
     return 63 - __builtin_clzll(x);
 #endif
 }
+// take one square out of a non-empty set (the highest: FLO finds it without a bit reversal)
+GCB_HD int gcb_take(u64& s) {
+    const int sq = gcb_msb(s);
+    s ^= 1ULL << sq;
+    return sq;
+}
 GCB_HD int gcb_popc(u64 x) {
 #if defined(__CUDA_ARCH__)
     return __popcll(x);
@@ -121,7 +127,72 @@ GCB_HD void put_sq(Board& b, int sq, int code, int white) {
     if (white && code) b.w |= bit;
 }
 
-// ---- arithmetic line masks (include the square itself)
+// ---------------------------------------------------------------------------------------------
+// Geometry tables, built at COMPILE time (constexpr) and placed in device global memory: every lookup is one
+// L1-resident LDG instead of 10-20 integer instructions -- the step kernel is bound by the integer pipe, the
+// load pipe is idle.  `ord` also is the single statement of the reference's per-piece move ORDER:
+//   class 0 slider : rook dirs (-1,0)(1,0)(0,-1)(0,1), bishop dirs (-1,-1)(-1,1)(1,-1)(1,1)   lib.rs:824-851
+//   class 1 king   : (1,0)(-1,0)(0,1)(0,-1)(1,1)(1,-1)(-1,1)(-1,-1)                            lib.rs:797-806
+//   class 2 knight : (-2,-1)(-2,1)(2,-1)(2,1)(-1,-2)(-1,2)(1,-2)(1,2)                          lib.rs:891-900
+//   class 3/4 white/black pawn : one step, two steps, (row-p, col+1), (row-p, col-1)            lib.rs:935-959
+// Entry k of a piece on sq = the squares its k-th direction can reach on an empty board (a ray for sliders, one
+// square for the others); the ordered move list of the piece is, for k = 0..7, (targets & entry k) by increasing
+// distance.  Entries 0,2,4,5 of every class point to LOWER square indices (or hold a single square).
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) GeomTables {
+    u64 line[64][4];    // file, rank, diagonal, anti-diagonal through sq, WITHOUT sq
+    u64 ord[5][64][8];  // ordered direction masks per class
+    u64 knight[64], king[64];
+    constexpr GeomTables() : line(), ord(), knight(), king() {
+        const int sl[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
+        const int kg[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+        const int kn[8][2] = {{-2, -1}, {-2, 1}, {2, -1}, {2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}};
+        const int wp[4][2] = {{-1, 0}, {-2, 0}, {-1, 1}, {-1, -1}};
+        const int bp[4][2] = {{1, 0}, {2, 0}, {1, 1}, {1, -1}};
+        for (int sq = 0; sq < 64; sq++) {
+            const int r = sq >> 3, c = sq & 7;
+            for (int t = 0; t < 64; t++) {
+                const int tr = t >> 3, tc = t & 7;
+                if (t == sq) continue;
+                if (tc == c) line[sq][0] |= 1ULL << t;
+                if (tr == r) line[sq][1] |= 1ULL << t;
+                if (tr - tc == r - c) line[sq][2] |= 1ULL << t;
+                if (tr + tc == r + c) line[sq][3] |= 1ULL << t;
+            }
+            for (int k = 0; k < 8; k++) {
+                for (int i = 1; i < 8; i++) {
+                    const int tr = r + i * sl[k][0], tc = c + i * sl[k][1];
+                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[0][sq][k] |= 1ULL << (tr * 8 + tc);
+                }
+                int tr = r + kg[k][0], tc = c + kg[k][1];
+                if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[1][sq][k] |= 1ULL << (tr * 8 + tc), king[sq] |= 1ULL << (tr * 8 + tc);
+                tr = r + kn[k][0], tc = c + kn[k][1];
+                if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[2][sq][k] |= 1ULL << (tr * 8 + tc), knight[sq] |= 1ULL << (tr * 8 + tc);
+                if (k < 4) {
+                    tr = r + wp[k][0], tc = c + wp[k][1];
+                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[3][sq][k] |= 1ULL << (tr * 8 + tc);
+                    tr = r + bp[k][0], tc = c + bp[k][1];
+                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[4][sq][k] |= 1ULL << (tr * 8 + tc);
+                }
+            }
+        }
+    }
+};
+#if defined(__CUDACC__)
+__device__ const GeomTables g_geom_dev = GeomTables();
+#endif
+static const GeomTables g_geom_host = GeomTables();
+#if defined(__CUDA_ARCH__)
+#define GCB_GEOM(field) __ldg(&g_geom_dev.field)
+#else
+#define GCB_GEOM(field) (g_geom_host.field)
+#endif
+#define GCB_RAY_DESC_MASK 0x35u  // entries 0,2,4,5: nearest square first = highest bit first
+GCB_HD int order_class(int code, int white) {
+    return code == PC_KING ? 1 : code == PC_KNIGHT ? 2 : code == PC_PAWN ? (white ? 3 : 4) : 0;
+}
+
+// ---- arithmetic line masks (include the square itself); only used on rare paths (pins, check masks)
 GCB_HD u64 mask_file(int sq) { return GCB_FILE_A << (sq & 7); }
 GCB_HD u64 mask_rank(int sq) { return 0xFFULL << (sq & 56); }
 GCB_HD u64 mask_diag(int sq) {  // steps of +-9: (row-col) constant
@@ -145,11 +216,11 @@ GCB_HD u64 hq_line(u64 occ, u64 maskEx, u64 bit, u64 rbit) {
 }
 GCB_HD u64 rook_att(int sq, u64 occ) {
     u64 bit = 1ULL << sq, rbit = 1ULL << (63 - sq);
-    return hq_line(occ, mask_file(sq) ^ bit, bit, rbit) | hq_line(occ, mask_rank(sq) ^ bit, bit, rbit);
+    return hq_line(occ, GCB_GEOM(line[sq][0]), bit, rbit) | hq_line(occ, GCB_GEOM(line[sq][1]), bit, rbit);
 }
 GCB_HD u64 bishop_att(int sq, u64 occ) {
     u64 bit = 1ULL << sq, rbit = 1ULL << (63 - sq);
-    return hq_line(occ, mask_diag(sq) ^ bit, bit, rbit) | hq_line(occ, mask_anti(sq) ^ bit, bit, rbit);
+    return hq_line(occ, GCB_GEOM(line[sq][2]), bit, rbit) | hq_line(occ, GCB_GEOM(line[sq][3]), bit, rbit);
 }
 
 // ---- set-wise leaper attacks (all pieces of the set at once)
@@ -303,8 +374,8 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     // opponent attack map (lib.rs:669-677): pawns minus squares holding the attacker's OWN king (Q14)
     u64 eatt = pawn_set_att(g.pawns & enemy, !white_to_move) & ~ekings;
     eatt |= knight_set_att(g.knights & enemy) | king_set_att(ekings);
-    for (u64 s = eRQ; s; s &= s - 1) eatt |= rook_att(gcb_lsb(s), occ);
-    for (u64 s = eBQ; s; s &= s - 1) eatt |= bishop_att(gcb_lsb(s), occ);
+    for (u64 s = eRQ; s;) eatt |= rook_att(gcb_take(s), occ);
+    for (u64 s = eBQ; s;) eatt |= bishop_att(gcb_take(s), occ);
     g.eatt = eatt;
 
     g.satt = 0, g.cm = ~0ULL, g.pinned = 0, g.pinrays = 0, g.ksq = 0, g.in_check = false;
@@ -327,8 +398,8 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     // pins: drop the own pieces the king "sees" first on each ray and look again
     const u64 xr = rook_att(ksq, occ ^ (rk & g.own)) & ~rk & eRQ;
     const u64 xb = bishop_att(ksq, occ ^ (bk & g.own)) & ~bk & eBQ;
-    for (u64 p = xr | xb; p; p &= p - 1) {
-        const int psq = gcb_lsb(p);
+    for (u64 p = xr | xb; p;) {
+        const int psq = gcb_take(p);
         const u64 btw = between_excl(ksq, psq);
         g.pinned |= btw & g.own;
         g.pinrays |= btw | (1ULL << psq);
@@ -357,37 +428,37 @@ GCB_HD int gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         total += gcb_popc(t__);                                        \
     } while (0)
     // rooks
-    for (u64 s = g.rooks & mine; s; s &= s - 1) {
-        const int sq = gcb_lsb(s);
+    for (u64 s = g.rooks & mine; s;) {
+        const int sq = gcb_take(s);
         const u64 bit = 1ULL << sq, a = rook_att(sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // bishops
-    for (u64 s = g.bishops & mine; s; s &= s - 1) {
-        const int sq = gcb_lsb(s);
+    for (u64 s = g.bishops & mine; s;) {
+        const int sq = gcb_take(s);
         const u64 bit = 1ULL << sq, a = bishop_att(sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // queens
-    for (u64 s = g.queens & mine; s; s &= s - 1) {
-        const int sq = gcb_lsb(s);
+    for (u64 s = g.queens & mine; s;) {
+        const int sq = gcb_take(s);
         const u64 bit = 1ULL << sq, a = rook_att(sq, occ) | bishop_att(sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // knights
-    for (u64 s = g.knights & mine; s; s &= s - 1) {
-        const int sq = gcb_lsb(s);
-        const u64 bit = 1ULL << sq, a = knight_set_att(bit);
+    for (u64 s = g.knights & mine; s;) {
+        const int sq = gcb_take(s);
+        const u64 bit = 1ULL << sq, a = GCB_GEOM(knight[sq]);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // kings: never passed through the legality filter (lib.rs:615-619); attack map with the king on it (Q6)
-    for (u64 s = g.kings & mine; s; s &= s - 1) {
-        const int sq = gcb_lsb(s);
-        const u64 bit = 1ULL << sq, a = king_set_att(bit);
+    for (u64 s = g.kings & mine; s;) {
+        const int sq = gcb_take(s);
+        const u64 bit = 1ULL << sq, a = GCB_GEOM(king[sq]);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & ~g.eatt);
     }
@@ -397,8 +468,8 @@ GCB_HD int gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         const u64 pw = g.pawns & mine, allp = g.pawns & own;
         g.satt |= pawn_set_att(pw, g.white) & ~(g.kings & own);  // Q14
         (void)allp;
-        for (u64 s = pw; s; s &= s - 1) {
-            const int sq = gcb_lsb(s);
+        for (u64 s = pw; s;) {
+            const int sq = gcb_take(s);
             const u64 bit = 1ULL << sq;
             // colour-agnostic: a rotation by 56 is a shift down by 8 for every row but row 0 (masked out), so the
             // white and black pawns of a warp run the same instructions
@@ -414,8 +485,8 @@ GCB_HD int gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
 #undef GCB_PUT
     // pinned pieces (rare per position, but some env of a warp nearly always has one): one fix-up pass over the
     // slots instead of a pin test at every generation site
-    for (u64 p = g.pinned & mine & ~g.kings; p; p &= p - 1) {
-        const int sq = gcb_lsb(p), r = gcb_popc(mine & ((1ULL << sq) - 1));
+    for (u64 p = g.pinned & mine & ~g.kings; p;) {
+        const int sq = gcb_take(p), r = gcb_popc(mine & ((1ULL << sq) - 1));
         const u64 t = sink.get(r), t2 = t & pin_mask(g, sq);
         sink.replace(r, t, t2);
         total -= gcb_popc(t ^ t2);
@@ -447,65 +518,16 @@ GCB_HD int castle_action(int white, int king_side) {
     return white ? (king_side ? ACT_CASTLE_KS_WHITE : ACT_CASTLE_QS_WHITE) : (king_side ? ACT_CASTLE_KS_BLACK : ACT_CASTLE_QS_BLACK);
 }
 
-// ---- the reference's move ORDER inside one piece, as a function of (code, colour, square, targets)
-// direction tables, 8 signed bytes packed little-endian in a u64 (entry k = (int8)(pack >> 8k))
-#define GCB_PACK8(a, b, c, d, e, f, g, h)                                                              \
-    (((u64)(uint8_t)(int8_t)(a)) | ((u64)(uint8_t)(int8_t)(b) << 8) | ((u64)(uint8_t)(int8_t)(c) << 16) | \
-     ((u64)(uint8_t)(int8_t)(d) << 24) | ((u64)(uint8_t)(int8_t)(e) << 32) | ((u64)(uint8_t)(int8_t)(f) << 40) | \
-     ((u64)(uint8_t)(int8_t)(g) << 48) | ((u64)(uint8_t)(int8_t)(h) << 56))
-// king (lib.rs:797-806): (1,0)(-1,0)(0,1)(0,-1)(1,1)(1,-1)(-1,1)(-1,-1)
-#define GCB_DELTAS_KING GCB_PACK8(8, -8, 1, -1, 9, 7, -7, -9)
-// knight (lib.rs:891-900): (-2,-1)(-2,1)(2,-1)(2,1)(-1,-2)(-1,2)(1,-2)(1,2)
-#define GCB_DELTAS_KNIGHT GCB_PACK8(-17, -15, 15, 17, -10, -6, 6, 10)
-// pawn (lib.rs:935-959): one step, two steps, (row-p, col+1), (row-p, col-1); white then black; rest unused (0)
-#define GCB_DELTAS_WPAWN GCB_PACK8(-8, -16, -7, -9, 0, 0, 0, 0)
-#define GCB_DELTAS_BPAWN GCB_PACK8(8, 16, 9, 7, 0, 0, 0, 0)
-
-GCB_HD u64 leaper_deltas(int code, int white) {
-    return code == PC_KING ? GCB_DELTAS_KING : code == PC_KNIGHT ? GCB_DELTAS_KNIGHT : white ? GCB_DELTAS_WPAWN : GCB_DELTAS_BPAWN;
-}
-GCB_HD int delta_at(u64 pack, int k) { return (int)(int8_t)(uint8_t)(pack >> (8 * k)); }
-
-// ray k (0..7) of a slider on sq in the reference's order: rook dirs (-1,0)(1,0)(0,-1)(0,1) then bishop dirs
-// (-1,-1)(-1,1)(1,-1)(1,1) (lib.rs:824-851).  Rays 0,2,4,5 run towards lower square indices.
-GCB_HD u64 slider_ray(int sq, int k) {
-    const u64 bit = 1ULL << sq, below = bit - 1, above = ~(bit | below);
-    switch (k) {
-    case 0: return mask_file(sq) & below;
-    case 1: return mask_file(sq) & above;
-    case 2: return mask_rank(sq) & below;
-    case 3: return mask_rank(sq) & above;
-    case 4: return mask_diag(sq) & below;
-    case 5: return mask_anti(sq) & below;
-    case 6: return mask_anti(sq) & above;
-    default: return mask_diag(sq) & above;
-    }
-}
-#define GCB_RAY_DESC_MASK 0x35u  // rays 0,2,4,5: nearest square first = highest bit first
-
+// ---- the reference's move ORDER inside one piece: a walk over the 8 ordered direction masks of its class
 template <class Emit>
 GCB_HD void emit_piece_moves(Emit& em, int code, int white, int sq, u64 T) {
     if (!T) return;
-    const int base = sq * 64;
-    if (code == PC_KING || code == PC_KNIGHT || code == PC_PAWN) {
-        const u64 d = leaper_deltas(code, white);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int k = 0; k < 8; k++) {
-            const int to = sq + delta_at(d, k);
-            if (T & sq_bit_safe(to)) em.push(base + to);
-        }
-        return;
-    }
-    // sliders: rook uses rays 0-3, bishop 4-7, queen all eight
-    const int k0 = code == PC_BISHOP ? 4 : 0, k1 = code == PC_ROOK ? 4 : 8;
+    const int base = sq * 64, cls = order_class(code, white);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int k = 0; k < 8; k++) {
-        if (k < k0 || k >= k1) continue;
-        u64 m = T & slider_ray(sq, k);
+        u64 m = T & GCB_GEOM(ord[cls][sq][k]);
         if ((GCB_RAY_DESC_MASK >> k) & 1) {
             while (m) {
                 const int to = gcb_msb(m);
@@ -522,36 +544,21 @@ GCB_HD void emit_piece_moves(Emit& em, int code, int white, int sq, u64 T) {
     }
 }
 
-// the idx-th (0-based) target of one piece in the reference's order; idx < popc(T)
+// the idx-th (0-based) target of one piece in the reference's order; idx < popc(T).  Same instructions for every
+// piece type: find the direction that holds the idx-th target, then walk idx squares along it (nearest first).
 GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
-    if (code == PC_KING || code == PC_KNIGHT || code == PC_PAWN) {
-        const u64 d = leaper_deltas(code, white);
-        int res = sq;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int k = 0; k < 8; k++) {
-            const int to = sq + delta_at(d, k);
-            if (T & sq_bit_safe(to)) {
-                if (idx == 0) res = to;
-                idx--;
-            }
-        }
-        return res;
-    }
-    // sliders: find the ray that holds the idx-th target, then walk idx squares along it (nearest first)
-    const int k0 = code == PC_BISHOP ? 4 : 0, k1 = code == PC_ROOK ? 4 : 8;
+    const int cls = order_class(code, white);
     u64 mf = 0;
-    bool found = false, desc = false;
+    bool desc = false;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int k = 0; k < 8; k++) {
-        if (k < k0 || k >= k1 || found) continue;
-        const u64 m = T & slider_ray(sq, k);
+        const u64 m = T & GCB_GEOM(ord[cls][sq][k]);
         const int c = gcb_popc(m);
-        if (idx < c) found = true, mf = m, desc = (GCB_RAY_DESC_MASK >> k) & 1;
-        else idx -= c;
+        const bool hit = !mf && idx < c;
+        if (hit) mf = m, desc = (GCB_RAY_DESC_MASK >> k) & 1;
+        if (!mf) idx -= c;
     }
     if (!mf) return sq;
     if (desc) mf = gcb_brev64(mf);  // nearest first = lowest bit first in both cases

@@ -133,8 +133,9 @@ struct TgtSink {
     u64 cnt_lo, cnt_hi;
     GCB_HD TgtSink(u64* tgt, int n, int e, int s) : base(tgt + e), N((size_t)n), slots(s), dropped(0), cnt_lo(0), cnt_hi(0) {}
     GCB_HD void add_count(int r, u64 c) {
-        if (r < 8) cnt_lo += c << (8 * r);
-        else if (r < 16) cnt_hi += c << (8 * (r - 8));
+        const u64 val = c << (8 * (r & 7));  // branch-free: the slot index differs from lane to lane
+        cnt_lo += (r >> 3) == 0 ? val : 0ULL;
+        cnt_hi += (r >> 3) == 1 ? val : 0ULL;
     }
     GCB_HD void put(int r, u64 t) {
         if (r < slots) base[(size_t)r * N] = t;
