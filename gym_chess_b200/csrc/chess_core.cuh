@@ -415,17 +415,15 @@ GCB_HD u64 pin_mask(const GenCtx& g, int sq) {
 
 // Targets of every own piece in `subset` (a set of squares; the caller passes all own pieces, or a
 // chunk of them when there are more pieces than slots).  sink.put(rank, targets): rank = index of the
-// piece among the own pieces of `subset` in ascending square order.  Returns the number of targets.
+// piece among the own pieces of `subset` in ascending square order.
 template <class Sink>
-GCB_HD int gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
+GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
     const u64 occ = g.occ, own = g.own, notown = ~g.own;
     const u64 mine = own & subset;
-    int total = 0;
 #define GCB_PUT(sq_, bit_, T_)                                         \
     do {                                                               \
         const u64 t__ = (T_);                                          \
         sink.put(gcb_popc(mine & ((bit_) - 1)), t__);                  \
-        total += gcb_popc(t__);                                        \
     } while (0)
     // rooks
     for (u64 s = g.rooks & mine; s;) {
@@ -489,9 +487,7 @@ GCB_HD int gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         const int sq = gcb_take(p), r = gcb_popc(mine & ((1ULL << sq) - 1));
         const u64 t = sink.get(r), t2 = t & pin_mask(g, sq);
         sink.replace(r, t, t2);
-        total -= gcb_popc(t ^ t2);
     }
-    return total;
 }
 
 // castles, lib.rs:578-610 + 966-1056: needs the mover's king on the board and K-right OR Q-right (Q4).

@@ -124,28 +124,48 @@ GCB_HD u64 pack_meta(const EnvRegs& s) {
 GCB_HD bool stm_checked(const EnvRegs& s) { return (s.chk >> s.stm_black) & 1u; }
 GCB_HD u64 stm_pieces(const EnvRegs& s) { return s.stm_black ? (bb_occ(s.b) & ~s.b.w) : s.b.w; }
 
-// piece slots of env e in the resident array (slot r of env e at tgt[r*N + e]: coalesced when a warp reads slot r)
-// plus the per-piece target counts of the first 16 slots, one byte each
+// piece slots of env e in the resident array (slot r of env e at tgt[r*N + e]: coalesced when a warp reads slot r).
+// The per-piece target counts of the first 16 slots go to 16 bytes of scratch (shared memory in the kernel: one
+// byte store per piece instead of a 128-bit shift-and-add; read back as one 16-byte record).
+struct alignas(16) CountBytes {
+    uint8_t c[16];
+};
 struct TgtSink {
     u64* base;
     size_t N;
-    int slots, dropped;
-    u64 cnt_lo, cnt_hi;
-    GCB_HD TgtSink(u64* tgt, int n, int e, int s) : base(tgt + e), N((size_t)n), slots(s), dropped(0), cnt_lo(0), cnt_hi(0) {}
-    GCB_HD void add_count(int r, u64 c) {
-        const u64 val = c << (8 * (r & 7));  // branch-free: the slot index differs from lane to lane
-        cnt_lo += (r >> 3) == 0 ? val : 0ULL;
-        cnt_hi += (r >> 3) == 1 ? val : 0ULL;
+    int slots, dropped, extra;  // extra = targets of pieces beyond the 16 counted slots
+    uint8_t* cb;
+    GCB_HD TgtSink(u64* tgt, int n, int e, int s, CountBytes* scratch)
+        : base(tgt + e), N((size_t)n), slots(s), dropped(0), extra(0), cb(scratch ? scratch->c : nullptr) {
+        if (scratch) {
+            u64* z = reinterpret_cast<u64*>(scratch);
+            z[0] = 0, z[1] = 0;
+        }
     }
     GCB_HD void put(int r, u64 t) {
         if (r < slots) base[(size_t)r * N] = t;
         else dropped++;
-        add_count(r, (u64)gcb_popc(t));
+        const int c = gcb_popc(t);
+        if (r < 16) cb[r] = (uint8_t)c;
+        else extra += c;
     }
     GCB_HD u64 get(int r) const { return r < slots ? base[(size_t)r * N] : 0ULL; }
     GCB_HD void replace(int r, u64 told, u64 tnew) {  // tnew is a subset of told
         if (r < slots) base[(size_t)r * N] = tnew;
-        add_count(r, (u64)0 - (u64)gcb_popc(told ^ tnew));  // the byte never underflows: no borrow leaves it
+        const int c = gcb_popc(tnew);
+        if (r < 16) cb[r] = (uint8_t)c;
+        else extra -= gcb_popc(told) - c;
+    }
+    GCB_HD u64 count_lo() const { return reinterpret_cast<const u64*>(cb)[0]; }
+    GCB_HD u64 count_hi() const { return reinterpret_cast<const u64*>(cb)[1]; }
+    GCB_HD int total() const {  // sum of the 16 bytes + extra
+        u64 a = count_lo(), b = count_hi();
+        a = (a & 0x00FF00FF00FF00FFULL) + ((a >> 8) & 0x00FF00FF00FF00FFULL);
+        b = (b & 0x00FF00FF00FF00FFULL) + ((b >> 8) & 0x00FF00FF00FF00FFULL);
+        a += b;
+        a += a >> 32;
+        a += a >> 16;
+        return (int)(a & 0xFFFF) + extra;
     }
 };
 
@@ -181,7 +201,7 @@ GCB_HD int action_at(const EnvView& v, int e, const EnvRegs& s, int idx) {
         if (hit_r < 0 && idx - acc < c) hit_r = r, hit_idx = idx - acc;
         acc += c;
     }
-    TgtSink slots(v.tgt, v.N, e, v.slots);
+    TgtSink slots(v.tgt, v.N, e, v.slots, nullptr);
     u64 own = stm_pieces(s);
     if (v.slots > 16 && hit_r < 0) {
         const int np = gcb_popc(own);
@@ -212,7 +232,7 @@ GCB_HD bool action_is_legal(const EnvView& v, int e, const EnvRegs& s, int actio
         const int from = action >> 6, to = action & 63;
         const u64 own = stm_pieces(s), fbit = 1ULL << from;
         if (!(own & fbit)) return false;
-        TgtSink slots(v.tgt, v.N, e, v.slots);
+        TgtSink slots(v.tgt, v.N, e, v.slots, nullptr);
         return (slots.get(gcb_popc(own & (fbit - 1))) >> to) & 1ULL;
     }
     if (action == castle_action(!s.stm_black, 0)) return s.castle & 1u;
@@ -229,7 +249,7 @@ struct StepStats {
 // side to move (573-582).  apply=false only switches the side and regenerates (BLACK-agent reset
 // when White has no move).  Returns the ply reward.
 GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int slot, int action, bool apply, bool* rep,
-                           StepStats& st) {
+                           StepStats& st, CountBytes* scratch) {
     int r = 0;
     *rep = false;
     if (apply) {
@@ -277,10 +297,11 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
     s.stm_black ^= 1;
     GenCtx g;
     gen_prepare(s.b, !s.stm_black, g);
-    TgtSink sink(v.tgt, v.N, e, v.slots);
-    const int n = gen_targets(s.b, g, g.own, sink);
+    TgtSink sink(v.tgt, v.N, e, v.slots, scratch);
+    gen_targets(s.b, g, g.own, sink);
+    const int n = sink.total();
     if (sink.dropped) st.v[ST_SLOTOVF] += 1;
-    s.cnt_lo = sink.cnt_lo, s.cnt_hi = sink.cnt_hi;
+    s.cnt_lo = sink.count_lo(), s.cnt_hi = sink.count_hi();
     s.castle = gen_castles(s.b, g, mask_rights(s.b, s.rights));
     s.n_legal = n + (int)(s.castle & 1u) + (int)(s.castle >> 1);
     // both check flags (update_state, lib.rs:1386-1393): the side to move from the attackers of its king
@@ -308,7 +329,7 @@ struct StepIO {
 
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step)
 template <int MODE>
-GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& st) {
+GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& st, CountBytes* scratch) {
     EnvRegs s;
     {
         ulonglong2 a = v.bb01[e], c = v.bb23[e];
@@ -423,7 +444,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
             continue;
         }
         bool rep;
-        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st);
+        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st, scratch);
         if (do_apply) st.v[ST_PLIES] += 1;
         const bool mate = s.n_legal == 0 && stm_checked(s);
         if (phase == PH_AGENT) {
@@ -482,11 +503,13 @@ GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulo
     s.stm_black = 0, s.done = 0, s.move_count = 0, s.step = 0, s.hist_len = 0;
     GenCtx g;
     gen_prepare(b, 1, g);
-    TgtSink sink(tgt + (size_t)i * slots, 1, 0, slots);
-    const int n = gen_targets(b, g, g.own, sink);
+    CountBytes scratch;
+    TgtSink sink(tgt + (size_t)i * slots, 1, 0, slots, &scratch);
+    gen_targets(b, g, g.own, sink);
+    const int n = sink.total();
     s.castle = gen_castles(b, g, s.rights);
     s.n_legal = n + (int)(s.castle & 1u) + (int)(s.castle >> 1);
-    cnt[i] = make_ulonglong2(sink.cnt_lo, sink.cnt_hi);
+    cnt[i] = make_ulonglong2(sink.count_lo(), sink.count_hi());
     bb01[i] = make_ulonglong2(b.t0, b.t1);
     bb23[i] = make_ulonglong2(b.t2, b.w);
     meta[i] = pack_meta(s);
@@ -500,7 +523,7 @@ GCB_HD void env_legal_list_one(const EnvView& v, int e, Emit& em) {
     ulonglong2 a = v.bb01[e], c = v.bb23[e];
     s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
     unpack_meta(v.meta[e], s);
-    TgtSink slots(v.tgt, v.N, e, v.slots);
+    TgtSink slots(v.tgt, v.N, e, v.slots, nullptr);
     int r = 0;
     for (u64 rem = stm_pieces(s); rem; rem &= rem - 1, r++) {
         const int sq = gcb_lsb(rem);

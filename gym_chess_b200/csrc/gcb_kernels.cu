@@ -175,13 +175,14 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions
 
 template <int MODE>
 __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
+    __shared__ CountBytes s_counts[GCB_BLOCK];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     StepStats st;
 #pragma unroll
     for (int k = 0; k < ST_USED; k++) st.v[k] = 0;
     bool active = e < v.N;
     if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;
-    if (active) env_step_one<MODE>(v, io, e, st);
+    if (active) env_step_one<MODE>(v, io, e, st, &s_counts[threadIdx.x]);
     if (MODE != MODE_RESET) {
         // episode statistics: warp reduce (REDUX), lane k keeps counter k, one coalesced read-modify-write of the
         // warp's own row -- no atomics and no block barrier

@@ -124,7 +124,8 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
     io.tick = E->tick++;
     StepStats st;
     memset(&st, 0, sizeof(st));
-    for (int e = 0; e < N; e++) env_step_one<MODE_RESET>(v, io, e, st);
+    CountBytes scratch;
+    for (int e = 0; e < N; e++) env_step_one<MODE_RESET>(v, io, e, st, &scratch);
     return E;
 }
 
@@ -136,13 +137,14 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
     io.tick = E->tick++, io.ep_inc = 1;
     StepStats st;
     memset(&st, 0, sizeof(st));
+    CountBytes scratch;
     for (int e = 0; e < E->v.N; e++) {
         switch (mode) {
-        case 0: env_step_one<MODE_ACTION>(E->v, io, e, st); break;
-        case 1: env_step_one<MODE_INDEX>(E->v, io, e, st); break;
-        case 2: env_step_one<MODE_SAMPLED>(E->v, io, e, st); break;
+        case 0: env_step_one<MODE_ACTION>(E->v, io, e, st, &scratch); break;
+        case 1: env_step_one<MODE_INDEX>(E->v, io, e, st, &scratch); break;
+        case 2: env_step_one<MODE_SAMPLED>(E->v, io, e, st, &scratch); break;
         default:
-            if (!in || ((const uint8_t*)in)[e]) env_step_one<MODE_RESET>(E->v, io, e, st);
+            if (!in || ((const uint8_t*)in)[e]) env_step_one<MODE_RESET>(E->v, io, e, st, &scratch);
         }
     }
     if (mode != 3)

@@ -125,3 +125,17 @@ def test_env_replays_real_chess_v2_selfplay_games(golden):
             continue
         n += ph.check_trajectory_replay(lambda ib: EmulAdapter(1, opponent="none", auto_reset=False, initial_boards=ib), t)
     assert n > 5000
+
+
+def test_many_piece_templates_use_more_slots():
+    """initial boards with more than 16 pieces of one colour: more piece slots, uncounted-slot path of the ordered pick"""
+    rng = np.random.RandomState(4)
+    boards = np.zeros((6, 64), np.int8)
+    for i in range(6):
+        sq = rng.permutation(64)
+        boards[i, sq[:22]] = rng.choice([2, 3, 4, 5, 6], size=22)
+        boards[i, sq[22:40]] = -rng.choice([2, 3, 4, 5, 6], size=18)
+        boards[i, sq[40]], boards[i, sq[41]] = 1, -1
+    for opponent, color in (("none", "WHITE"), ("random", "BLACK")):
+        env = EmulAdapter(12, opponent=opponent, player_color=color, seed=11, auto_reset=True, initial_boards=boards)
+        ph.check_sampled_vs_oracle(env, opponent, color, 11, 150, boards=boards, compare_every=10)

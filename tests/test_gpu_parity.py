@@ -211,3 +211,79 @@ def test_smoke_entry():
     import __graft_entry__ as g
 
     g.smoke()
+
+
+def test_legal_views_agree_and_many_piece_templates(golden):
+    """possible_actions as list / mask / piece slots are three views of the same resident legal set; initial boards with
+    more than 16 pieces of one colour use more slots (and the uncounted-slot path of the ordered pick)."""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv
+
+    rng = np.random.RandomState(4)
+    boards = np.zeros((6, 64), np.int8)
+    for i in range(6):
+        sq = rng.permutation(64)
+        boards[i, sq[:22]] = rng.choice([2, 3, 4, 5, 6], size=22)       # 22 white pieces + king
+        boards[i, sq[22:40]] = -rng.choice([2, 3, 4, 5, 6], size=18)    # 18 black pieces + king
+        boards[i, sq[40]], boards[i, sq[41]] = 1, -1
+    env = GpuAdapter(24, opponent="none", seed=11, auto_reset=True, initial_boards=boards)
+    ph.check_sampled_vs_oracle(env, "none", "WHITE", 11, 120, boards=boards, compare_every=10)
+    e = env.env
+    assert e.piece_slots().shape[0] >= 23
+    legal, cnt = e.legal_actions(stride=256)
+    mask = e.legal_mask()
+    legal, cnt, mask = legal.cpu().numpy().view(np.uint16), cnt.cpu().numpy(), mask.cpu().numpy()
+    info = e.info_tensor().cpu().numpy()
+    assert (cnt == info[:, 9]).all()
+    for i in range(24):
+        assert sorted(int(a) for a in legal[i, : cnt[i]]) == [int(a) for a in np.nonzero(mask[i])[0]]
+    # default start position: slots are per-piece target sets whose sizes add up to n_legal
+    e2 = BatchedChessEnv(512, opponent="none", seed=3)
+    e2.step_sampled(40)
+    slots = e2.piece_slots()
+    pop = sum(((slots >> k) & 1) for k in range(64)).sum(0)
+    inf = e2.info_tensor()
+    castles = (inf[:, 13] & 1) + ((inf[:, 13] >> 1) & 1)
+    stm_pieces = torch.where(inf[:, 0] > 0, (e2.observe().reshape(512, 64) > 0).sum(1), (e2.observe().reshape(512, 64) < 0).sum(1))
+    live = torch.arange(slots.shape[0], device=slots.device)[:, None] < stm_pieces[None, :]
+    pop = (sum(((slots >> k) & 1) for k in range(64)) * live).sum(0)
+    assert torch.equal(pop.to(torch.int32) + castles.to(torch.int32), inf[:, 9])
+
+
+def test_compat_env_v2_replays_recorded_games(golden):
+    """the single-env gym-style class (reference surface) against games recorded from the REAL chess_v2.py: self-play,
+    and WHITE vs a callable opponent that replays the recorded bot moves (chess_v2.py:171-179 accepts callables)"""
+    from gym_chess_b200 import ChessEnvV2, codec
+
+    done_games = 0
+    for t in golden["trajectories"]:
+        if t["player_color"] != "WHITE" or done_games >= 14:
+            continue
+        if any(s["raised"] for s in t["steps"]):
+            continue
+        bot_moves = [s["bot_action"] for s in t["steps"]]
+        it = iter(bot_moves)
+        if t["opponent"] == "none":
+            env = ChessEnvV2(opponent="none", log=False, initial_board=np.array(t["initial_board"], np.int8).reshape(8, 8))
+        else:
+            cursor = {"i": 0}
+
+            def bot(e, cursor=cursor, moves=bot_moves):
+                return codec.action_to_move(moves[cursor["i"]])
+
+            env = ChessEnvV2(opponent=bot, log=False, initial_board=np.array(t["initial_board"], np.int8).reshape(8, 8))
+        assert [v for row in env.state["board"] for v in row] == t["reset"]["board"]
+        assert env.possible_actions == t["reset"]["legal"]
+        for i, s in enumerate(t["steps"][:120]):
+            if t["opponent"] != "none":
+                cursor["i"] = i
+            state, reward, done, info = env.step(s["action"])
+            assert (reward, done) == (s["reward"], s["done"]), (t["name"], i, reward, done, s["reward"], s["done"])
+            assert [v for row in state["board"] for v in row] == s["board"], (t["name"], i)
+            assert env.possible_actions == s["legal"] and info["move_count"] == s["move_count"], (t["name"], i)
+            assert state["current_player"] == s["current_player"]
+            if done:
+                break
+        env.close()
+        done_games += 1
+    assert done_games >= 10
