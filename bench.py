@@ -145,7 +145,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     N = args.envs_per_gpu
-    env = BatchedChessEnv(N, opponent="none", seed=2, device=local_rank, auto_reset=True, env_id_offset=rank * N)
+    off, _ = __import__("gym_chess_b200.sharding", fromlist=["x"]).shard_of(rank, world, N)
+    env = BatchedChessEnv(N, opponent="none", seed=2, device=local_rank, auto_reset=True, env_id_offset=off)
     L = _lib.lib()
 
     def barrier():
@@ -153,12 +154,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from gym_chess_b200 import sharding
+
     def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
+        return sharding.max_over_ranks(ms, device=dev)
 
     # ---- burn-in (game phases mix: episodes are ~270 plies long) + warm-up
     env.step_sampled(args.burn_in)
@@ -183,10 +182,7 @@ def main():
     value = world * N * args.steps / (ms * 1e-3)
 
     # ---- final NCCL reduce of the episode statistics (the only collective of the job)
-    stats_t = env.stats_tensor().clone()
-    if world > 1:
-        dist.all_reduce(stats_t, op=dist.ReduceOp.SUM)
-    tot = stats_t.cpu().numpy()
+    tot = sharding.reduce_stats(env.stats_tensor()).cpu().numpy()
 
     # ---- timed region 2: end to end through the host-buffer C ABI call, pinned host memory
     words = torch.empty((8, N), dtype=torch.int32).pin_memory()
@@ -216,6 +212,13 @@ def main():
     kernel_ms = ms / args.steps  # one launch per step, nothing else in the timed region
     achieved = bytes_per_step * N / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = peaks()
+    traffic = None  # dram bytes per launch of the step kernel from the committed ncu --set full capture (same N)
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        if tj.get("envs") == N:
+            traffic = tj["dram_bytes_per_launch"]
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -227,9 +230,10 @@ def main():
                 "steps": e2e_steps, "api": "gcb_env_step_index_host (BatchedChessEnv.step_index_host), pinned host buffers"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_env_step<MODE_SAMPLED>", "bytes_per_unit": bytes_per_step,
+                     "traffic": traffic, "kernel": "k_env_step<MODE_SAMPLED>", "bytes_per_unit": bytes_per_step,
                      "mean_hist_window": W, "peak_source": peak_src,
-                     "note": "integer-pipe / divergence bound, not HBM bound: see DESIGN.md and profiles/"},
+                     "algorithmic_bytes_per_launch": bytes_per_step * N,
+                     "note": "integer-pipe (ALU) bound, not HBM bound: see DESIGN.md section 3 and profiles/"},
         "episode_stats_all_ranks": {k: int(tot[i]) for i, k in enumerate(
             ("steps", "plies", "episodes", "mates", "repetitions", "caps", "wedged", "invalid", "reward_sum", "legal_sum",
              "in_check", "hist_overflow", "slot_overflow", "hist_scanned", "hist_window"))},
@@ -241,13 +245,16 @@ def main():
         import ctypes as C
         from gym_chess_b200._lib import Positions, check
 
-        # ---- legal-movegen positions/s on 1,048,576 positions (BASELINE.json configs[1]); positions = the first 1M
-        # resident env states of this rank (mid-game mix after burn-in), packed form, kernel-only
-        M = min(N, 1 << 20)
-        info = env.info_tensor()
-        pl = (info[:M, 0] < 0).to(torch.uint8).contiguous()
-        rt = (info[:M, 1] + 2 * info[:M, 2] + 4 * info[:M, 3] + 8 * info[:M, 4]).to(torch.uint8).contiguous()
-        p = env.positions()
+        # ---- legal-movegen positions/s on 1,048,576 positions (BASELINE.json configs[1]): the states of 1M envs after
+        # a burn-in of random self-play (all game phases, ~6% in check), packed form, kernel-only; output = the
+        # reference-ordered uint16 move list + count per position
+        M = 1 << 20
+        big = BatchedChessEnv(M, opponent="none", seed=7, device=local_rank)
+        big.step_sampled(max(200, min(args.burn_in, 400)))
+        info = big.info_tensor()
+        pl = (info[:, 0] < 0).to(torch.uint8).contiguous()
+        rt = (info[:, 1] + 2 * info[:, 2] + 4 * info[:, 3] + 8 * info[:, 4]).to(torch.uint8).contiguous()
+        p = big.positions()
         pos = Positions(p.bb01, p.bb23, pl.data_ptr(), rt.data_ptr())
         out = torch.empty((M, 144), dtype=torch.int16, device=dev)
         cnt = torch.empty(M, dtype=torch.int32, device=dev)
@@ -266,6 +273,22 @@ def main():
         line["movegen"] = {"metric": "legal_movegen_positions_per_sec", "value": M / (mg_ms * 1e-3), "positions": M,
                            "ms_per_launch": mg_ms, "mean_legal": nl, "bytes_per_position": mg_bytes,
                            "hbm_frac": mg_bytes * M / (mg_ms * 1e-3) / 1e9 / peak, "kernel": "k_movegen<false>"}
+        big.close()
+        del big, out, cnt
+        # ---- the same step with the reference-ordered action list of every env materialised after every step
+        # (possible_actions decoded from the resident piece slots): what a caller that reads the list each step pays
+        lst = torch.empty((N, 144), dtype=torch.int16, device=dev)
+        lcnt = torch.empty(N, dtype=torch.int32, device=dev)
+        ksteps = max(10, min(args.steps, 100))
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(ksteps):
+            env.step_sampled(1)
+            check(L.gcb_env_legal_actions(env._h, lst.data_ptr(), 144, lcnt.data_ptr(), None))
+        ev1.record()
+        torch.cuda.synchronize()
+        line["step_plus_action_list"] = {"value": N * ksteps / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT,
+                                         "note": "k_env_step + k_env_legal_list (uint16[N][144] list + count) per step"}
         # ---- BASELINE.json configs[2]: 65,536 envs on one GPU
         small = BatchedChessEnv(65536, opponent="none", seed=2, device=local_rank)
         small.step_sampled(args.burn_in)

@@ -325,6 +325,7 @@ struct StepIO {
     int32_t* bot_out;
     u64 tick;
     int ep_inc;
+    int e_begin, e_end;  // env range of this launch (host-buffer steps are pipelined in chunks)
 };
 
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step)

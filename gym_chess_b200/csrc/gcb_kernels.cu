@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -176,11 +177,11 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions
 template <int MODE>
 __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
     __shared__ CountBytes s_counts[GCB_BLOCK];
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = io.e_begin + blockIdx.x * blockDim.x + threadIdx.x;
     StepStats st;
 #pragma unroll
     for (int k = 0; k < ST_USED; k++) st.v[k] = 0;
-    bool active = e < v.N;
+    bool active = e < io.e_end;
     if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;
     if (active) env_step_one<MODE>(v, io, e, st, &s_counts[threadIdx.x]);
     if (MODE != MODE_RESET) {
@@ -467,6 +468,7 @@ struct gcb_env {
     // staging for the host-buffer step calls
     int32_t *d_in = nullptr, *d_reward = nullptr;
     uint8_t *d_done = nullptr, *d_flags = nullptr;
+    cudaStream_t streams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static const int8_t kDefaultBoard[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6, -6, -6, -6, -6, -6, -6, 0, 0, 0, 0, 0, 0,
@@ -474,15 +476,22 @@ static const int8_t kDefaultBoard[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6,
                                          0,  0,  0,  0,  6,  6,  6,  6,  6,  6,  6,  6,  3,  5,  4,  2,  1, 4, 5, 3};
 
 template <int MODE>
-static int launch_step(gcb_env* env, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, int32_t* act_out,
-                       int32_t* bot_out, int ep_inc, cudaStream_t s) {
+static int launch_range(gcb_env* env, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, int32_t* act_out,
+                        int32_t* bot_out, int ep_inc, int e_begin, int e_end, cudaStream_t s) {
     StepIO io;
     io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
-    io.tick = env->tick, io.ep_inc = ep_inc;
-    k_env_step<MODE><<<grid_for(env->v.N), GCB_BLOCK, 0, s>>>(env->v, io);
-    env->tick++;
+    io.tick = env->tick, io.ep_inc = ep_inc, io.e_begin = e_begin, io.e_end = e_end;
+    k_env_step<MODE><<<grid_for(e_end - e_begin), GCB_BLOCK, 0, s>>>(env->v, io);
     LAUNCHED();
     return GCB_OK;
+}
+
+template <int MODE>
+static int launch_step(gcb_env* env, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, int32_t* act_out,
+                       int32_t* bot_out, int ep_inc, cudaStream_t s) {
+    int rc = launch_range<MODE>(env, in, reward, done, flags, act_out, bot_out, ep_inc, 0, env->v.N, s);
+    env->tick++;
+    return rc;
 }
 
 extern "C" int gcb_env_destroy(gcb_env* env) {
@@ -492,6 +501,8 @@ extern "C" int gcb_env_destroy(gcb_env* env) {
     cudaFree(env->v.episode), cudaFree(env->v.tgt), cudaFree(env->v.hist), cudaFree(env->v.stats), cudaFree(env->v.stat_rows);
     cudaFree(env->t_bb01), cudaFree(env->t_bb23), cudaFree(env->t_meta), cudaFree(env->t_zkey), cudaFree(env->t_tgt), cudaFree(env->zob);
     cudaFree(env->d_in), cudaFree(env->d_reward), cudaFree(env->d_done), cudaFree(env->d_flags);
+    for (int c = 0; c < 8; c++)
+        if (env->streams[c]) cudaStreamDestroy(env->streams[c]);
     delete env;
     return GCB_OK;
 }
@@ -591,7 +602,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
         // episode 0 starts with a reset that does not advance the episode counter
         StepIO io;
         memset(&io, 0, sizeof(io));
-        io.tick = env->tick;
+        io.tick = env->tick, io.e_begin = 0, io.e_end = N;
         k_env_step<MODE_RESET><<<grid_for(N), GCB_BLOCK>>>(v, io);
         env->tick++;
         g_launches.fetch_add(1);
@@ -643,17 +654,74 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
     return GCB_OK;
 }
 
+// Host-buffer step: the batch is cut into chunks that travel on their own streams, so the H2D copy of chunk k+1, the
+// kernel of chunk k and the D2H copies of chunk k-1 overlap (PCIe is full duplex).  Envs are independent, so a step may
+// be issued range by range; all chunks share the step's ring tick.  Pass page-locked host buffers to get the overlap
+// (pageable memory still works, the copies then serialise).
+#define GCB_HOST_CHUNKS 8
+// device-visible alias of a page-locked host buffer (NULL for pageable memory)
+static void* mapped_ptr(const void* host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 static int step_host_common(gcb_env* env, int mode, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags) {
-    const size_t N = (size_t)env->v.N;
-    CU(cudaMemcpyAsync(env->d_in, in, N * 4, cudaMemcpyHostToDevice, 0));
-    int rc = mode == MODE_ACTION
-                 ? launch_step<MODE_ACTION>(env, env->d_in, env->d_reward, env->d_done, env->d_flags, nullptr, nullptr, 1, 0)
-                 : launch_step<MODE_INDEX>(env, env->d_in, env->d_reward, env->d_done, env->d_flags, nullptr, nullptr, 1, 0);
-    if (rc) return rc;
-    if (reward) CU(cudaMemcpyAsync(reward, env->d_reward, N * 4, cudaMemcpyDeviceToHost, 0));
-    if (done) CU(cudaMemcpyAsync(done, env->d_done, N, cudaMemcpyDeviceToHost, 0));
-    if (flags) CU(cudaMemcpyAsync(flags, env->d_flags, N, cudaMemcpyDeviceToHost, 0));
-    CU(cudaStreamSynchronize(0));
+    const int N = env->v.N;
+    // Zero-copy path: when every buffer is page-locked, the step kernel reads the actions and writes reward / done /
+    // flags straight through PCIe (coalesced 128-byte rows per warp) -- one launch, no staging copies, the transfers
+    // overlap the move generation of the other warps.
+    static int zero_copy = -1;
+    if (zero_copy < 0) {
+        const char* ev = getenv("GCB_HOST_ZEROCOPY");
+        zero_copy = ev ? atoi(ev) : 1;
+    }
+    if (zero_copy) {
+        void* m_in = mapped_ptr(in);
+        void* m_r = mapped_ptr(reward);
+        void* m_d = mapped_ptr(done);
+        void* m_f = mapped_ptr(flags);
+        if (m_in && (m_r || !reward) && (m_d || !done) && (m_f || !flags)) {
+            int rc = mode == MODE_ACTION
+                         ? launch_step<MODE_ACTION>(env, m_in, (int32_t*)m_r, (uint8_t*)m_d, (uint8_t*)m_f, nullptr, nullptr, 1, 0)
+                         : launch_step<MODE_INDEX>(env, m_in, (int32_t*)m_r, (uint8_t*)m_d, (uint8_t*)m_f, nullptr, nullptr, 1, 0);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(0));
+            return GCB_OK;
+        }
+    }
+    static int want = 0;  // GCB_HOST_CHUNKS=<1..8> overrides the default pipelining depth
+    if (!want) {
+        const char* ev = getenv("GCB_HOST_CHUNKS");
+        want = ev ? atoi(ev) : 4;
+        if (want < 1 || want > GCB_HOST_CHUNKS) want = 4;
+    }
+    int chunks = N >= want * 16384 ? want : (N >= 32768 ? 2 : 1);
+    int per = (((N + chunks - 1) / chunks) + GCB_BLOCK - 1) / GCB_BLOCK * GCB_BLOCK;  // whole blocks (and whole stat rows)
+    if (!env->streams[0])
+        for (int c = 0; c < GCB_HOST_CHUNKS; c++) CU(cudaStreamCreateWithFlags(&env->streams[c], cudaStreamNonBlocking));
+    CU(cudaStreamSynchronize(0));  // earlier work of this env on the default stream
+    const char* src = reinterpret_cast<const char*>(in);
+    for (int c = 0; c < chunks; c++) {
+        const int b = c * per, e = (b + per < N) ? b + per : N;
+        if (b >= e) break;
+        cudaStream_t s = env->streams[c];
+        CU(cudaMemcpyAsync(env->d_in + b, src + (size_t)b * 4, (size_t)(e - b) * 4, cudaMemcpyHostToDevice, s));
+        int rc = mode == MODE_ACTION ? launch_range<MODE_ACTION>(env, env->d_in, env->d_reward, env->d_done, env->d_flags, nullptr,
+                                                                  nullptr, 1, b, e, s)
+                                     : launch_range<MODE_INDEX>(env, env->d_in, env->d_reward, env->d_done, env->d_flags, nullptr,
+                                                                 nullptr, 1, b, e, s);
+        if (rc) return rc;
+        if (reward) CU(cudaMemcpyAsync(reward + b, env->d_reward + b, (size_t)(e - b) * 4, cudaMemcpyDeviceToHost, s));
+        if (done) CU(cudaMemcpyAsync(done + b, env->d_done + b, (size_t)(e - b), cudaMemcpyDeviceToHost, s));
+        if (flags) CU(cudaMemcpyAsync(flags + b, env->d_flags + b, (size_t)(e - b), cudaMemcpyDeviceToHost, s));
+    }
+    env->tick++;
+    for (int c = 0; c < chunks; c++) CU(cudaStreamSynchronize(env->streams[c]));
     return GCB_OK;
 }
 

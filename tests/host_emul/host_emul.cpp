@@ -121,7 +121,7 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
         make_template_one(i, n_templates > 0 ? template_boards : def, E->t_bb01, E->t_bb23, E->t_meta, E->t_zkey, E->t_tgt, E->t_cnt, slots);
     StepIO io;
     memset(&io, 0, sizeof(io));
-    io.tick = E->tick++;
+    io.tick = E->tick++, io.e_begin = 0, io.e_end = N;
     StepStats st;
     memset(&st, 0, sizeof(st));
     CountBytes scratch;
@@ -134,7 +134,7 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
                    int32_t* bot_out) {
     StepIO io;
     io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
-    io.tick = E->tick++, io.ep_inc = 1;
+    io.tick = E->tick++, io.ep_inc = 1, io.e_begin = 0, io.e_end = E->v.N;
     StepStats st;
     memset(&st, 0, sizeof(st));
     CountBytes scratch;

@@ -287,3 +287,27 @@ def test_compat_env_v2_replays_recorded_games(golden):
         env.close()
         done_games += 1
     assert done_games >= 10
+
+
+def test_host_step_paths_agree():
+    """the three transports of the same step -- device pointers, host buffers staged in pipelined chunks (pageable
+    memory), host buffers read/written in place by the kernel (page-locked memory, zero copy) -- give identical results"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv
+
+    N = 70000  # > 2 chunks of whole blocks, not a multiple of the block size
+    envs = [BatchedChessEnv(N, opponent="random", seed=13) for _ in range(3)]
+    rng = np.random.RandomState(2)
+    pin = lambda dt: torch.empty(N, dtype=dt).pin_memory()
+    pw, pr, pd, pf = pin(torch.int32), pin(torch.int32), pin(torch.uint8), pin(torch.uint8)
+    for t in range(60):
+        words = rng.randint(0, 2 ** 32, size=N, dtype=np.uint64).astype(np.uint32)
+        r0, d0, f0 = envs[0].step_index(torch.from_numpy(words.view(np.int32)).cuda())
+        r1, d1, f1 = envs[1].step_index_host(words)                       # pageable -> staged chunks
+        pw.numpy().view(np.uint32)[:] = words
+        envs[2].step_index_host(pw.numpy().view(np.uint32), pr.numpy(), pd.numpy(), pf.numpy())  # pinned -> zero copy
+        r0, d0, f0 = r0.cpu().numpy(), d0.cpu().numpy(), f0.cpu().numpy()
+        assert (r0 == r1).all() and (d0 == d1).all() and (f0 == f1).all(), t
+        assert (r0 == pr.numpy()).all() and (d0 == pd.numpy()).all() and (f0 == pf.numpy()).all(), t
+    s = [e.stats() for e in envs]
+    assert s[0] == s[1] == s[2] and s[0]["episodes"] > 0
