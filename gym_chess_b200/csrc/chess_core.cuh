@@ -597,14 +597,116 @@ GCB_HD void gen_attack_moves(const Board& b, int white_to_move, Emit& em) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ordered list from the slots, TYPE-MAJOR.  The position of a move in the reference-ordered list is
+//     offset(piece) + rank of the move inside the piece,     offset = prefix sum of the slot popcounts,
+// so once the offsets are known the pieces can be decoded in ANY order: all rooks, then bishops, ... -- the 32
+// positions of a warp run the same code (a rook's four rays, a knight's eight jumps) instead of 32 different
+// piece types.  Slots: get(r).  Offs: set(r, v) / get(r) (16 small integers of scratch).  Out: put(pos, action).
+// `mine` = the own pieces of this chunk (<= GCB_SLOTS), `base` = list length before the chunk; returns the new length.
+// ---------------------------------------------------------------------------------------------
+template <class Out>
+GCB_HD void emit_ray(Out& out, int& pos, int from64, u64 m, bool desc) {
+    if (desc) {
+        while (m) {
+            const int to = gcb_msb(m);
+            m ^= 1ULL << to;
+            out.put(pos++, from64 + to);
+        }
+    } else {
+        while (m) {
+            const int to = gcb_lsb(m);
+            m &= m - 1;
+            out.put(pos++, from64 + to);
+        }
+    }
+}
+
+template <class Slots, class Offs, class Out>
+GCB_HD int emit_chunk_typemajor(const Board& b, int white, u64 mine, const Slots& slots, Offs& offs, Out& out, int base) {
+    {
+        const int np = gcb_popc(mine);
+        int acc = base;
+        for (int r = 0; r < np; r++) {
+            offs.set(r, acc);
+            acc += gcb_popc(slots.get(r));
+        }
+        base = acc;
+    }
+    const u64 t0 = b.t0, t1 = b.t1, t2 = b.t2;
+#define GCB_PIECE(sq_)                                              \
+    const int sq = (sq_);                                           \
+    const int r = gcb_popc(mine & ((1ULL << sq) - 1));              \
+    const u64 T = slots.get(r);                                     \
+    int pos = offs.get(r);                                          \
+    const int from64 = sq * 64
+    // rooks: rays 0-3
+    for (u64 s = (t0 & t1 & ~t2) & mine; s;) {
+        GCB_PIECE(gcb_take(s));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++) emit_ray(out, pos, from64, T & GCB_GEOM(ord[0][sq][k]), (GCB_RAY_DESC_MASK >> k) & 1);
+    }
+    // bishops: rays 4-7
+    for (u64 s = (~t0 & ~t1 & t2) & mine; s;) {
+        GCB_PIECE(gcb_take(s));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 4; k < 8; k++) emit_ray(out, pos, from64, T & GCB_GEOM(ord[0][sq][k]), (GCB_RAY_DESC_MASK >> k) & 1);
+    }
+    // queens: all eight
+    for (u64 s = (~t0 & t1 & ~t2) & mine; s;) {
+        GCB_PIECE(gcb_take(s));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 8; k++) emit_ray(out, pos, from64, T & GCB_GEOM(ord[0][sq][k]), (GCB_RAY_DESC_MASK >> k) & 1);
+    }
+    // knights (lib.rs:891-900) and kings (lib.rs:797-806): eight single squares in the reference's order
+    for (u64 s = (t0 & ~t1 & t2) & mine; s;) {
+        GCB_PIECE(gcb_take(s));
+        const int d[8] = {-17, -15, 15, 17, -10, -6, 6, 10};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 8; k++)
+            if (T & sq_bit_safe(sq + d[k])) out.put(pos++, from64 + sq + d[k]);
+    }
+    for (u64 s = (t0 & ~t1 & ~t2) & mine; s;) {
+        GCB_PIECE(gcb_take(s));
+        const int d[8] = {8, -8, 1, -1, 9, 7, -7, -9};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 8; k++)
+            if (T & sq_bit_safe(sq + d[k])) out.put(pos++, from64 + sq + d[k]);
+    }
+    // pawns (lib.rs:935-959): one step, two steps, (row-p, col+1), (row-p, col-1)
+    {
+        const int d0 = white ? -8 : 8, d1 = white ? -16 : 16, d2 = white ? -7 : 9, d3 = white ? -9 : 7;
+        for (u64 s = (~t0 & t1 & t2) & mine; s;) {
+            GCB_PIECE(gcb_take(s));
+            if (T & sq_bit_safe(sq + d0)) out.put(pos++, from64 + sq + d0);
+            if (T & sq_bit_safe(sq + d1)) out.put(pos++, from64 + sq + d1);
+            if (T & sq_bit_safe(sq + d2)) out.put(pos++, from64 + sq + d2);
+            if (T & sq_bit_safe(sq + d3)) out.put(pos++, from64 + sq + d3);
+        }
+    }
+#undef GCB_PIECE
+    return base;
+}
+
 // Whole ordered legal list of one position through a small slot buffer (any number of own pieces): the
-// engine-level get_possible_moves.  Slots must offer put(r, T) / get(r) for r < GCB_SLOTS.
+// engine-level get_possible_moves.  Returns the list length.
 #define GCB_SLOTS 16
-template <class Slots, class Emit>
-GCB_HD void gen_legal_list(const Board& b, int white_to_move, u32 rights, Slots& slots, Emit& em, bool* in_check_out) {
+template <class Slots, class Offs, class Out>
+GCB_HD int gen_legal_list(const Board& b, int white_to_move, u32 rights, Slots& slots, Offs& offs, Out& out, bool* in_check_out) {
     GenCtx g;
     gen_prepare(b, white_to_move, g);
     if (in_check_out) *in_check_out = g.in_check;
+    int n = 0;
     u64 rem = g.own;
     while (rem) {
         // next chunk of at most GCB_SLOTS own pieces in square order
@@ -616,15 +718,12 @@ GCB_HD void gen_legal_list(const Board& b, int white_to_move, u32 rights, Slots&
         }
         rem ^= chunk;
         gen_targets(b, g, chunk, slots);
-        int r = 0;
-        for (u64 s = chunk; s; s &= s - 1, r++) {
-            const int sq = gcb_lsb(s);
-            emit_piece_moves(em, piece_code(b, sq), white_to_move, sq, slots.get(r));
-        }
+        n = emit_chunk_typemajor(b, white_to_move, chunk, slots, offs, out, n);
     }
     const u32 c = gen_castles(b, g, rights);
-    if (c & 1u) em.push(castle_action(white_to_move, 0));
-    if (c & 2u) em.push(castle_action(white_to_move, 1));
+    if (c & 1u) out.put(n++, castle_action(white_to_move, 0));
+    if (c & 2u) out.put(n++, castle_action(white_to_move, 1));
+    return n;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -517,21 +517,40 @@ GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulo
     zkey[i] = s.zk;
 }
 
-// ChessEnvV2.possible_actions (chess_v2.py:333-335) of env e: decode the slots into the reference-ordered list
-template <class Emit>
-GCB_HD void env_legal_list_one(const EnvView& v, int e, Emit& em) {
+// ordered list -> memory, one uint16 per move at its list position (moves beyond `cap` are dropped, the count is kept)
+struct ListOut {
+    uint16_t* out;
+    int cap;
+    GCB_HD void put(int pos, int action) {
+        if (pos < cap) out[pos] = (uint16_t)action;
+    }
+};
+
+// ChessEnvV2.possible_actions (chess_v2.py:333-335) of env e: decode the slots into the reference-ordered list.
+// Handles any number of slots by chunks of GCB_SLOTS.  Returns the list length.
+template <class Offs, class Out>
+GCB_HD int env_legal_list_one(const EnvView& v, int e, Offs& offs, Out& out) {
     EnvRegs s;
     ulonglong2 a = v.bb01[e], c = v.bb23[e];
     s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
     unpack_meta(v.meta[e], s);
-    TgtSink slots(v.tgt, v.N, e, v.slots, nullptr);
-    int r = 0;
-    for (u64 rem = stm_pieces(s); rem; rem &= rem - 1, r++) {
-        const int sq = gcb_lsb(rem);
-        emit_piece_moves(em, piece_code(s.b, sq), !s.stm_black, sq, slots.get(r));
+    int n = 0, r0 = 0;
+    u64 rem = stm_pieces(s);
+    while (rem) {
+        u64 chunk = rem;
+        if (gcb_popc(rem) > GCB_SLOTS) {
+            u64 t = rem;
+            for (int i = 0; i < GCB_SLOTS; i++) t &= t - 1;
+            chunk = rem ^ t;
+        }
+        rem ^= chunk;
+        TgtSink slots(v.tgt + (size_t)r0 * v.N, v.N, e, v.slots - r0, nullptr);
+        n = emit_chunk_typemajor(s.b, !s.stm_black, chunk, slots, offs, out, n);
+        r0 += GCB_SLOTS;
     }
-    if (s.castle & 1u) em.push(castle_action(!s.stm_black, 0));
-    if (s.castle & 2u) em.push(castle_action(!s.stm_black, 1));
+    if (s.castle & 1u) out.put(n++, castle_action(!s.stm_black, 0));
+    if (s.castle & 2u) out.put(n++, castle_action(!s.stm_black, 1));
+    return n;
 }
 
 // unpacked view of one env for export: board int8[64] (may be NULL) and info int32[16]

@@ -107,27 +107,38 @@ struct SmemSlots {
     __device__ __forceinline__ void replace(int r, u64, u64 t) { base[r * GCB_BLOCK] = t; }
 };
 
+// list offsets of one thread's pieces in shared memory
+struct SmemOffs {
+    uint16_t* base;
+    __device__ __forceinline__ void set(int r, int v) { base[r * GCB_BLOCK] = (uint16_t)v; }
+    __device__ __forceinline__ int get(int r) const { return base[r * GCB_BLOCK]; }
+};
+
 template <bool ATTACK>
 __global__ void __launch_bounds__(GCB_BLOCK) k_movegen(int n, gcb_positions pos, int castles_only,
                                                        uint16_t* __restrict__ actions, int stride,
                                                        int32_t* __restrict__ counts, uint8_t* __restrict__ incheck) {
     __shared__ u64 s_slots[ATTACK ? 1 : GCB_SLOTS * GCB_BLOCK];
+    __shared__ uint16_t s_offs[ATTACK ? 1 : GCB_SLOTS * GCB_BLOCK];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     ulonglong2 a = reinterpret_cast<const ulonglong2*>(pos.bb01)[i], c = reinterpret_cast<const ulonglong2*>(pos.bb23)[i];
     Board b = {a.x, a.y, c.x, c.y};
     const int white = pos.player[i] == 0;
     const u32 rights = mask_rights(b, pos.rights[i]);  // convert_py_state -> State::new, lib.rs:1267-1274
-    ListWriter lw(actions + (size_t)i * stride, stride);
     bool chk = false;
+    int cnt;
     if (ATTACK) {
+        ListWriter lw(actions + (size_t)i * stride, stride);
         gen_attack_moves(b, white, lw);
+        lw.flush();
+        cnt = lw.n;
     } else {
         SmemSlots slots = {s_slots + threadIdx.x};
-        gen_legal_list(b, white, rights, slots, lw, &chk);
+        SmemOffs offs = {s_offs + threadIdx.x};
+        ListOut out = {actions + (size_t)i * stride, stride};
+        cnt = gen_legal_list(b, white, rights, slots, offs, out, &chk);
     }
-    lw.flush();
-    int cnt = lw.n;
     if (castles_only) {  // get_castle_moves, lib.rs:1482-1500: the castle tail of the same list
         uint16_t* l = actions + (size_t)i * stride;
         int m = 0, lim = cnt < stride ? cnt : stride;
@@ -246,23 +257,26 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_export(EnvView v, int8_t* __r
 // ChessEnvV2.possible_actions for every env: the reference-ordered list decoded from the resident piece slots
 __global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_list(EnvView v, uint16_t* __restrict__ actions, int stride,
                                                               int32_t* __restrict__ counts) {
+    __shared__ uint16_t s_offs[GCB_SLOTS * GCB_BLOCK];
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= v.N) return;
-    ListWriter lw(actions + (size_t)e * stride, stride);
-    env_legal_list_one(v, e, lw);
-    lw.flush();
-    if (counts) counts[e] = lw.n;
+    SmemOffs offs = {s_offs + threadIdx.x};
+    ListOut out = {actions + (size_t)e * stride, stride};
+    const int n = env_legal_list_one(v, e, offs, out);
+    if (counts) counts[e] = n;
 }
 
-struct MaskWriter {
+struct MaskOut {
     uint8_t* m;
-    __device__ __forceinline__ void push(int action) { m[action] = 1; }
+    __device__ __forceinline__ void put(int, int action) { m[action] = 1; }
 };
 __global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_mask(EnvView v, uint8_t* __restrict__ mask) {
+    __shared__ uint16_t s_offs[GCB_SLOTS * GCB_BLOCK];
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= v.N) return;
-    MaskWriter mw = {mask + (size_t)e * 4101};
-    env_legal_list_one(v, e, mw);
+    SmemOffs offs = {s_offs + threadIdx.x};
+    MaskOut mo = {mask + (size_t)e * 4101};
+    env_legal_list_one(v, e, offs, mo);
 }
 
 // ------------------------------------------------------------------------------------------------ host side

@@ -15,6 +15,11 @@ struct LocalSlots {
     u64 get(int r) const { return t[r]; }
     void replace(int r, u64, u64 v) { t[r] = v; }
 };
+struct LocalOffs {
+    int o[GCB_SLOTS];
+    void set(int r, int v) { o[r] = v; }
+    int get(int r) const { return o[r]; }
+};
 
 void emul_movegen(int n, const int8_t* boards, const int8_t* players, const uint8_t* rights4, int attack, int castles_only,
                   uint16_t* out, int stride, int32_t* counts, uint8_t* incheck) {
@@ -23,13 +28,19 @@ void emul_movegen(int n, const int8_t* boards, const int8_t* players, const uint
         const uint8_t* q = rights4 + (size_t)i * 4;
         u32 rights = (q[0] ? RT_WK : 0) | (q[1] ? RT_WQ : 0) | (q[2] ? RT_BK : 0) | (q[3] ? RT_BQ : 0);
         rights = mask_rights(b, rights);
-        ListWriter lw(out + (size_t)i * stride, stride);
         bool chk = false;
-        LocalSlots slots;
-        if (attack) gen_attack_moves(b, players[i] > 0, lw);
-        else gen_legal_list(b, players[i] > 0, rights, slots, lw, &chk);
-        lw.flush();
-        int cnt = lw.n;
+        int cnt;
+        if (attack) {
+            ListWriter lw(out + (size_t)i * stride, stride);
+            gen_attack_moves(b, players[i] > 0, lw);
+            lw.flush();
+            cnt = lw.n;
+        } else {
+            LocalSlots slots;
+            LocalOffs offs;
+            ListOut lo = {out + (size_t)i * stride, stride};
+            cnt = gen_legal_list(b, players[i] > 0, rights, slots, offs, lo, &chk);
+        }
         if (castles_only) {
             uint16_t* l = out + (size_t)i * stride;
             int m = 0, lim = cnt < stride ? cnt : stride;
@@ -155,9 +166,9 @@ void emul_env_export(EmulEnv* E, int8_t* boards, int32_t* info, uint16_t* legal,
     for (int e = 0; e < E->v.N; e++) {
         env_export_one(E->v, e, boards ? boards + (size_t)e * 64 : nullptr, info ? info + (size_t)e * 16 : nullptr);
         if (legal) {  // possible_actions: decode of the piece slots
-            ListWriter lw(legal + (size_t)e * legal_stride, legal_stride);
-            env_legal_list_one(E->v, e, lw);
-            lw.flush();
+            LocalOffs offs;
+            ListOut lo = {legal + (size_t)e * legal_stride, legal_stride};
+            env_legal_list_one(E->v, e, offs, lo);
         }
     }
 }
