@@ -736,4 +736,6 @@ void gco_env_view(const gco_env *e, int8_t *board, int32_t *info, uint16_t *lega
     for (int k = 0; k < e->n_legal && k < legal_cap; k++) legal[k] = e->legal[k];
 }
 void gco_env_set_episode(gco_env *e, uint32_t episode) { e->episode = episode; }
+/* ChessEnvV2.moves_max (chess_v2.py:141) is a plain attribute: 149 unless the user changes it */
+void gco_env_set_moves_max(gco_env *e, int moves_max) { e->moves_max = moves_max; }
 void gco_env_force_bot(gco_env *e, int action) { e->forced_bot_action = action; }

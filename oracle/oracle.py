@@ -89,6 +89,7 @@ def lib():
         L.gco_env_pick.argtypes = [C.c_void_p, C.c_uint32]
         L.gco_env_view.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gco_env_set_episode.argtypes = [C.c_void_p, C.c_uint32]
+        L.gco_env_set_moves_max.argtypes = [C.c_void_p, C.c_int]
         L.gco_env_force_bot.argtypes = [C.c_void_p, C.c_int]
         L.gco_selfplay.argtypes = [C.c_void_p, C.c_uint64, P(Stats)]
         L.gco_selfplay_mt.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, P(Stats)]
@@ -194,12 +195,15 @@ class OracleEngine:
 class OracleEnv:
     """One env of the C restatement of chess_v2.py:183-294 (step / reset / random bot)."""
 
-    def __init__(self, initial_board=None, player_color=WHITE, opponent="none", seed=0, env_id=0, first_bot_action=-1):
+    def __init__(self, initial_board=None, player_color=WHITE, opponent="none", seed=0, env_id=0, first_bot_action=-1,
+                 moves_max=149):
         ib = None
         if initial_board is not None:
             self._ib = np.ascontiguousarray(np.asarray(initial_board, dtype=np.int8).reshape(64))
             ib = self._ib.ctypes.data
         self._h = lib().gco_env_new(ib, int(player_color == BLACK), {"none": 0, "random": 1}[opponent], seed, env_id)
+        if moves_max != 149:
+            lib().gco_env_set_moves_max(self._h, int(moves_max))
         if first_bot_action >= 0:  # replay: the reset inside gco_env_new already drew; redo it with the forced move
             lib().gco_env_force_bot(self._h, first_bot_action)
             lib().gco_env_reset(self._h)

@@ -158,12 +158,13 @@ def _cmp_export(env, oracles, tag):
 
 
 def check_sampled_vs_oracle(env, opponent, color, seed, steps, auto_reset=True, boards=None, env_id_offset=0,
-                            compare_every=25, mode="sampled", rng=None):
+                            compare_every=25, mode="sampled", rng=None, moves_max=149):
     """Run `steps` steps on the device env and replay the SAME draws through N oracle envs; compare every output of
     every step, the full state every `compare_every` steps, and the statistics at the end."""
     N = env.N
     nt = 1 if boards is None else len(boards)
-    O = [orc.OracleEnv(None if boards is None else boards[(env_id_offset + i) % nt], color, opponent, seed, env_id_offset + i)
+    O = [orc.OracleEnv(None if boards is None else boards[(env_id_offset + i) % nt], color, opponent, seed, env_id_offset + i,
+                       moves_max=moves_max)
          for i in range(N)]
     _cmp_export(env, O, "reset")
     tot = dict(steps=0, reward_sum=0, episodes=0)
@@ -217,3 +218,22 @@ def check_trajectory_replay(make_env, traj):
         assert (int(r[0]), bool(d[0])) == (int(s["reward"]), bool(s["done"])), (traj["name"], traj["seed"], i, r, d, s["reward"], s["done"])
         cmp(s, (traj["name"], traj["seed"], i))
     return len(traj["steps"])
+
+
+def endgame_boards():
+    """BASELINE.json configs[4]: repetition-heavy endgames (few irreversible moves -> long repetition windows)"""
+    def board(**pieces):
+        b = np.zeros(64, np.int8)
+        for sq, p in pieces.items():
+            b[int(sq[1:])] = p
+        return b
+    K, Q, R, B, N, P = 1, 2, 3, 4, 5, 6
+    return np.array([
+        board(s60=K, s4=-K),                        # K v K
+        board(s60=K, s59=R, s4=-K),                 # KR v K
+        board(s60=K, s58=B, s57=N, s4=-K),          # KBN v K
+        board(s60=K, s59=Q, s4=-K, s3=-R),          # KQ v KR
+        board(s60=K, s62=N, s4=-K, s1=-N),          # KN v KN
+        board(s60=K, s52=P, s4=-K, s12=-P),         # KP v KP (pawns stall on the last rank: no promotion, Q1)
+        board(s60=K, s61=B, s4=-K, s2=-B),          # KB v KB
+    ], np.int8)

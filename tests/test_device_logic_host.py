@@ -139,3 +139,15 @@ def test_many_piece_templates_use_more_slots():
     for opponent, color in (("none", "WHITE"), ("random", "BLACK")):
         env = EmulAdapter(12, opponent=opponent, player_color=color, seed=11, auto_reset=True, initial_boards=boards)
         ph.check_sampled_vs_oracle(env, opponent, color, 11, 150, boards=boards, compare_every=10)
+
+
+def test_endgames_with_long_repetition_windows():
+    """BASELINE.json configs[4]: repetition-heavy endgames, move cap lifted, 512-slot ring: the Bloom-gated ring scan
+    must find every 3-fold the reference's dict finds (windows grow to hundreds of plies here)"""
+    boards = ph.endgame_boards()
+    env = EmulAdapter(21, opponent="none", seed=17, auto_reset=True, initial_boards=boards, moves_max=250, history_cap=512)
+    st = ph.check_sampled_vs_oracle(env, "none", "WHITE", 17, 900, boards=boards, compare_every=50, moves_max=250)
+    assert st[4] > 20 and st[11] == 0  # repetitions happened, no ring overflow
+    assert st[14] / st[1] > 20         # mean window far above random play's ~6
+    env = EmulAdapter(14, opponent="random", player_color="BLACK", seed=18, auto_reset=True, initial_boards=boards, history_cap=512)
+    ph.check_sampled_vs_oracle(env, "random", "BLACK", 18, 500, boards=boards, compare_every=50)  # BLACK agent: no cap (Q12)

@@ -311,3 +311,27 @@ def test_host_step_paths_agree():
         assert (r0 == pr.numpy()).all() and (d0 == pd.numpy()).all() and (f0 == pf.numpy()).all(), t
     s = [e.stats() for e in envs]
     assert s[0] == s[1] == s[2] and s[0]["episodes"] > 0
+
+
+def test_endgames_with_long_repetition_windows():
+    """BASELINE.json configs[4]: repetition/promotion-heavy endgames with a 512-ply Zobrist history.  Parity against the
+    oracle at a size it replays in seconds; at 1M envs the size-independent properties."""
+    from gym_chess_b200 import BatchedChessEnv
+
+    boards = ph.endgame_boards()
+    env = GpuAdapter(210, opponent="none", seed=17, auto_reset=True, initial_boards=boards, moves_max=250, history_cap=512)
+    st = ph.check_sampled_vs_oracle(env, "none", "WHITE", 17, 900, boards=boards, compare_every=100, moves_max=250)
+    assert st[4] > 100 and st[11] == 0 and st[14] / st[1] > 20, [int(x) for x in st]
+    N = 1 << 20
+    big = BatchedChessEnv(N, opponent="none", seed=5, initial_boards=boards, moves_max=250, history_cap=512)
+    big.step_sampled(700)
+    s = big.stats()
+    assert s["steps"] == N * 700 and s["hist_overflow"] == 0 and s["slot_overflow"] == 0 and s["caps"] >= 0
+    assert s["episodes"] == s["mates"] + s["repetitions"] + s["wedged"] + s["caps"] and s["repetitions"] > N // 4, s
+    assert s["hist_window"] / s["plies"] > 20, s
+    # sharding invariance at full size: the first 4096 envs of the 1M set == a 4096-env set with the same ids
+    small = BatchedChessEnv(4096, opponent="none", seed=5, initial_boards=boards, moves_max=250, history_cap=512)
+    small.step_sampled(700)
+    bb, ib, _ = big.export_numpy()
+    bs, is_, _ = small.export_numpy()
+    assert (bb[:4096] == bs).all() and (ib[:4096] == is_).all()
