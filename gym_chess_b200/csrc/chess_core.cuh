@@ -143,7 +143,8 @@ struct alignas(16) GeomTables {
     u64 line[64][4];    // file, rank, diagonal, anti-diagonal through sq, WITHOUT sq
     u64 ord[5][64][8];  // ordered direction masks per class
     u64 knight[64], king[64];
-    constexpr GeomTables() : line(), ord(), knight(), king() {
+    u64 pawn[2][64][2];  // [black][sq]: {push squares (one step; two from the start row), capture squares}
+    constexpr GeomTables() : line(), ord(), knight(), king(), pawn() {
         const int sl[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
         const int kg[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
         const int kn[8][2] = {{-2, -1}, {-2, 1}, {2, -1}, {2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}};
@@ -170,9 +171,15 @@ struct alignas(16) GeomTables {
                 if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[2][sq][k] |= 1ULL << (tr * 8 + tc), knight[sq] |= 1ULL << (tr * 8 + tc);
                 if (k < 4) {
                     tr = r + wp[k][0], tc = c + wp[k][1];
-                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[3][sq][k] |= 1ULL << (tr * 8 + tc);
+                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) {
+                        ord[3][sq][k] |= 1ULL << (tr * 8 + tc);
+                        if (k != 1 || r == 6) pawn[0][sq][k >= 2] |= 1ULL << (tr * 8 + tc);  // two steps from row 6 only
+                    }
                     tr = r + bp[k][0], tc = c + bp[k][1];
-                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[4][sq][k] |= 1ULL << (tr * 8 + tc);
+                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) {
+                        ord[4][sq][k] |= 1ULL << (tr * 8 + tc);
+                        if (k != 1 || r == 1) pawn[1][sq][k >= 2] |= 1ULL << (tr * 8 + tc);  // two steps from row 1 only
+                    }
                 }
             }
         }
@@ -469,14 +476,7 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         for (u64 s = pw; s;) {
             const int sq = gcb_take(s);
             const u64 bit = 1ULL << sq;
-            // colour-agnostic: a rotation by 56 is a shift down by 8 for every row but row 0 (masked out), so the
-            // white and black pawns of a warp run the same instructions
-            const int fwd = g.white ? 56 : 8;
-            const u64 last = g.white ? 0x00000000000000FFULL : 0xFF00000000000000ULL;   // no step from the last row
-            const u64 start = g.white ? 0x00FF000000000000ULL : 0x000000000000FF00ULL;  // two steps from here
-            const u64 one = gcb_rotl64(bit & ~last, fwd);
-            const u64 push = one | gcb_rotl64(gcb_rotl64(bit & start, fwd), fwd);
-            const u64 cap = ((one & ~GCB_FILE_H) << 1) | ((one & ~GCB_FILE_A) >> 1);
+            const u64 push = GCB_GEOM(pawn[!g.white][sq][0]), cap = GCB_GEOM(pawn[!g.white][sq][1]);
             GCB_PUT(sq, bit, ((push & ~occ) | (cap & g.enemy)) & g.cm);
         }
     }

@@ -132,26 +132,26 @@ struct alignas(16) CountBytes {
 };
 struct TgtSink {
     u64* base;
-    size_t N;
+    unsigned N;  // slot r of this env at base[r * N]; slots * N < 2^31 (checked at create), 32-bit index arithmetic
     int slots, dropped, extra;  // extra = targets of pieces beyond the 16 counted slots
     uint8_t* cb;
     GCB_HD TgtSink(u64* tgt, int n, int e, int s, CountBytes* scratch)
-        : base(tgt + e), N((size_t)n), slots(s), dropped(0), extra(0), cb(scratch ? scratch->c : nullptr) {
+        : base(tgt + e), N((unsigned)n), slots(s), dropped(0), extra(0), cb(scratch ? scratch->c : nullptr) {
         if (scratch) {
             u64* z = reinterpret_cast<u64*>(scratch);
             z[0] = 0, z[1] = 0;
         }
     }
     GCB_HD void put(int r, u64 t) {
-        if (r < slots) base[(size_t)r * N] = t;
+        if (r < slots) base[(unsigned)r * N] = t;
         else dropped++;
         const int c = gcb_popc(t);
         if (r < 16) cb[r] = (uint8_t)c;
         else extra += c;
     }
-    GCB_HD u64 get(int r) const { return r < slots ? base[(size_t)r * N] : 0ULL; }
+    GCB_HD u64 get(int r) const { return r < slots ? base[(unsigned)r * N] : 0ULL; }
     GCB_HD void replace(int r, u64 told, u64 tnew) {  // tnew is a subset of told
-        if (r < slots) base[(size_t)r * N] = tnew;
+        if (r < slots) base[(unsigned)r * N] = tnew;
         const int c = gcb_popc(tnew);
         if (r < 16) cb[r] = (uint8_t)c;
         else extra -= gcb_popc(told) - c;

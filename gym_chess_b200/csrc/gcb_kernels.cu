@@ -541,6 +541,8 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
         if (cfg.piece_slots == 0) cfg.piece_slots = need;
         if (cfg.piece_slots < need || cfg.piece_slots > 64)
             return fail(GCB_E_ARG, "gcb_env_create", "piece_slots must be 0 (auto) or in [max pieces per side, 64]");
+        if ((long long)cfg.piece_slots * cfg.num_envs >= (1LL << 31))
+            return fail(GCB_E_ARG, "gcb_env_create", "num_envs * piece_slots must stay below 2^31 (shard the envs)");
     }
     if (cfg.history_cap == 0) cfg.history_cap = 512;
     if (cfg.moves_max < 0) cfg.moves_max = 149;
