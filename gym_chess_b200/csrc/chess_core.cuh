@@ -144,7 +144,8 @@ struct alignas(16) GeomTables {
     u64 ord[5][64][8];  // ordered direction masks per class
     u64 knight[64], king[64];
     u64 pawn[2][64][2];  // [black][sq]: {push squares (one step; two from the start row), capture squares}
-    constexpr GeomTables() : line(), ord(), knight(), king(), pawn() {
+    u64 between[64][64]; // squares strictly between two aligned squares (0 when not aligned)
+    constexpr GeomTables() : line(), ord(), knight(), king(), pawn(), between() {
         const int sl[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
         const int kg[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
         const int kn[8][2] = {{-2, -1}, {-2, 1}, {2, -1}, {2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}};
@@ -161,9 +162,14 @@ struct alignas(16) GeomTables {
                 if (tr + tc == r + c) line[sq][3] |= 1ULL << t;
             }
             for (int k = 0; k < 8; k++) {
+                u64 walked = 0;
                 for (int i = 1; i < 8; i++) {
                     const int tr = r + i * sl[k][0], tc = c + i * sl[k][1];
-                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[0][sq][k] |= 1ULL << (tr * 8 + tc);
+                    if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) {
+                        ord[0][sq][k] |= 1ULL << (tr * 8 + tc);
+                        between[sq][tr * 8 + tc] = walked;
+                        walked |= 1ULL << (tr * 8 + tc);
+                    }
                 }
                 int tr = r + kg[k][0], tc = c + kg[k][1];
                 if (tr >= 0 && tr < 8 && tc >= 0 && tc < 8) ord[1][sq][k] |= 1ULL << (tr * 8 + tc), king[sq] |= 1ULL << (tr * 8 + tc);
@@ -392,25 +398,25 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     const int ksq = ref_king_square(ownk);
     const u64 kbit = 1ULL << ksq;
     g.ksq = ksq;
-    const u64 rk = rook_att(ksq, occ), bk = bishop_att(ksq, occ);
-    // pieces that attack the king square right now (attack sets are symmetric; an enemy pawn attacks ksq
-    // iff it stands where a pawn of the MOVER's colour on ksq would attack; enemy kings count, Q22)
-    const u64 chk = (knight_set_att(kbit) & g.knights & enemy) | (king_set_att(kbit) & ekings) |
-                    (pawn_set_att(kbit, white_to_move) & g.pawns & enemy) | (rk & eRQ) | (bk & eBQ);
+    // pieces that attack the king square right now (attack sets are symmetric; an enemy pawn attacks ksq iff it
+    // stands where a pawn of the MOVER's colour on ksq would attack; enemy kings count, Q22)
+    u64 chk = (GCB_GEOM(knight[ksq]) & g.knights & enemy) | (GCB_GEOM(king[ksq]) & ekings) |
+              (GCB_GEOM(pawn[!white_to_move][ksq][1]) & g.pawns & enemy);
+    // enemy sliders on a line through the king square that they move along: nothing in between -> checker; exactly
+    // one piece in between and it is ours -> that piece is pinned to the ray (between | pinner)
+    const u64 cand = (eRQ & (GCB_GEOM(line[ksq][0]) | GCB_GEOM(line[ksq][1]))) | (eBQ & (GCB_GEOM(line[ksq][2]) | GCB_GEOM(line[ksq][3])));
+    for (u64 p = cand; p;) {
+        const int psq = gcb_take(p);
+        const u64 btw = GCB_GEOM(between[ksq][psq]), blockers = btw & occ;
+        if (!blockers) chk |= 1ULL << psq;
+        else if (!(blockers & (blockers - 1)) && (blockers & g.own)) g.pinned |= blockers, g.pinrays |= btw | (1ULL << psq);
+    }
     g.in_check = chk != 0;
     if (chk) {
         if (chk & (chk - 1)) g.cm = 0;  // two or more attackers: no non-king move can remove both
-        else g.cm = chk | between_excl(ksq, gcb_lsb(chk));
+        else g.cm = chk | GCB_GEOM(between[ksq][gcb_lsb(chk)]);
     }
-    // pins: drop the own pieces the king "sees" first on each ray and look again
-    const u64 xr = rook_att(ksq, occ ^ (rk & g.own)) & ~rk & eRQ;
-    const u64 xb = bishop_att(ksq, occ ^ (bk & g.own)) & ~bk & eBQ;
-    for (u64 p = xr | xb; p;) {
-        const int psq = gcb_take(p);
-        const u64 btw = between_excl(ksq, psq);
-        g.pinned |= btw & g.own;
-        g.pinrays |= btw | (1ULL << psq);
-    }
+    (void)kbit;
 }
 
 // the squares a pinned piece on `sq` may move to: its own pin ray (between(king, pinner) | pinner)
