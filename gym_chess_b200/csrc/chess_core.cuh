@@ -361,8 +361,7 @@ GCB_HD u64 between_excl(int a, int b) {
 }
 
 struct GenCtx {
-    u64 occ, own, enemy;
-    u64 kings, queens, rooks, bishops, knights, pawns;
+    u64 occ, own, enemy;  // the per-type sets are recomputed from the planes where they are used (2 LOP3 each): fewer live registers
     u64 eatt;     // opponent attack map on the CURRENT board, own king left on it (lib.rs:466-470; Q6)
     u64 satt;     // attack map of the side to move, accumulated by gen_targets (check flag of the other side)
     u64 cm;       // targets that resolve the check for a non-king piece (all ones when not in check / no king)
@@ -378,21 +377,19 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     g.occ = bb_occ(b);
     g.own = white_to_move ? b.w : (g.occ & ~b.w);
     g.enemy = g.occ & ~g.own;
-    g.kings = bb_kings(b), g.queens = bb_queens(b), g.rooks = bb_rooks(b), g.bishops = bb_bishops(b);
-    g.knights = bb_knights(b), g.pawns = bb_pawns(b);
     const u64 occ = g.occ, enemy = g.enemy;
-    const u64 ekings = g.kings & enemy;
-    const u64 eRQ = (g.rooks | g.queens) & enemy, eBQ = (g.bishops | g.queens) & enemy;
+    const u64 ekings = bb_kings(b) & enemy;
+    const u64 eRQ = (bb_rooks(b) | bb_queens(b)) & enemy, eBQ = (bb_bishops(b) | bb_queens(b)) & enemy;
 
     // opponent attack map (lib.rs:669-677): pawns minus squares holding the attacker's OWN king (Q14)
-    u64 eatt = pawn_set_att(g.pawns & enemy, !white_to_move) & ~ekings;
-    eatt |= knight_set_att(g.knights & enemy) | king_set_att(ekings);
+    u64 eatt = pawn_set_att(bb_pawns(b) & enemy, !white_to_move) & ~ekings;
+    eatt |= knight_set_att(bb_knights(b) & enemy) | king_set_att(ekings);
     for (u64 s = eRQ; s;) eatt |= rook_att(gcb_take(s), occ);
     for (u64 s = eBQ; s;) eatt |= bishop_att(gcb_take(s), occ);
     g.eatt = eatt;
 
     g.satt = 0, g.cm = ~0ULL, g.pinned = 0, g.pinrays = 0, g.ksq = 0, g.in_check = false;
-    const u64 ownk = g.kings & g.own;
+    const u64 ownk = bb_kings(b) & g.own;
     g.has_king = ownk != 0;
     if (!g.has_king) return;  // lib.rs:655-658: no king -> nothing is filtered
     const int ksq = ref_king_square(ownk);
@@ -400,8 +397,8 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     g.ksq = ksq;
     // pieces that attack the king square right now (attack sets are symmetric; an enemy pawn attacks ksq iff it
     // stands where a pawn of the MOVER's colour on ksq would attack; enemy kings count, Q22)
-    u64 chk = (GCB_GEOM(knight[ksq]) & g.knights & enemy) | (GCB_GEOM(king[ksq]) & ekings) |
-              (GCB_GEOM(pawn[!white_to_move][ksq][1]) & g.pawns & enemy);
+    u64 chk = (GCB_GEOM(knight[ksq]) & bb_knights(b) & enemy) | (GCB_GEOM(king[ksq]) & ekings) |
+              (GCB_GEOM(pawn[!white_to_move][ksq][1]) & bb_pawns(b) & enemy);
     // enemy sliders on a line through the king square that they move along: nothing in between -> checker; exactly
     // one piece in between and it is ours -> that piece is pinned to the ray (between | pinner)
     const u64 cand = (eRQ & (GCB_GEOM(line[ksq][0]) | GCB_GEOM(line[ksq][1]))) | (eBQ & (GCB_GEOM(line[ksq][2]) | GCB_GEOM(line[ksq][3])));
@@ -439,35 +436,35 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         sink.put(gcb_popc(mine & ((bit_) - 1)), t__);                  \
     } while (0)
     // rooks
-    for (u64 s = g.rooks & mine; s;) {
+    for (u64 s = bb_rooks(b) & mine; s;) {
         const int sq = gcb_take(s);
         const u64 bit = 1ULL << sq, a = rook_att(sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // bishops
-    for (u64 s = g.bishops & mine; s;) {
+    for (u64 s = bb_bishops(b) & mine; s;) {
         const int sq = gcb_take(s);
         const u64 bit = 1ULL << sq, a = bishop_att(sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // queens
-    for (u64 s = g.queens & mine; s;) {
+    for (u64 s = bb_queens(b) & mine; s;) {
         const int sq = gcb_take(s);
         const u64 bit = 1ULL << sq, a = rook_att(sq, occ) | bishop_att(sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // knights
-    for (u64 s = g.knights & mine; s;) {
+    for (u64 s = bb_knights(b) & mine; s;) {
         const int sq = gcb_take(s);
         const u64 bit = 1ULL << sq, a = GCB_GEOM(knight[sq]);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // kings: never passed through the legality filter (lib.rs:615-619); attack map with the king on it (Q6)
-    for (u64 s = g.kings & mine; s;) {
+    for (u64 s = bb_kings(b) & mine; s;) {
         const int sq = gcb_take(s);
         const u64 bit = 1ULL << sq, a = GCB_GEOM(king[sq]);
         g.satt |= a;
@@ -476,8 +473,8 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
     // pawns (lib.rs:918-964): one step if empty; two steps from the start row if the TARGET is empty (the
     // jumped square is not tested, Q13); diagonals onto enemy pieces incl. the king; no en passant
     {
-        const u64 pw = g.pawns & mine, allp = g.pawns & own;
-        g.satt |= pawn_set_att(pw, g.white) & ~(g.kings & own);  // Q14
+        const u64 pw = bb_pawns(b) & mine, allp = bb_pawns(b) & own;
+        g.satt |= pawn_set_att(pw, g.white) & ~(bb_kings(b) & own);  // Q14
         (void)allp;
         for (u64 s = pw; s;) {
             const int sq = gcb_take(s);
@@ -489,7 +486,7 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
 #undef GCB_PUT
     // pinned pieces (rare per position, but some env of a warp nearly always has one): one fix-up pass over the
     // slots instead of a pin test at every generation site
-    for (u64 p = g.pinned & mine & ~g.kings; p;) {
+    for (u64 p = g.pinned & mine & ~bb_kings(b); p;) {
         const int sq = gcb_take(p), r = gcb_popc(mine & ((1ULL << sq) - 1));
         const u64 t = sink.get(r), t2 = t & pin_mask(g, sq);
         sink.replace(r, t, t2);
@@ -501,7 +498,7 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
 // true in play.  bit0 = queen side (listed first, lib.rs:992), bit1 = king side.
 GCB_HD u32 gen_castles(const Board& b, const GenCtx& g, u32 rights) {
     if (!g.has_king) return 0;
-    const u64 wR = g.rooks & b.w, wK = g.kings & b.w, occ = g.occ, eatt = g.eatt;
+    const u64 wR = bb_rooks(b) & b.w, wK = bb_kings(b) & b.w, occ = g.occ, eatt = g.eatt;
     u32 c = 0;
     if (g.white) {
         if (!(rights & (RT_WK | RT_WQ))) return 0;

@@ -169,6 +169,45 @@ struct TgtSink {
     }
 };
 
+// per-thread statistics of one step: the small counters live as bit fields of ONE register (fewer live registers in
+// the step kernel), the wide ones in four ints
+struct StepStats {
+    u32 f;  // bit 0 steps, 1-2 plies, 3 episodes, 4 mates, 5 repetitions, 6 caps, 7 wedged, 8 invalid, 9 in_check,
+            // 10-12 hist_overflow, 13-14 slot_overflow
+    int reward, legal, scan, window;
+    GCB_HD void clear() { f = 0, reward = 0, legal = 0, scan = 0, window = 0; }
+    GCB_HD int get(int k) const {
+        switch (k) {
+        case ST_STEPS: return (int)(f & 1u);
+        case ST_PLIES: return (int)((f >> 1) & 3u);
+        case ST_EPISODES: return (int)((f >> 3) & 1u);
+        case ST_MATES: return (int)((f >> 4) & 1u);
+        case ST_REPS: return (int)((f >> 5) & 1u);
+        case ST_CAPS: return (int)((f >> 6) & 1u);
+        case ST_WEDGED: return (int)((f >> 7) & 1u);
+        case ST_INVALID: return (int)((f >> 8) & 1u);
+        case ST_REWARD: return reward;
+        case ST_LEGAL: return legal;
+        case ST_INCHECK: return (int)((f >> 9) & 1u);
+        case ST_HISTOVF: return (int)((f >> 10) & 7u);
+        case ST_SLOTOVF: return (int)((f >> 13) & 3u);
+        case ST_HISTSCAN: return scan;
+        default: return window;
+        }
+    }
+};
+#define SF_STEPS 1u
+#define SF_PLIES (1u << 1)
+#define SF_EPISODES (1u << 3)
+#define SF_MATES (1u << 4)
+#define SF_REPS (1u << 5)
+#define SF_CAPS (1u << 6)
+#define SF_WEDGED (1u << 7)
+#define SF_INVALID (1u << 8)
+#define SF_INCHECK (1u << 9)
+#define SF_HISTOVF (1u << 10)
+#define SF_SLOTOVF (1u << 13)
+
 // history ring bookkeeping: `cursor` = next slot of this tick; hist_len = length of the contiguous
 // window of slots behind the cursor that may hold an equal board (reset by irreversible plies)
 struct HistCursor {
@@ -176,12 +215,12 @@ struct HistCursor {
     int cursor;  // 0..pps
 };
 
-GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int k, int* ovf) {
+GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int k, StepStats& st) {
     while (hc.cursor < k) {
         if (s.hist_len > 0) {
             v.hist[((hc.base + hc.cursor) & (u64)v.hist_mask) * (u64)v.N + e] = 0;  // "no ply in this slot"
             if (s.hist_len < v.hist_mask) s.hist_len++;
-            else (*ovf)++;
+            else st.f += SF_HISTOVF;
         }
         hc.cursor++;
     }
@@ -240,9 +279,7 @@ GCB_HD bool action_is_legal(const EnvView& v, int e, const EnvRegs& s, int actio
     return false;
 }
 
-struct StepStats {
-    int v[ST_USED];
-};
+
 
 // One ply = player_move (chess_v2.py:393-412: engine.next_state + repetition count on the PRE-move
 // board) + the state setter (315-323) + switch_player (296-299) + get_possible_moves for the new
@@ -253,7 +290,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
     int r = 0;
     *rep = false;
     if (apply) {
-        hist_skip_to(v, e, s, hc, slot, &st.v[ST_HISTOVF]);
+        hist_skip_to(v, e, s, hc, slot, st);
         const u64 key = hist_key(s.zk);
         const u64 cur = hc.base + slot;
         // repetition count of the pre-move board over the reversible window.  The ring is read only when the
@@ -276,9 +313,9 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
 #endif
                 for (int i = 0; i < 8; i++) cnt += (h[i] == key);
             }
-            st.v[ST_HISTSCAN] += s.hist_len;
+            st.scan += s.hist_len;
         }
-        st.v[ST_WINDOW] += s.hist_len;
+        st.window += s.hist_len;
         *rep = cnt >= 2;  // saved_boards[key] reaches 3 with this ply
         v.hist[(cur & (u64)v.hist_mask) * (u64)v.N + e] = key;
         hc.cursor = slot + 1;
@@ -292,7 +329,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
         s.rights = rights;
         if (irr) s.hist_len = 0, s.seen1 = 0, s.seen2 = 0;
         else if (s.hist_len < v.hist_mask) s.hist_len++;
-        else st.v[ST_HISTOVF]++;
+        else st.f += SF_HISTOVF;
     }
     s.stm_black ^= 1;
     GenCtx g;
@@ -300,14 +337,14 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
     TgtSink sink(v.tgt, v.N, e, v.slots, scratch);
     gen_targets(s.b, g, g.own, sink);
     const int n = sink.total();
-    if (sink.dropped) st.v[ST_SLOTOVF] += 1;
+    if (sink.dropped) st.f += SF_SLOTOVF;
     s.cnt_lo = sink.count_lo(), s.cnt_hi = sink.count_hi();
     s.castle = gen_castles(s.b, g, mask_rights(s.b, s.rights));
     s.n_legal = n + (int)(s.castle & 1u) + (int)(s.castle >> 1);
     // both check flags (update_state, lib.rs:1386-1393): the side to move from the attackers of its king
     // square, the side that just moved from the attack map the generation accumulated
     u32 chk = g.in_check ? (1u << s.stm_black) : 0u;
-    const u64 mk = g.kings & g.enemy;
+    const u64 mk = bb_kings(s.b) & g.enemy;
     if (mk && ((g.satt >> ref_king_square(mk)) & 1ULL)) chk |= 1u << (s.stm_black ^ 1);
     s.chk = chk;
     return r;
@@ -366,10 +403,10 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
                 valid = true;
             }
         }
-        st.v[ST_STEPS] += 1, st.v[ST_LEGAL] += n0, st.v[ST_INCHECK] += stm_checked(s) ? 1 : 0;
+        st.f += SF_STEPS + (stm_checked(s) ? SF_INCHECK : 0u), st.legal += n0;
         s.step++;
         if (!valid) {  // chess_v2.py:240-242, before the done test (Q16)
-            R = -10, d_out = s.done, fl |= EF_INVALID, st.v[ST_INVALID] += 1;
+            R = -10, d_out = s.done, fl |= EF_INVALID, st.f += SF_INVALID;
             phase = PH_FINAL;
         } else if (s.done) {  // chess_v2.py:245-251
             R = 0, d_out = true;
@@ -398,13 +435,13 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
                 terminal = d_out || s.n_legal == 0;
                 if (!d_out && s.n_legal == 0) fl |= EF_WEDGED;
                 if (n0 == 0 || was_done || (fl & EF_INVALID)) {
-                } else if (capped) st.v[ST_CAPS] += 1;
+                } else if (capped) st.f += SF_CAPS;
                 else if (d_out) {
-                    if (fl & EF_MATE) st.v[ST_MATES] += 1;
-                    else st.v[ST_REPS] += 1;
-                } else if (s.n_legal == 0) st.v[ST_WEDGED] += 1;
-                if (terminal) st.v[ST_EPISODES] += 1;
-                st.v[ST_REWARD] += R;
+                    if (fl & EF_MATE) st.f += SF_MATES;
+                    else st.f += SF_REPS;
+                } else if (s.n_legal == 0) st.f += SF_WEDGED;
+                if (terminal) st.f += SF_EPISODES;
+                st.reward += R;
                 if (v.auto_reset && terminal) fl |= EF_RESET;
                 if (io.reward) io.reward[e] = R;
                 if (io.done) io.done[e] = d_out ? 1 : 0;
@@ -446,7 +483,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
         }
         bool rep;
         const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st, scratch);
-        if (do_apply) st.v[ST_PLIES] += 1;
+        if (do_apply) st.f += SF_PLIES;
         const bool mate = s.n_legal == 0 && stm_checked(s);
         if (phase == PH_AGENT) {
             agent_ply = true;
@@ -479,7 +516,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
             phase = PH_END;
         }
     }
-    hist_skip_to(v, e, s, hc, v.pps, &st.v[ST_HISTOVF]);
+    hist_skip_to(v, e, s, hc, v.pps, st);
     if (MODE != MODE_RESET && io.bot_out) io.bot_out[e] = bot_action;
 
     v.bb01[e] = make_ulonglong2(s.b.t0, s.b.t1);

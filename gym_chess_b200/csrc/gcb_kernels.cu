@@ -43,7 +43,9 @@ extern "C" int gcb_device_count(void) {
     return n;
 }
 
+#ifndef GCB_BLOCK
 #define GCB_BLOCK 128
+#endif
 #ifndef GCB_STEP_MIN_BLOCKS
 #define GCB_STEP_MIN_BLOCKS 5
 #endif
@@ -190,8 +192,7 @@ __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(Env
     __shared__ CountBytes s_counts[GCB_BLOCK];
     const int e = io.e_begin + blockIdx.x * blockDim.x + threadIdx.x;
     StepStats st;
-#pragma unroll
-    for (int k = 0; k < ST_USED; k++) st.v[k] = 0;
+    st.clear();
     bool active = e < io.e_end;
     if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;
     if (active) env_step_one<MODE>(v, io, e, st, &s_counts[threadIdx.x]);
@@ -199,11 +200,33 @@ __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(Env
         // episode statistics: warp reduce (REDUX), lane k keeps counter k, one coalesced read-modify-write of the
         // warp's own row -- no atomics and no block barrier
         const int lane = threadIdx.x & 31;
+        // the bit-field counters are widened into three words whose fields cannot overflow over 32 lanes:
+        // 7 REDUX in all instead of one per counter
+        const u32 f = st.f;
+        const u32 w0 = (f & 1u) | (((f >> 1) & 3u) << 6) | (((f >> 3) & 1u) << 13) | (((f >> 4) & 1u) << 19) | (((f >> 5) & 1u) << 25);
+        const u32 w1 = ((f >> 6) & 1u) | (((f >> 7) & 1u) << 6) | (((f >> 8) & 1u) << 12) | (((f >> 9) & 1u) << 18) | (((f >> 13) & 3u) << 24);
+        const u32 r0 = __reduce_add_sync(0xffffffffu, w0), r1 = __reduce_add_sync(0xffffffffu, w1);
+        const u32 r2 = __reduce_add_sync(0xffffffffu, (f >> 10) & 7u);
+        const int t_reward = __reduce_add_sync(0xffffffffu, st.reward), t_legal = __reduce_add_sync(0xffffffffu, st.legal);
+        const int t_scan = __reduce_add_sync(0xffffffffu, st.scan), t_window = __reduce_add_sync(0xffffffffu, st.window);
         long long mine = 0;
-#pragma unroll
-        for (int k = 0; k < ST_USED; k++) {
-            const int t = __reduce_add_sync(0xffffffffu, st.v[k]);
-            if (lane == k) mine = t;
+        switch (lane) {
+        case ST_STEPS: mine = r0 & 63u; break;
+        case ST_PLIES: mine = (r0 >> 6) & 127u; break;
+        case ST_EPISODES: mine = (r0 >> 13) & 63u; break;
+        case ST_MATES: mine = (r0 >> 19) & 63u; break;
+        case ST_REPS: mine = (r0 >> 25) & 63u; break;
+        case ST_CAPS: mine = r1 & 63u; break;
+        case ST_WEDGED: mine = (r1 >> 6) & 63u; break;
+        case ST_INVALID: mine = (r1 >> 12) & 63u; break;
+        case ST_REWARD: mine = t_reward; break;
+        case ST_LEGAL: mine = t_legal; break;
+        case ST_INCHECK: mine = (r1 >> 18) & 63u; break;
+        case ST_HISTOVF: mine = r2; break;
+        case ST_SLOTOVF: mine = (r1 >> 24) & 127u; break;
+        case ST_HISTSCAN: mine = t_scan; break;
+        case ST_WINDOW: mine = t_window; break;
+        default: break;
         }
         if (lane < ST_USED) v.stat_rows[(size_t)(e >> 5) * ST_COUNT + lane] += (u64)mine;
     }

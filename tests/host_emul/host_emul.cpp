@@ -134,9 +134,11 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
     memset(&io, 0, sizeof(io));
     io.tick = E->tick++, io.e_begin = 0, io.e_end = N;
     StepStats st;
-    memset(&st, 0, sizeof(st));
     CountBytes scratch;
-    for (int e = 0; e < N; e++) env_step_one<MODE_RESET>(v, io, e, st, &scratch);
+    for (int e = 0; e < N; e++) {
+        st.clear();
+        env_step_one<MODE_RESET>(v, io, e, st, &scratch);
+    }
     return E;
 }
 
@@ -147,9 +149,9 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
     io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
     io.tick = E->tick++, io.ep_inc = 1, io.e_begin = 0, io.e_end = E->v.N;
     StepStats st;
-    memset(&st, 0, sizeof(st));
     CountBytes scratch;
     for (int e = 0; e < E->v.N; e++) {
+        st.clear();  // the counters of ONE env step (bit fields): summed into the totals env by env
         switch (mode) {
         case 0: env_step_one<MODE_ACTION>(E->v, io, e, st, &scratch); break;
         case 1: env_step_one<MODE_INDEX>(E->v, io, e, st, &scratch); break;
@@ -157,9 +159,9 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
         default:
             if (!in || ((const uint8_t*)in)[e]) env_step_one<MODE_RESET>(E->v, io, e, st, &scratch);
         }
+        if (mode != 3)
+            for (int k = 0; k < ST_USED; k++) E->v.stats[k] += (u64)(long long)st.get(k);
     }
-    if (mode != 3)
-        for (int k = 0; k < ST_USED; k++) E->v.stats[k] += (u64)(long long)st.v[k];
 }
 
 void emul_env_export(EmulEnv* E, int8_t* boards, int32_t* info, uint16_t* legal, int legal_stride) {
