@@ -33,6 +33,16 @@ static inline ulonglong2 make_ulonglong2(u64 x, u64 y) {
 }
 #endif
 
+// The resident state is touched once per step: stream it past L1 (ld.global.cs / st.global.cs, evict-first) so that
+// the geometry tables the generation hammers stay L1-resident.
+#if defined(__CUDA_ARCH__)
+#define GCB_LDS(p) __ldcs(p)
+#define GCB_STS(p, v) __stcs((p), (v))
+#else
+#define GCB_LDS(p) (*(p))
+#define GCB_STS(p, v) (*(p) = (v))
+#endif
+
 // per-env flags (mirrors include/gymchess_b200.h GCB_F_*)
 #define EF_INVALID 1u
 #define EF_MATE 2u
@@ -143,15 +153,15 @@ struct TgtSink {
         }
     }
     GCB_HD void put(int r, u64 t) {
-        if (r < slots) base[(unsigned)r * N] = t;
+        if (r < slots) GCB_STS(&base[(unsigned)r * N], t);
         else dropped++;
         const int c = gcb_popc(t);
         if (r < 16) cb[r] = (uint8_t)c;
         else extra += c;
     }
-    GCB_HD u64 get(int r) const { return r < slots ? base[(unsigned)r * N] : 0ULL; }
+    GCB_HD u64 get(int r) const { return r < slots ? GCB_LDS(&base[(unsigned)r * N]) : 0ULL; }
     GCB_HD void replace(int r, u64 told, u64 tnew) {  // tnew is a subset of told
-        if (r < slots) base[(unsigned)r * N] = tnew;
+        if (r < slots) GCB_STS(&base[(unsigned)r * N], tnew);
         const int c = gcb_popc(tnew);
         if (r < 16) cb[r] = (uint8_t)c;
         else extra -= gcb_popc(told) - c;
@@ -218,7 +228,7 @@ struct HistCursor {
 GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int k, StepStats& st) {
     while (hc.cursor < k) {
         if (s.hist_len > 0) {
-            v.hist[((hc.base + hc.cursor) & (u64)v.hist_mask) * (u64)v.N + e] = 0;  // "no ply in this slot"
+            GCB_STS(&v.hist[((hc.base + hc.cursor) & (u64)v.hist_mask) * (u64)v.N + e], 0ULL);  // "no ply in this slot"
             if (s.hist_len < v.hist_mask) s.hist_len++;
             else st.f += SF_HISTOVF;
         }
@@ -307,7 +317,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
 #pragma unroll
 #endif
                 for (int i = 0; i < 8; i++)
-                    h[i] = (j0 + i <= s.hist_len) ? v.hist[((cur - (u64)(j0 + i)) & (u64)v.hist_mask) * (u64)v.N + e] : 0ULL;
+                    h[i] = (j0 + i <= s.hist_len) ? GCB_LDS(&v.hist[((cur - (u64)(j0 + i)) & (u64)v.hist_mask) * (u64)v.N + e]) : 0ULL;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -317,7 +327,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
         }
         st.window += s.hist_len;
         *rep = cnt >= 2;  // saved_boards[key] reaches 3 with this ply
-        v.hist[(cur & (u64)v.hist_mask) * (u64)v.N + e] = key;
+        GCB_STS(&v.hist[(cur & (u64)v.hist_mask) * (u64)v.N + e], key);
         hc.cursor = slot + 1;
         if (s.seen1 & bbit) s.seen2 |= bbit;
         s.seen1 |= bbit;
@@ -370,14 +380,14 @@ template <int MODE>
 GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& st, CountBytes* scratch) {
     EnvRegs s;
     {
-        ulonglong2 a = v.bb01[e], c = v.bb23[e];
+        ulonglong2 a = GCB_LDS(&v.bb01[e]), c = GCB_LDS(&v.bb23[e]);
         s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
-        ulonglong2 bl = v.bloom[e], ct = v.cnt[e];
+        ulonglong2 bl = GCB_LDS(&v.bloom[e]), ct = GCB_LDS(&v.cnt[e]);
         s.seen1 = bl.x, s.seen2 = bl.y, s.cnt_lo = ct.x, s.cnt_hi = ct.y;
     }
-    unpack_meta(v.meta[e], s);
-    s.zk = v.zkey[e];
-    u32 ep = v.episode[e];
+    unpack_meta(GCB_LDS(&v.meta[e]), s);
+    s.zk = GCB_LDS(&v.zkey[e]);
+    u32 ep = GCB_LDS(&v.episode[e]);
     const u32 genv = v.env_offset + (u32)e;
     HistCursor hc;
     hc.base = io.tick * (u64)v.pps, hc.cursor = 0;
@@ -519,13 +529,13 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     hist_skip_to(v, e, s, hc, v.pps, st);
     if (MODE != MODE_RESET && io.bot_out) io.bot_out[e] = bot_action;
 
-    v.bb01[e] = make_ulonglong2(s.b.t0, s.b.t1);
-    v.bb23[e] = make_ulonglong2(s.b.t2, s.b.w);
-    v.bloom[e] = make_ulonglong2(s.seen1, s.seen2);
-    v.cnt[e] = make_ulonglong2(s.cnt_lo, s.cnt_hi);
-    v.meta[e] = pack_meta(s);
-    v.zkey[e] = s.zk;
-    v.episode[e] = ep;
+    GCB_STS(&v.bb01[e], make_ulonglong2(s.b.t0, s.b.t1));
+    GCB_STS(&v.bb23[e], make_ulonglong2(s.b.t2, s.b.w));
+    GCB_STS(&v.bloom[e], make_ulonglong2(s.seen1, s.seen2));
+    GCB_STS(&v.cnt[e], make_ulonglong2(s.cnt_lo, s.cnt_hi));
+    GCB_STS(&v.meta[e], pack_meta(s));
+    GCB_STS(&v.zkey[e], s.zk);
+    GCB_STS(&v.episode[e], ep);
 }
 
 // initial state of one template board (ChessEnvV2.reset up to the first movegen, chess_v2.py:188-206)
