@@ -50,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
         except OSError:
             self.proc = None
             return
@@ -93,7 +93,7 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     # a step = one env step of a bounded sample of the workload's envs
-    sample = 2048
+    sample = 8192
     from oracle import oracle as orc
 
     for _ in range(args.warmup):
