@@ -373,6 +373,7 @@ struct StepIO {
     u64 tick;
     int ep_inc;
     int e_begin, e_end;  // env range of this launch (host-buffer steps are pipelined in chunks)
+    int nsteps;          // MODE_SAMPLED: consecutive steps run by ONE launch (envs are independent: no grid-wide sync needed)
 };
 
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step)

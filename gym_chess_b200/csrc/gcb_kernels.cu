@@ -191,45 +191,55 @@ template <int MODE>
 __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
     __shared__ CountBytes s_counts[GCB_BLOCK];
     const int e = io.e_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    StepStats st;
-    st.clear();
+    const int lane = threadIdx.x & 31;
     bool active = e < io.e_end;
     if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;
-    if (active) env_step_one<MODE>(v, io, e, st, &s_counts[threadIdx.x]);
-    if (MODE != MODE_RESET) {
-        // episode statistics: warp reduce (REDUX), lane k keeps counter k, one coalesced read-modify-write of the
-        // warp's own row -- no atomics and no block barrier
-        const int lane = threadIdx.x & 31;
-        // the bit-field counters are widened into three words whose fields cannot overflow over 32 lanes:
-        // 7 REDUX in all instead of one per counter
-        const u32 f = st.f;
-        const u32 w0 = (f & 1u) | (((f >> 1) & 3u) << 6) | (((f >> 3) & 1u) << 13) | (((f >> 4) & 1u) << 19) | (((f >> 5) & 1u) << 25);
-        const u32 w1 = ((f >> 6) & 1u) | (((f >> 7) & 1u) << 6) | (((f >> 8) & 1u) << 12) | (((f >> 9) & 1u) << 18) | (((f >> 13) & 3u) << 24);
-        const u32 r0 = __reduce_add_sync(0xffffffffu, w0), r1 = __reduce_add_sync(0xffffffffu, w1);
-        const u32 r2 = __reduce_add_sync(0xffffffffu, (f >> 10) & 7u);
-        const int t_reward = __reduce_add_sync(0xffffffffu, st.reward), t_legal = __reduce_add_sync(0xffffffffu, st.legal);
-        const int t_scan = __reduce_add_sync(0xffffffffu, st.scan), t_window = __reduce_add_sync(0xffffffffu, st.window);
-        long long mine = 0;
-        switch (lane) {
-        case ST_STEPS: mine = r0 & 63u; break;
-        case ST_PLIES: mine = (r0 >> 6) & 127u; break;
-        case ST_EPISODES: mine = (r0 >> 13) & 63u; break;
-        case ST_MATES: mine = (r0 >> 19) & 63u; break;
-        case ST_REPS: mine = (r0 >> 25) & 63u; break;
-        case ST_CAPS: mine = r1 & 63u; break;
-        case ST_WEDGED: mine = (r1 >> 6) & 63u; break;
-        case ST_INVALID: mine = (r1 >> 12) & 63u; break;
-        case ST_REWARD: mine = t_reward; break;
-        case ST_LEGAL: mine = t_legal; break;
-        case ST_INCHECK: mine = (r1 >> 18) & 63u; break;
-        case ST_HISTOVF: mine = r2; break;
-        case ST_SLOTOVF: mine = (r1 >> 24) & 127u; break;
-        case ST_HISTSCAN: mine = t_scan; break;
-        case ST_WINDOW: mine = t_window; break;
-        default: break;
+    // Sampled self-play runs `nsteps` consecutive steps in one launch: every env only depends on its own previous step,
+    // so a block simply keeps stepping its envs -- no launch gap, no wave tail between steps.
+    const int nsteps = MODE == MODE_SAMPLED ? io.nsteps : 1;
+    long long acc = 0;  // lane k accumulates statistics counter k of this warp
+#pragma unroll 1
+    for (int t = 0; t < nsteps; t++) {
+        StepStats st;
+        st.clear();
+        if (active) env_step_one<MODE>(v, io, e, st, &s_counts[threadIdx.x]);
+        if (MODE != MODE_RESET) {
+            // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The bit-field counters are widened into
+            // three words whose fields cannot overflow over 32 lanes: 7 REDUX in all instead of one per counter
+            const u32 f = st.f;
+            const u32 w0 = (f & 1u) | (((f >> 1) & 3u) << 6) | (((f >> 3) & 1u) << 13) | (((f >> 4) & 1u) << 19) | (((f >> 5) & 1u) << 25);
+            const u32 w1 = ((f >> 6) & 1u) | (((f >> 7) & 1u) << 6) | (((f >> 8) & 1u) << 12) | (((f >> 9) & 1u) << 18) | (((f >> 13) & 3u) << 24);
+            const u32 r0 = __reduce_add_sync(0xffffffffu, w0), r1 = __reduce_add_sync(0xffffffffu, w1);
+            const u32 r2 = __reduce_add_sync(0xffffffffu, (f >> 10) & 7u);
+            const int t_reward = __reduce_add_sync(0xffffffffu, st.reward), t_legal = __reduce_add_sync(0xffffffffu, st.legal);
+            const int t_scan = __reduce_add_sync(0xffffffffu, st.scan), t_window = __reduce_add_sync(0xffffffffu, st.window);
+            long long mine = 0;
+            switch (lane) {
+            case ST_STEPS: mine = r0 & 63u; break;
+            case ST_PLIES: mine = (r0 >> 6) & 127u; break;
+            case ST_EPISODES: mine = (r0 >> 13) & 63u; break;
+            case ST_MATES: mine = (r0 >> 19) & 63u; break;
+            case ST_REPS: mine = (r0 >> 25) & 63u; break;
+            case ST_CAPS: mine = r1 & 63u; break;
+            case ST_WEDGED: mine = (r1 >> 6) & 63u; break;
+            case ST_INVALID: mine = (r1 >> 12) & 63u; break;
+            case ST_REWARD: mine = t_reward; break;
+            case ST_LEGAL: mine = t_legal; break;
+            case ST_INCHECK: mine = (r1 >> 18) & 63u; break;
+            case ST_HISTOVF: mine = r2; break;
+            case ST_SLOTOVF: mine = (r1 >> 24) & 127u; break;
+            case ST_HISTSCAN: mine = t_scan; break;
+            case ST_WINDOW: mine = t_window; break;
+            default: break;
+            }
+            acc += mine;
         }
-        if (lane < ST_USED) v.stat_rows[(size_t)(e >> 5) * ST_COUNT + lane] += (u64)mine;
+        io.tick++;
+        if (io.act_out) io.act_out += v.N;
+        if (io.bot_out) io.bot_out += v.N;
     }
+    // one coalesced read-modify-write of the warp's own row -- no atomics and no block barrier
+    if (MODE != MODE_RESET && lane < ST_USED) v.stat_rows[(size_t)(e >> 5) * ST_COUNT + lane] += (u64)acc;
 }
 
 // totals = column sums of the per-warp rows (one block; deterministic order)
@@ -517,7 +527,7 @@ static int launch_range(gcb_env* env, const void* in, int32_t* reward, uint8_t* 
                         int32_t* bot_out, int ep_inc, int e_begin, int e_end, cudaStream_t s) {
     StepIO io;
     io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
-    io.tick = env->tick, io.ep_inc = ep_inc, io.e_begin = e_begin, io.e_end = e_end;
+    io.tick = env->tick, io.ep_inc = ep_inc, io.e_begin = e_begin, io.e_end = e_end, io.nsteps = 1;
     k_env_step<MODE><<<grid_for(e_end - e_begin), GCB_BLOCK, 0, s>>>(env->v, io);
     LAUNCHED();
     return GCB_OK;
@@ -641,7 +651,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
         // episode 0 starts with a reset that does not advance the episode counter
         StepIO io;
         memset(&io, 0, sizeof(io));
-        io.tick = env->tick, io.e_begin = 0, io.e_end = N;
+        io.tick = env->tick, io.e_begin = 0, io.e_end = N, io.nsteps = 1;
         k_env_step<MODE_RESET><<<grid_for(N), GCB_BLOCK>>>(v, io);
         env->tick++;
         g_launches.fetch_add(1);
@@ -680,15 +690,22 @@ extern "C" int gcb_env_step_index(gcb_env* env, const uint32_t* d_u32, int32_t* 
     return launch_step<MODE_INDEX>(env, d_u32, d_reward, d_done, d_flags, nullptr, nullptr, 1, (cudaStream_t)stream);
 }
 
+#define GCB_MAX_STEPS_PER_LAUNCH 64
 extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward, uint8_t* d_done, uint8_t* d_flags,
                                     int32_t* d_actions_out, int32_t* d_bot_out, void* stream) {
     ENV_CHECK(env);
     if (nsteps < 0) return fail(GCB_E_ARG, "gcb_env_step_sampled", "nsteps < 0");
     const size_t N = (size_t)env->v.N;
-    for (int t = 0; t < nsteps; t++) {
-        int rc = launch_step<MODE_SAMPLED>(env, nullptr, d_reward, d_done, d_flags, d_actions_out ? d_actions_out + t * N : nullptr,
-                                           d_bot_out ? d_bot_out + t * N : nullptr, 1, (cudaStream_t)stream);
-        if (rc) return rc;
+    for (int t = 0; t < nsteps;) {
+        const int k = nsteps - t < GCB_MAX_STEPS_PER_LAUNCH ? nsteps - t : GCB_MAX_STEPS_PER_LAUNCH;
+        StepIO io;
+        io.in = nullptr, io.reward = d_reward, io.done = d_done, io.flags = d_flags;
+        io.act_out = d_actions_out ? d_actions_out + t * N : nullptr, io.bot_out = d_bot_out ? d_bot_out + t * N : nullptr;
+        io.tick = env->tick, io.ep_inc = 1, io.e_begin = 0, io.e_end = env->v.N, io.nsteps = k;
+        k_env_step<MODE_SAMPLED><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
+        LAUNCHED();
+        env->tick += (u64)k;
+        t += k;
     }
     return GCB_OK;
 }

@@ -132,7 +132,7 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
         make_template_one(i, n_templates > 0 ? template_boards : def, E->t_bb01, E->t_bb23, E->t_meta, E->t_zkey, E->t_tgt, E->t_cnt, slots);
     StepIO io;
     memset(&io, 0, sizeof(io));
-    io.tick = E->tick++, io.e_begin = 0, io.e_end = N;
+    io.tick = E->tick++, io.e_begin = 0, io.e_end = N, io.nsteps = 1;
     StepStats st;
     CountBytes scratch;
     for (int e = 0; e < N; e++) {
@@ -147,7 +147,7 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
                    int32_t* bot_out) {
     StepIO io;
     io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
-    io.tick = E->tick++, io.ep_inc = 1, io.e_begin = 0, io.e_end = E->v.N;
+    io.tick = E->tick++, io.ep_inc = 1, io.e_begin = 0, io.e_end = E->v.N, io.nsteps = 1;
     StepStats st;
     CountBytes scratch;
     for (int e = 0; e < E->v.N; e++) {
