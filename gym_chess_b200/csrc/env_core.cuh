@@ -376,19 +376,29 @@ struct StepIO {
     int nsteps;          // MODE_SAMPLED: consecutive steps run by ONE launch (envs are independent: no grid-wide sync needed)
 };
 
-// chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step)
-template <int MODE>
-GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& st, CountBytes* scratch) {
-    EnvRegs s;
-    {
-        ulonglong2 a = GCB_LDS(&v.bb01[e]), c = GCB_LDS(&v.bb23[e]);
-        s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
-        ulonglong2 bl = GCB_LDS(&v.bloom[e]), ct = GCB_LDS(&v.cnt[e]);
-        s.seen1 = bl.x, s.seen2 = bl.y, s.cnt_lo = ct.x, s.cnt_hi = ct.y;
-    }
+// resident state of env e <-> registers
+GCB_HD void env_load(const EnvView& v, int e, EnvRegs& s, u32& ep) {
+    ulonglong2 a = GCB_LDS(&v.bb01[e]), c = GCB_LDS(&v.bb23[e]);
+    s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
+    ulonglong2 bl = GCB_LDS(&v.bloom[e]), ct = GCB_LDS(&v.cnt[e]);
+    s.seen1 = bl.x, s.seen2 = bl.y, s.cnt_lo = ct.x, s.cnt_hi = ct.y;
     unpack_meta(GCB_LDS(&v.meta[e]), s);
     s.zk = GCB_LDS(&v.zkey[e]);
-    u32 ep = GCB_LDS(&v.episode[e]);
+    ep = GCB_LDS(&v.episode[e]);
+}
+GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
+    GCB_STS(&v.bb01[e], make_ulonglong2(s.b.t0, s.b.t1));
+    GCB_STS(&v.bb23[e], make_ulonglong2(s.b.t2, s.b.w));
+    GCB_STS(&v.bloom[e], make_ulonglong2(s.seen1, s.seen2));
+    GCB_STS(&v.cnt[e], make_ulonglong2(s.cnt_lo, s.cnt_hi));
+    GCB_STS(&v.meta[e], pack_meta(s));
+    GCB_STS(&v.zkey[e], s.zk);
+    GCB_STS(&v.episode[e], ep);
+}
+
+// chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step), state in registers
+template <int MODE>
+GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch) {
     const u32 genv = v.env_offset + (u32)e;
     HistCursor hc;
     hc.base = io.tick * (u64)v.pps, hc.cursor = 0;
@@ -529,14 +539,15 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     }
     hist_skip_to(v, e, s, hc, v.pps, st);
     if (MODE != MODE_RESET && io.bot_out) io.bot_out[e] = bot_action;
+}
 
-    GCB_STS(&v.bb01[e], make_ulonglong2(s.b.t0, s.b.t1));
-    GCB_STS(&v.bb23[e], make_ulonglong2(s.b.t2, s.b.w));
-    GCB_STS(&v.bloom[e], make_ulonglong2(s.seen1, s.seen2));
-    GCB_STS(&v.cnt[e], make_ulonglong2(s.cnt_lo, s.cnt_hi));
-    GCB_STS(&v.meta[e], pack_meta(s));
-    GCB_STS(&v.zkey[e], s.zk);
-    GCB_STS(&v.episode[e], ep);
+template <int MODE>
+GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& st, CountBytes* scratch) {
+    EnvRegs s;
+    u32 ep;
+    env_load(v, e, s, ep);
+    env_step_regs<MODE>(v, io, e, s, ep, st, scratch);
+    env_store(v, e, s, ep);
 }
 
 // initial state of one template board (ChessEnvV2.reset up to the first movegen, chess_v2.py:188-206)

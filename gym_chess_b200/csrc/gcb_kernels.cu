@@ -198,11 +198,14 @@ __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(Env
     // so a block simply keeps stepping its envs -- no launch gap, no wave tail between steps.
     const int nsteps = MODE == MODE_SAMPLED ? io.nsteps : 1;
     long long acc = 0;  // lane k accumulates statistics counter k of this warp
+    EnvRegs s;          // the env's state stays in registers from step to step
+    u32 ep = 0;
+    if (active) env_load(v, e, s, ep);
 #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
         StepStats st;
         st.clear();
-        if (active) env_step_one<MODE>(v, io, e, st, &s_counts[threadIdx.x]);
+        if (active) env_step_regs<MODE>(v, io, e, s, ep, st, &s_counts[threadIdx.x]);
         if (MODE != MODE_RESET) {
             // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The bit-field counters are widened into
             // three words whose fields cannot overflow over 32 lanes: 7 REDUX in all instead of one per counter
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(Env
         if (io.act_out) io.act_out += v.N;
         if (io.bot_out) io.bot_out += v.N;
     }
+    if (active) env_store(v, e, s, ep);
     // one coalesced read-modify-write of the warp's own row -- no atomics and no block barrier
     if (MODE != MODE_RESET && lane < ST_USED) v.stat_rows[(size_t)(e >> 5) * ST_COUNT + lane] += (u64)acc;
 }
