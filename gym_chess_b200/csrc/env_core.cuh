@@ -140,28 +140,48 @@ GCB_HD u64 stm_pieces(const EnvRegs& s) { return s.stm_black ? (bb_occ(s.b) & ~s
 struct alignas(16) CountBytes {
     uint8_t c[16];
 };
+// where the piece slots of one env live: slot r at base[r * stride].  Resident form: base = tgt + e, stride = N
+// (streamed past L1); inside a multi-step launch: the thread's column of a shared-memory tile (plain accesses).
+struct SlotRef {
+    u64* base;
+    unsigned stride;  // slots * stride < 2^31 (checked at create): 32-bit index arithmetic
+    int slots;
+    bool plain;
+};
+GCB_HD SlotRef resident_slots(const EnvView& v, int e) {
+    SlotRef r = {v.tgt + e, (unsigned)v.N, v.slots, false};
+    return r;
+}
 struct TgtSink {
     u64* base;
-    unsigned N;  // slot r of this env at base[r * N]; slots * N < 2^31 (checked at create), 32-bit index arithmetic
+    unsigned N;
     int slots, dropped, extra;  // extra = targets of pieces beyond the 16 counted slots
+    bool plain;
     uint8_t* cb;
-    GCB_HD TgtSink(u64* tgt, int n, int e, int s, CountBytes* scratch)
-        : base(tgt + e), N((unsigned)n), slots(s), dropped(0), extra(0), cb(scratch ? scratch->c : nullptr) {
+    GCB_HD TgtSink(const SlotRef& sr, CountBytes* scratch)
+        : base(sr.base), N(sr.stride), slots(sr.slots), dropped(0), extra(0), plain(sr.plain), cb(scratch ? scratch->c : nullptr) {
         if (scratch) {
             u64* z = reinterpret_cast<u64*>(scratch);
             z[0] = 0, z[1] = 0;
         }
     }
     GCB_HD void put(int r, u64 t) {
-        if (r < slots) GCB_STS(&base[(unsigned)r * N], t);
+        if (r < slots) st(r, t);
         else dropped++;
         const int c = gcb_popc(t);
         if (r < 16) cb[r] = (uint8_t)c;
         else extra += c;
     }
-    GCB_HD u64 get(int r) const { return r < slots ? GCB_LDS(&base[(unsigned)r * N]) : 0ULL; }
+    GCB_HD void st(int r, u64 t) {
+        if (plain) base[(unsigned)r * N] = t;
+        else GCB_STS(&base[(unsigned)r * N], t);
+    }
+    GCB_HD u64 get(int r) const {
+        if (r >= slots) return 0ULL;
+        return plain ? base[(unsigned)r * N] : GCB_LDS(&base[(unsigned)r * N]);
+    }
     GCB_HD void replace(int r, u64 told, u64 tnew) {  // tnew is a subset of told
-        if (r < slots) GCB_STS(&base[(unsigned)r * N], tnew);
+        if (r < slots) st(r, tnew);
         const int c = gcb_popc(tnew);
         if (r < 16) cb[r] = (uint8_t)c;
         else extra -= gcb_popc(told) - c;
@@ -238,7 +258,7 @@ GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, in
 
 // The action `possible_moves[idx]` of the reference-ordered list, decoded from the slots (chess_v2.py:116-127:
 // the uniform draw indexes the ORDERED list).  idx < n_legal.
-GCB_HD int action_at(const EnvView& v, int e, const EnvRegs& s, int idx) {
+GCB_HD int action_at(const SlotRef& sr, const EnvRegs& s, int idx) {
     // which piece: prefix scan over the 16 count bytes (registers only); pieces beyond 16 (only on crafted initial
     // boards) by reading their slots
     int acc = 0, hit_r = -1, hit_idx = 0;
@@ -250,9 +270,9 @@ GCB_HD int action_at(const EnvView& v, int e, const EnvRegs& s, int idx) {
         if (hit_r < 0 && idx - acc < c) hit_r = r, hit_idx = idx - acc;
         acc += c;
     }
-    TgtSink slots(v.tgt, v.N, e, v.slots, nullptr);
+    TgtSink slots(sr, nullptr);
     u64 own = stm_pieces(s);
-    if (v.slots > 16 && hit_r < 0) {
+    if (sr.slots > 16 && hit_r < 0) {
         const int np = gcb_popc(own);
         for (int r = 16; r < np && hit_r < 0; r++) {
             const int c = gcb_popc(slots.get(r));
@@ -275,13 +295,13 @@ GCB_HD int action_at(const EnvView& v, int e, const EnvRegs& s, int idx) {
 }
 
 // action in possible_actions ? (chess_v2.py:240)
-GCB_HD bool action_is_legal(const EnvView& v, int e, const EnvRegs& s, int action) {
+GCB_HD bool action_is_legal(const SlotRef& sr, const EnvRegs& s, int action) {
     if (action < 0) return false;
     if (action < 4096) {
         const int from = action >> 6, to = action & 63;
         const u64 own = stm_pieces(s), fbit = 1ULL << from;
         if (!(own & fbit)) return false;
-        TgtSink slots(v.tgt, v.N, e, v.slots, nullptr);
+        TgtSink slots(sr, nullptr);
         return (slots.get(gcb_popc(own & (fbit - 1))) >> to) & 1ULL;
     }
     if (action == castle_action(!s.stm_black, 0)) return s.castle & 1u;
@@ -296,7 +316,7 @@ GCB_HD bool action_is_legal(const EnvView& v, int e, const EnvRegs& s, int actio
 // side to move (573-582).  apply=false only switches the side and regenerates (BLACK-agent reset
 // when White has no move).  Returns the ply reward.
 GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int slot, int action, bool apply, bool* rep,
-                           StepStats& st, CountBytes* scratch) {
+                           StepStats& st, CountBytes* scratch, const SlotRef& sr) {
     int r = 0;
     *rep = false;
     if (apply) {
@@ -344,7 +364,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
     s.stm_black ^= 1;
     GenCtx g;
     gen_prepare(s.b, !s.stm_black, g);
-    TgtSink sink(v.tgt, v.N, e, v.slots, scratch);
+    TgtSink sink(sr, scratch);
     gen_targets(s.b, g, g.own, sink);
     const int n = sink.total();
     if (sink.dropped) st.f += SF_SLOTOVF;
@@ -398,7 +418,8 @@ GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
 
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step), state in registers
 template <int MODE>
-GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch) {
+GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch,
+                          const SlotRef& sr) {
     const u32 genv = v.env_offset + (u32)e;
     HistCursor hc;
     hc.base = io.tick * (u64)v.pps, hc.cursor = 0;
@@ -416,11 +437,11 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
         bool valid = false;
         if (MODE == MODE_ACTION) {
             action = reinterpret_cast<const int32_t*>(io.in)[e];
-            valid = action_is_legal(v, e, s, action);  // action in possible_actions
+            valid = action_is_legal(sr, s, action);  // action in possible_actions
         } else {
             u32 u = (MODE == MODE_INDEX) ? reinterpret_cast<const u32*>(io.in)[e] : philox_draw(v.seed, genv, ep, step_idx, 0u);
             if (n0 > 0) {
-                action = action_at(v, e, s, (int)gcb_umulhi(u, (u32)n0));
+                action = action_at(sr, s, (int)gcb_umulhi(u, (u32)n0));
                 valid = true;
             }
         }
@@ -483,13 +504,16 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 }
                 const int np = gcb_popc(s.b.w);  // White is to move in every initial state
                 const u64* ts = v.t_tgt + (size_t)t * v.slots;
-                for (int r = 0; r < np && r < v.slots; r++) v.tgt[(size_t)r * v.N + e] = ts[r];
+                {
+                    TgtSink dst(sr, nullptr);
+                    for (int r = 0; r < np && r < sr.slots; r++) dst.st(r, ts[r]);
+                }
                 ep += (u32)io.ep_inc;
                 if (v.agent_black) {
                     // the bot opens for White (chess_v2.py:208-216)
                     if (s.n_legal > 0) {
                         u32 u = philox_draw(v.seed, genv, ep, 0u, 2u);
-                        cur = action_at(v, e, s, (int)gcb_umulhi(u, (u32)s.n_legal));
+                        cur = action_at(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
                         do_apply = true;
                     } else {
                         do_apply = false;
@@ -503,7 +527,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             continue;
         }
         bool rep;
-        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st, scratch);
+        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st, scratch, sr);
         if (do_apply) st.f += SF_PLIES;
         const bool mate = s.n_legal == 0 && stm_checked(s);
         if (phase == PH_AGENT) {
@@ -515,7 +539,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             if (!s.done && v.opponent == 1) {
                 if (s.n_legal > 0) {  // chess_v2.py:277-288
                     u32 u = philox_draw(v.seed, genv, ep, step_idx, 1u);
-                    bot_action = action_at(v, e, s, (int)gcb_umulhi(u, (u32)s.n_legal));
+                    bot_action = action_at(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
                     cur = bot_action, slot = 1, phase = PH_BOT;
                     continue;
                 }
@@ -546,7 +570,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     EnvRegs s;
     u32 ep;
     env_load(v, e, s, ep);
-    env_step_regs<MODE>(v, io, e, s, ep, st, scratch);
+    env_step_regs<MODE>(v, io, e, s, ep, st, scratch, resident_slots(v, e));
     env_store(v, e, s, ep);
 }
 
@@ -564,7 +588,8 @@ GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulo
     GenCtx g;
     gen_prepare(b, 1, g);
     CountBytes scratch;
-    TgtSink sink(tgt + (size_t)i * slots, 1, 0, slots, &scratch);
+    SlotRef tsr = {tgt + (size_t)i * slots, 1u, slots, true};
+    TgtSink sink(tsr, &scratch);
     gen_targets(b, g, g.own, sink);
     const int n = sink.total();
     s.castle = gen_castles(b, g, s.rights);
@@ -603,7 +628,8 @@ GCB_HD int env_legal_list_one(const EnvView& v, int e, Offs& offs, Out& out) {
             chunk = rem ^ t;
         }
         rem ^= chunk;
-        TgtSink slots(v.tgt + (size_t)r0 * v.N, v.N, e, v.slots - r0, nullptr);
+        SlotRef csr = {v.tgt + (size_t)r0 * v.N + e, (unsigned)v.N, v.slots - r0, false};
+        TgtSink slots(csr, nullptr);
         n = emit_chunk_typemajor(s.b, !s.stm_black, chunk, slots, offs, out, n);
         r0 += GCB_SLOTS;
     }

