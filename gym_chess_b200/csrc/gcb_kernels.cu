@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(GCB_BLOCK, GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
+// measured on B200: the multi-step sampled kernel is fastest with 4 resident blocks per SM (128 registers; more warps
+// thrash the instruction cache), the single-step kernels with 5 (96 registers)
+__global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_STEP_MIN_BLOCKS - 1 : GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
     __shared__ CountBytes s_counts[GCB_BLOCK];
     const int e = io.e_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
