@@ -231,25 +231,15 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_STEP_MIN
             const u32 r2 = __reduce_add_sync(0xffffffffu, (f >> 10) & 7u);
             const int t_reward = __reduce_add_sync(0xffffffffu, st.reward), t_legal = __reduce_add_sync(0xffffffffu, st.legal);
             const int t_scan = __reduce_add_sync(0xffffffffu, st.scan), t_window = __reduce_add_sync(0xffffffffu, st.window);
+            // lane k picks counter k: a chain of selects (a switch on the lane id would run its 15 cases one by one)
             long long mine = 0;
-            switch (lane) {
-            case ST_STEPS: mine = r0 & 63u; break;
-            case ST_PLIES: mine = (r0 >> 6) & 127u; break;
-            case ST_EPISODES: mine = (r0 >> 13) & 63u; break;
-            case ST_MATES: mine = (r0 >> 19) & 63u; break;
-            case ST_REPS: mine = (r0 >> 25) & 63u; break;
-            case ST_CAPS: mine = r1 & 63u; break;
-            case ST_WEDGED: mine = (r1 >> 6) & 63u; break;
-            case ST_INVALID: mine = (r1 >> 12) & 63u; break;
-            case ST_REWARD: mine = t_reward; break;
-            case ST_LEGAL: mine = t_legal; break;
-            case ST_INCHECK: mine = (r1 >> 18) & 63u; break;
-            case ST_HISTOVF: mine = r2; break;
-            case ST_SLOTOVF: mine = (r1 >> 24) & 127u; break;
-            case ST_HISTSCAN: mine = t_scan; break;
-            case ST_WINDOW: mine = t_window; break;
-            default: break;
-            }
+#define GCB_PICK(k_, v_) mine = lane == (k_) ? (long long)(v_) : mine
+            GCB_PICK(ST_STEPS, r0 & 63u), GCB_PICK(ST_PLIES, (r0 >> 6) & 127u), GCB_PICK(ST_EPISODES, (r0 >> 13) & 63u);
+            GCB_PICK(ST_MATES, (r0 >> 19) & 63u), GCB_PICK(ST_REPS, (r0 >> 25) & 63u), GCB_PICK(ST_CAPS, r1 & 63u);
+            GCB_PICK(ST_WEDGED, (r1 >> 6) & 63u), GCB_PICK(ST_INVALID, (r1 >> 12) & 63u), GCB_PICK(ST_REWARD, t_reward);
+            GCB_PICK(ST_LEGAL, t_legal), GCB_PICK(ST_INCHECK, (r1 >> 18) & 63u), GCB_PICK(ST_HISTOVF, r2);
+            GCB_PICK(ST_SLOTOVF, (r1 >> 24) & 127u), GCB_PICK(ST_HISTSCAN, t_scan), GCB_PICK(ST_WINDOW, t_window);
+#undef GCB_PICK
             acc += mine;
         }
         io.tick++;
