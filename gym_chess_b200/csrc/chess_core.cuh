@@ -63,6 +63,22 @@ GCB_HD int gcb_popc(u64 x) {
     return __builtin_popcountll(x);
 #endif
 }
+// index of the r-th (0-based) set bit of x, r < popc(x): a 6-step binary search on popcounts -- the same instructions in
+// every lane, where clearing r low bits one by one would run the warp for the largest r
+GCB_HD int gcb_select64(u64 x, int r) {
+    u32 w = (u32)x;
+    int base = 0, c = gcb_popc((u64)w);
+    if (r >= c) r -= c, w = (u32)(x >> 32), base = 32;
+    c = gcb_popc((u64)(w & 0xFFFFu));
+    if (r >= c) r -= c, w >>= 16, base += 16;
+    c = gcb_popc((u64)(w & 0xFFu));
+    if (r >= c) r -= c, w >>= 8, base += 8;
+    c = gcb_popc((u64)(w & 0xFu));
+    if (r >= c) r -= c, w >>= 4, base += 4;
+    c = gcb_popc((u64)(w & 0x3u));
+    if (r >= c) r -= c, w >>= 2, base += 2;
+    return base + ((w & 1u) ? r : 1);
+}
 GCB_HD u64 gcb_rotl64(u64 x, int k) { return (x << (k & 63)) | (x >> ((64 - k) & 63)); }  // 0 < k < 64
 GCB_HD u32 gcb_umulhi(u32 a, u32 b) {
 #if defined(__CUDA_ARCH__)
@@ -561,11 +577,7 @@ GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
     }
     if (!mf) return sq;
     if (desc) mf = gcb_brev64(mf);  // nearest first = lowest bit first in both cases
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int j = 0; j < idx; j++) mf &= mf - 1;
-    const int t = gcb_lsb(mf);
+    const int t = gcb_select64(mf, idx);
     return desc ? 63 - t : t;
 }
 

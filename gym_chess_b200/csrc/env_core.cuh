@@ -282,11 +282,7 @@ GCB_HD int action_at(const SlotRef& sr, const EnvRegs& s, int idx) {
     }
     if (hit_r >= 0) {
         const u64 T = slots.get(hit_r);  // the one slot this draw needs
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int i = 0; i < hit_r; i++) own &= own - 1;
-        const int sq = gcb_lsb(own);
+        const int sq = gcb_select64(own, hit_r);
         return sq * 64 + nth_target(piece_code(s.b, sq), !s.stm_black, sq, T, hit_idx);
     }
     // castles come last, queen side first (lib.rs:1473-1479, 992, 1011)
