@@ -7,10 +7,11 @@
 
 Workload (BASELINE.json configs[3] "4M envs sharded across 8xB200", per-GPU shard): 524,288 envs per GPU, random
 self-play (opponent "none"), uniformly random legal action per ply drawn on the device (Philox4x32-10), auto-reset.
-A "step" is one ChessEnvV2.step() of every env of the rank = one launch of the fused step kernel.  `value` = env
+A "step" is one ChessEnvV2.step() of every env of the rank; the fused step kernel runs up to 64 consecutive steps per launch.  `value` = env
 steps of all ranks / max-over-ranks device time, state resident in HBM.  `e2e` = the same metric through the
 host-buffer C ABI call gcb_env_step_index_host (what a binding of the reference env would call): per step the
-caller's random words are copied H2D from pinned memory and reward/done/flags D2H, inside the timed region.
+caller's random words cross PCIe host->device from pinned memory and reward/done/flags device->host, inside the timed
+region (the kernel reads / writes the page-locked buffers in place; pageable buffers would be staged in chunks).
 """
 import argparse
 import json
@@ -213,7 +214,11 @@ def main():
     # reads far fewer ring entries (Bloom pre-filter, "hist_scanned") -- the algorithmic figure stays the survey's.
     W = st["hist_window"] / max(1, st["plies"])
     bytes_per_step = 97.0 + 8.0 * W
-    kernel_ms = ms / args.steps  # one launch per step, nothing else in the timed region
+    # the step kernel is the only kernel in the timed region; one launch runs up to 64 consecutive steps
+    # (gcb_env_step_sampled), so bytes per launch = N * steps-per-launch * bytes_per_step and
+    # achieved = bytes per launch / average launch duration = N * bytes_per_step / (ms per step)
+    kernel_ms = ms / args.steps
+    steps_per_launch = args.steps / max(1, launches)
     achieved = bytes_per_step * N / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = peaks()
     traffic = None  # dram bytes per launch of the step kernel from the committed ncu --set full capture (same N)
@@ -221,8 +226,8 @@ def main():
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-        if tj.get("envs") == N:
-            traffic = tj["dram_bytes_per_launch"]
+        if tj.get("envs") == N:  # per launch like `achieved`: a launch of the sampled kernel runs up to 64 steps
+            traffic = tj["dram_bytes_per_step"] * args.steps / max(1, launches)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -236,7 +241,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "k_env_step<MODE_SAMPLED>", "bytes_per_unit": bytes_per_step,
                      "mean_hist_window": W, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": bytes_per_step * N,
+                     "algorithmic_bytes_per_launch": bytes_per_step * N * steps_per_launch, "steps_per_launch": steps_per_launch,
+                     "launch_ms": ms / max(1, launches),
                      "note": "integer-pipe (ALU) bound, not HBM bound: see DESIGN.md section 3 and profiles/"},
         "episode_stats_all_ranks": {k: int(tot[i]) for i, k in enumerate(
             ("steps", "plies", "episodes", "mates", "repetitions", "caps", "wedged", "invalid", "reward_sum", "legal_sum",
