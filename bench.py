@@ -182,7 +182,6 @@ def main():
     barrier()
     launches = L.gcb_launch_count() - launches0
     ms = max_over_ranks(ev0.elapsed_time(ev1))
-    clk = clocks.stop() if rank == 0 else None
     st = env.stats()
     value = world * N * args.steps / (ms * 1e-3)
 
@@ -206,6 +205,7 @@ def main():
     ev1.record()
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clk = clocks.stop() if rank == 0 else None  # sampled over both timed regions (kernel-only and end-to-end)
     e2e_value = world * N * e2e_steps / (e2e_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (k_env_step<sampled>): algorithmic bytes per env step, SURVEY.md 8(d):
