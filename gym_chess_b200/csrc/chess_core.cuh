@@ -79,7 +79,6 @@ GCB_HD int gcb_select64(u64 x, int r) {
     if (r >= c) r -= c, w >>= 2, base += 2;
     return base + ((w & 1u) ? r : 1);
 }
-GCB_HD u64 gcb_rotl64(u64 x, int k) { return (x << (k & 63)) | (x >> ((64 - k) & 63)); }  // 0 < k < 64
 GCB_HD u32 gcb_umulhi(u32 a, u32 b) {
 #if defined(__CUDA_ARCH__)
     return __umulhi(a, b);
@@ -278,32 +277,7 @@ GCB_HD int ref_king_square(u64 kings) {
     return gcb_lsb(rowbits);
 }
 
-// Attack/defence map of one side (lib.rs:669-677 with the attack-mode branches of the piece
-// generators): sliders/knights: every on-board target up to the first piece inclusive; pawns:
-// both forward diagonals unless the square holds that side's OWN king (lib.rs:928-933, Q14);
-// king: all 8 neighbours (the map passed down is empty, lib.rs:670-671).
-GCB_HD u64 side_attack_map(const Board& b, u64 side, int side_is_white) {
-    u64 occ = bb_occ(b);
-    u64 kings = bb_kings(b) & side;
-    u64 att = pawn_set_att(bb_pawns(b) & side, side_is_white) & ~kings;
-    att |= knight_set_att(bb_knights(b) & side);
-    att |= king_set_att(kings);
-    u64 rq = (bb_rooks(b) | bb_queens(b)) & side;
-    while (rq) {
-        int sq = gcb_lsb(rq);
-        rq &= rq - 1;
-        att |= rook_att(sq, occ);
-    }
-    u64 bq = (bb_bishops(b) | bb_queens(b)) & side;
-    while (bq) {
-        int sq = gcb_lsb(bq);
-        bq &= bq - 1;
-        att |= bishop_att(sq, occ);
-    }
-    return att;
-}
-
-// Is `sq` in the attack map of `side`?  Symmetric form of side_attack_map(): a slider attacks sq
+// Is `sq` in the attack/defence map of `side` (lib.rs:669-677)?  Symmetric form: a slider attacks sq
 // iff sq's own ray reaches it, leapers likewise; used where only one square matters.  (The Q14
 // pawn exclusion cannot apply: callers pass the square of a king of the OTHER colour.)
 GCB_HD bool square_attacked_by(const Board& b, int sq, u64 side, int side_is_white) {
@@ -368,12 +342,6 @@ GCB_HD u64 line_through(int a, int b) {
     else if (ra - ca == rb - cb) m = mask_diag(a);
     else if (ra + ca == rb + cb) m = mask_anti(a);
     return m;
-}
-// squares strictly between two aligned squares (0 when not aligned or adjacent)
-GCB_HD u64 between_excl(int a, int b) {
-    const int lo = a < b ? a : b, hi = a < b ? b : a;
-    const u64 span = (1ULL << hi) - (2ULL << lo);  // bits lo+1 .. hi-1
-    return span & line_through(a, b);
 }
 
 struct GenCtx {
