@@ -24,7 +24,8 @@ def load_golden():
 
     with open(os.path.join(GOLD, "reference_v2_tests.json")) as f:
         ref = json.load(f)
-    return dict(reference_tests=ref, trajectories=gz("trajectories.json.gz"), positions=gz("positions.json.gz"))
+    return dict(reference_tests=ref, trajectories=gz("trajectories.json.gz"), positions=gz("positions.json.gz"),
+                v1_move_sets=gz("v1_move_sets.json.gz"))
 
 
 # ------------------------------------------------------------------ engine level
@@ -237,3 +238,22 @@ def endgame_boards():
         board(s60=K, s52=P, s4=-K, s12=-P),         # KP v KP (pawns stall on the last rank: no promotion, Q1)
         board(s60=K, s61=B, s4=-K, s2=-B),          # KB v KB
     ], np.int8)
+
+
+def check_v1_move_sets(movegen_fn, records):
+    """Move SETS of the reference's own pure-Python env (chess_v1.py, unmodified; tests/golden/make_golden_v1.py): an
+    implementation that shares no code with lib.rs or with the oracle.  v1 never captures a king with a non-pawn piece
+    and castles under other conditions: castles and moves onto the enemy king square are dropped from
+    both sides, everything else must agree exactly."""
+    boards = np.array([r["board"] for r in records], np.int8)
+    players = np.array([r["player"] for r in records], np.int8)
+    res = movegen_fn(boards, players, np.zeros((len(records), 4), np.uint8), False)
+    out, cnt = res[0], res[1]
+    n = 0
+    for i, r in enumerate(records):
+        eking = int(np.nonzero(boards[i] == -r["player"])[0][0])
+        mine = {(int(a) >> 6, int(a) & 63) for a in out[i, : cnt[i]] if a < 4096 and (int(a) & 63) != eking}
+        theirs = {tuple(m) for m in r["moves"] if not isinstance(m, str) and m[1] != eking}
+        assert mine == theirs, (i, np.array(r["board"]).reshape(8, 8), r["player"], sorted(mine ^ theirs))
+        n += len(theirs)
+    return n

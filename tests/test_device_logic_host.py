@@ -151,3 +151,7 @@ def test_endgames_with_long_repetition_windows():
     assert st[14] / st[1] > 20         # mean window far above random play's ~6
     env = EmulAdapter(14, opponent="random", player_color="BLACK", seed=18, auto_reset=True, initial_boards=boards, history_cap=512)
     ph.check_sampled_vs_oracle(env, "random", "BLACK", 18, 500, boards=boards, compare_every=50)  # BLACK agent: no cap (Q12)
+
+
+def test_move_sets_of_the_reference_pure_python_env(golden):
+    assert ph.check_v1_move_sets(_mg, golden["v1_move_sets"]) > 15000

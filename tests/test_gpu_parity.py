@@ -359,3 +359,7 @@ def test_multi_step_launch_equals_single_steps(opponent, color):
     assert (ba == bb).all() and (ia == ib).all() and (la == lb).all()
     assert a.stats() == b.stats() and a.stats()["episodes"] > 0
     assert torch.equal(a.piece_slots()[:, :8], b.piece_slots()[:, :8]) or True  # slots beyond the live pieces are unspecified
+
+
+def test_move_sets_of_the_reference_pure_python_env(eng, golden):
+    assert ph.check_v1_move_sets(_mg(eng), golden["v1_move_sets"]) > 15000

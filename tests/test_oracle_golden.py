@@ -136,3 +136,13 @@ def test_selfplay_statistics_shape():
     assert st["steps"] == 32 * 3000
     assert 20 < st["legal_sum"] / st["steps"] < 27
     assert st["caps"] > st["mates"] > 0 and st["episodes"] == st["mates"] + st["repetitions"] + st["caps"] + st["wedged"]
+
+
+def test_oracle_matches_move_sets_of_the_reference_pure_python_env(golden):
+    """second, independent pin: the reference's own chess_v1.py (pure Python, shares no code with lib.rs or the oracle)
+    produced these move sets in the build container (tests/golden/make_golden_v1.py)"""
+    def mg(boards, players, rights, attack):
+        return orc.movegen_batch(boards, players, rights, attack, stride=256)
+
+    assert len(golden["v1_move_sets"]) > 800
+    assert ph.check_v1_move_sets(mg, golden["v1_move_sets"]) > 15000
