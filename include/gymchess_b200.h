@@ -146,12 +146,17 @@ int gcb_env_step(gcb_env *env, const int32_t *d_actions, int32_t *d_reward, uint
 int gcb_env_step_index(gcb_env *env, const uint32_t *d_u32, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
                        void *stream);
 /* same, the word is drawn on the device: Philox4x32-10, counter (global env id, episode, step in episode, 0),
- * key = seed.  Runs `nsteps` consecutive steps; outputs are those of the LAST step.  d_actions_out int32[nsteps][N]
- * (may be NULL) records the action each env played, d_bot_out likewise the bot's reply (-1 = none). */
+ * key = seed.  Runs `nsteps` consecutive steps -- up to 64 of them per kernel launch: envs are independent, so a thread
+ * keeps stepping its env with the state in registers (no launch gap, no grid-wide sync); outputs are those of the LAST
+ * step.  d_actions_out int32[nsteps][N] (may be NULL) records the action each env played, d_bot_out likewise the bot's
+ * reply (-1 = none). */
 int gcb_env_step_sampled(gcb_env *env, int nsteps, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
                          int32_t *d_actions_out, int32_t *d_bot_out, void *stream);
 
-/* HOST-buffer forms (pinned staging + copies inside the call; synchronous) */
+/* HOST-buffer forms (synchronous; what a binding of the reference env calls).  Page-locked buffers (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory) are read and written IN PLACE by the step kernel through their device aliases --
+ * one launch, no staging copy; pageable buffers are staged in up to 4 pipelined chunks.  Both order themselves after
+ * earlier work on the default stream only. */
 int gcb_env_step_host(gcb_env *env, const int32_t *actions, int32_t *reward, uint8_t *done, uint8_t *flags);
 int gcb_env_step_index_host(gcb_env *env, const uint32_t *u32, int32_t *reward, uint8_t *done, uint8_t *flags);
 
