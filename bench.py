@@ -133,7 +133,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    assert args.warmup >= 3, "W >= 3 warm-up steps"
+    args.warmup = max(3, args.warmup)  # timing rule: at least 3 warm-up steps (the JSON reports the value used)
+    args.steps = max(1, args.steps)
     # stdout carries exactly ONE JSON line: anything a library prints meanwhile (e.g. NCCL's version banner) goes to stderr
     sys.stdout.flush()
     saved_stdout = os.dup(1)
