@@ -80,6 +80,7 @@ SIGNATURES = {
     "gcb_env_create": (i32, [C.POINTER(EnvConfig), C.POINTER(vp)]),
     "gcb_env_destroy": (i32, [vp]),
     "gcb_env_reset": (i32, [vp, vp, vp]),
+    "gcb_env_import": (i32, [vp, vp, vp, vp, vp, vp, vp]),
     "gcb_env_step": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_step_index": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_step_sampled": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),

@@ -89,6 +89,21 @@ class BatchedChessEnv:
             check(_lib.lib().gcb_env_reset(self._h, C.c_void_p(m.data_ptr()) if m is not None else None, _stream_ptr()))
         return self.observe()
 
+    def set_state(self, boards, players, rights, move_count=None, mask=None):
+        """State import (the reference's `state` setter, chess_v2.py:315-323, for many envs): a new episode of the selected
+        envs from arbitrary positions.  boards int8 [N,8,8] or [N,64]; players int8 [N] (+1 WHITE / -1 BLACK); rights
+        uint8 [N,4] (wk, wq, bk, bq); move_count int32 [N] or None; mask [N] or None (all)."""
+        dev = self.device
+        b = torch.as_tensor(boards, device=dev).to(torch.int8).reshape(self.num_envs, 64).contiguous()
+        p = torch.as_tensor(players, device=dev).to(torch.int8).reshape(self.num_envs).contiguous()
+        r = torch.as_tensor(rights, device=dev).to(torch.uint8).reshape(self.num_envs, 4).contiguous()
+        mc = None if move_count is None else torch.as_tensor(move_count, device=dev).to(torch.int32).contiguous()
+        m = None if mask is None else torch.as_tensor(mask, device=dev).to(torch.uint8).contiguous()
+        with torch.cuda.device(dev):
+            check(_lib.lib().gcb_env_import(self._h, C.c_void_p(b.data_ptr()), C.c_void_p(p.data_ptr()), C.c_void_p(r.data_ptr()),
+                                            C.c_void_p(mc.data_ptr()) if mc is not None else None,
+                                            C.c_void_p(m.data_ptr()) if m is not None else None, _stream_ptr()))
+
     def _outs(self):
         return C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()), C.c_void_p(self.flags.data_ptr())
 

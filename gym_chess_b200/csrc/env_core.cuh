@@ -570,6 +570,42 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     env_store(v, e, s, ep);
 }
 
+// A new episode of env e from an arbitrary position in the reference's wire format (the `state` setter of
+// chess_v2.py:315-323 + engine.update_state + get_possible_moves for the side to move): rights masked by king presence,
+// both check flags, legal set, empty repetition window, episode counter + 1.
+GCB_HD void env_import_one(const EnvView& v, int e, const int8_t* board, int player, u32 rights, int move_count, u64 tick,
+                           StepStats& st, CountBytes* scratch) {
+    EnvRegs s;
+    u32 ep;
+    env_load(v, e, s, ep);
+    s.b = board_from_mailbox(board);
+    s.zk = zobrist_full(s.b);
+    s.seen1 = s.seen2 = 0;
+    s.rights = mask_rights(s.b, rights);
+    s.done = 0, s.move_count = move_count, s.step = 0, s.hist_len = 0;
+    s.stm_black = player < 0 ? 0 : 1;  // ply_and_movegen(apply = false) flips the side, then generates for it
+    HistCursor hc;
+    hc.base = tick * (u64)v.pps, hc.cursor = 0;
+    bool rep;
+    ply_and_movegen(v, e, s, hc, 0, 0, false, &rep, st, scratch, resident_slots(v, e));
+    env_store(v, e, s, ep + 1u);
+}
+
+// Launches that do not step every env (masked reset / import) still consume a ring tick: the envs they leave alone
+// mark the tick's slots "no ply" so that their repetition window stays contiguous in the ring.
+GCB_HD void env_idle_tick(const EnvView& v, int e, u64 tick) {
+    EnvRegs s;
+    unpack_meta(v.meta[e], s);
+    s.seen1 = s.seen2 = 0, s.zk = 0, s.cnt_lo = s.cnt_hi = 0;  // (not touched: only meta is rewritten)
+    if (s.hist_len == 0) return;
+    HistCursor hc;
+    hc.base = tick * (u64)v.pps, hc.cursor = 0;
+    StepStats st;
+    st.clear();
+    hist_skip_to(v, e, s, hc, v.pps, st);
+    v.meta[e] = pack_meta(s);
+}
+
 // initial state of one template board (ChessEnvV2.reset up to the first movegen, chess_v2.py:188-206)
 GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulonglong2* bb23, u64* meta, u64* zkey,
                               u64* tgt, ulonglong2* cnt, int slots) {

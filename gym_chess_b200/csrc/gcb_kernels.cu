@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_STEP_MIN
     const int e = io.e_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool active = e < io.e_end;
-    if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;
+    if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) {
+        env_idle_tick(v, e, io.tick);  // a masked reset leaves this env alone, but the launch consumes a ring tick
+        active = false;
+    }
     // Sampled self-play runs `nsteps` consecutive steps in one launch: every env only depends on its own previous step,
     // so a block simply keeps stepping its envs -- no launch gap, no wave tail between steps.
     const int nsteps = MODE == MODE_SAMPLED ? io.nsteps : 1;
@@ -277,6 +280,28 @@ __global__ void k_make_templates(int n, const int8_t* __restrict__ boards, ulong
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     make_template_one(i, boards, bb01, bb23, meta, zkey, tgt, cnt, slots);
+}
+
+__global__ void __launch_bounds__(GCB_BLOCK) k_env_import(EnvView v, const int8_t* __restrict__ boards,
+                                                          const int8_t* __restrict__ players, const uint8_t* __restrict__ rights4,
+                                                          const int32_t* __restrict__ move_count, const uint8_t* __restrict__ mask,
+                                                          u64 tick) {
+    __shared__ CountBytes s_counts[GCB_BLOCK];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.N) return;
+    if (mask && !mask[e]) {
+        env_idle_tick(v, e, tick);
+        return;
+    }
+    alignas(16) int8_t m[64];
+    const int4* src = reinterpret_cast<const int4*>(boards + (size_t)e * 64);
+#pragma unroll
+    for (int k = 0; k < 4; k++) *reinterpret_cast<int4*>(m + 16 * k) = __ldg(src + k);
+    const uchar4 q = reinterpret_cast<const uchar4*>(rights4)[e];
+    const u32 rights = (q.x ? RT_WK : 0) | (q.y ? RT_WQ : 0) | (q.z ? RT_BK : 0) | (q.w ? RT_BQ : 0);
+    StepStats st;
+    st.clear();
+    env_import_one(v, e, m, players[e], rights, move_count ? move_count[e] : 0, tick, st, &s_counts[threadIdx.x]);
 }
 
 __global__ void k_init_zobrist(u64* tab) {
@@ -806,6 +831,17 @@ extern "C" int gcb_env_step_index_host(gcb_env* env, const uint32_t* u32, int32_
     ENV_CHECK(env);
     if (!u32) return fail(GCB_E_ARG, "gcb_env_step_index_host", "null random words");
     return step_host_common(env, MODE_INDEX, u32, reward, done, flags);
+}
+
+extern "C" int gcb_env_import(gcb_env* env, const int8_t* d_boards, const int8_t* d_players, const uint8_t* d_rights4,
+                              const int32_t* d_move_count, const uint8_t* d_mask, void* stream) {
+    ENV_CHECK(env);
+    if (!d_boards || !d_players || !d_rights4) return fail(GCB_E_ARG, "gcb_env_import", "null pointer");
+    k_env_import<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, d_boards, d_players, d_rights4, d_move_count,
+                                                                               d_mask, env->tick);
+    env->tick++;
+    LAUNCHED();
+    return GCB_OK;
 }
 
 extern "C" int gcb_env_export(gcb_env* env, int8_t* d_boards, int32_t* d_info, void* stream) {

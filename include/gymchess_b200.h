@@ -137,6 +137,15 @@ int gcb_env_destroy(gcb_env *env);
  * episode (episode counter + 1, enters the Philox counter). */
 int gcb_env_reset(gcb_env *env, const uint8_t *d_mask, void *stream);
 
+/* State import: a new episode of the selected envs (d_mask uint8[N], NULL = all) from arbitrary positions in the
+ * reference's wire format -- what assigning `env.state = s` (the setter of chess_v2.py:315-323) and the bookkeeping of
+ * reset() amount to: rights masked by king presence and both check flags (engine.update_state), the legal set of the side
+ * to move, empty repetition window, done = False, step_in_episode = 0, episode counter + 1.  d_boards int8[N][64],
+ * d_players int8[N] (+1/-1), d_rights4 uint8[N][4], d_move_count int32[N] (NULL = 0).  More own pieces than the env has
+ * piece slots (gcb_env_config.piece_slots) are reported through the slot_overflow statistic of later steps. */
+int gcb_env_import(gcb_env *env, const int8_t *d_boards, const int8_t *d_players, const uint8_t *d_rights4,
+                   const int32_t *d_move_count, const uint8_t *d_mask, void *stream);
+
 /* ChessEnvV2.step(action), chess_v2.py:219-294, for all N envs.  Outputs (device, any may be NULL):
  * d_reward int32[N] (the two float 0.0 literals are 0), d_done uint8[N], d_flags uint8[N] (GCB_F_*). */
 int gcb_env_step(gcb_env *env, const int32_t *d_actions, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,

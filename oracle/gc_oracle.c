@@ -739,3 +739,17 @@ void gco_env_set_episode(gco_env *e, uint32_t episode) { e->episode = episode; }
 /* ChessEnvV2.moves_max (chess_v2.py:141) is a plain attribute: 149 unless the user changes it */
 void gco_env_set_moves_max(gco_env *e, int moves_max) { e->moves_max = moves_max; }
 void gco_env_force_bot(gco_env *e, int action) { e->forced_bot_action = action; }
+/* A new episode from an arbitrary state (what assigning `env.state = s` -- the setter of chess_v2.py:315-323 -- plus the
+ * bookkeeping of reset() amounts to): engine.update_state masks the flags and computes the check flags, then
+ * get_possible_moves for the side to move.  The episode counter is set by the caller (gco_env_set_episode). */
+void gco_env_import(gco_env *e, const int8_t *board, int player, int wk, int wq, int bk, int bq, int move_count) {
+    e->done = 0;
+    e->hist_n = 0;
+    e->move_count = move_count;
+    e->wedged_bot = 0;
+    e->step_in_episode = 0;
+    e->last_bot_action = -1;
+    gco_state_new(&e->st, board, player, wk, wq, bk, bq);
+    gco_update_state(&e->st);
+    env_movegen(e, player);
+}

@@ -90,6 +90,7 @@ def lib():
         L.gco_env_view.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gco_env_set_episode.argtypes = [C.c_void_p, C.c_uint32]
         L.gco_env_set_moves_max.argtypes = [C.c_void_p, C.c_int]
+        L.gco_env_import.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6
         L.gco_env_force_bot.argtypes = [C.c_void_p, C.c_int]
         L.gco_selfplay.argtypes = [C.c_void_p, C.c_uint64, P(Stats)]
         L.gco_selfplay_mt.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, P(Stats)]
@@ -218,6 +219,13 @@ class OracleEnv:
         if episode is not None:
             lib().gco_env_set_episode(self._h, episode)
         lib().gco_env_reset(self._h)
+
+    def import_state(self, board, player, rights, move_count=0, episode=None):
+        """new episode from an arbitrary position (board int8[64], player +1/-1, rights (wk, wq, bk, bq))"""
+        if episode is not None:
+            lib().gco_env_set_episode(self._h, episode)
+        b = np.ascontiguousarray(np.asarray(board, np.int8).reshape(64))
+        lib().gco_env_import(self._h, b.ctypes.data, int(player), *[int(x) for x in rights], int(move_count))
 
     def step(self, action, bot_action=-1):
         """-> (reward, done, raised).  bot_action >= 0 forces the bot's reply (replay of a recorded game)."""

@@ -38,6 +38,7 @@ def lib():
         L.emul_env_destroy.argtypes = [vp]
         L.emul_env_step.argtypes = [vp, C.c_int] + [vp] * 6
         L.emul_env_export.argtypes = [vp, vp, vp, vp, C.c_int]
+        L.emul_env_import.argtypes = [vp] * 6
         L.emul_env_stats.argtypes = [vp, vp]
         _lib = L
     return _lib
@@ -122,6 +123,14 @@ class EmulEnv:
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(np.asarray(mask, np.uint8))
         lib().emul_env_step(self._h, 3, _p(m), None, None, None, None, None)
+
+    def set_state(self, boards, players, rights, move_count=None, mask=None):
+        b = np.ascontiguousarray(np.asarray(boards, np.int8).reshape(self.N, 64))
+        p = np.ascontiguousarray(np.asarray(players, np.int8).reshape(self.N))
+        r = np.ascontiguousarray(np.asarray(rights, np.uint8).reshape(self.N, 4))
+        mc = None if move_count is None else np.ascontiguousarray(np.asarray(move_count, np.int32))
+        m = None if mask is None else np.ascontiguousarray(np.asarray(mask, np.uint8))
+        lib().emul_env_import(self._h, _p(b), _p(p), _p(r), _p(mc), _p(m))
 
     def export(self):
         boards = np.zeros((self.N, 64), np.int8)

@@ -158,9 +158,27 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
         case 2: env_step_one<MODE_SAMPLED>(E->v, io, e, st, &scratch); break;
         default:
             if (!in || ((const uint8_t*)in)[e]) env_step_one<MODE_RESET>(E->v, io, e, st, &scratch);
+            else env_idle_tick(E->v, e, io.tick);
         }
         if (mode != 3)
             for (int k = 0; k < ST_USED; k++) E->v.stats[k] += (u64)(long long)st.get(k);
+    }
+}
+
+void emul_env_import(EmulEnv* E, const int8_t* boards, const int8_t* players, const uint8_t* rights4, const int32_t* move_count,
+                     const uint8_t* mask) {
+    StepStats st;
+    CountBytes scratch;
+    const u64 tick = E->tick++;
+    for (int e = 0; e < E->v.N; e++) {
+        if (mask && !mask[e]) {
+            env_idle_tick(E->v, e, tick);
+            continue;
+        }
+        const uint8_t* q = rights4 + (size_t)e * 4;
+        u32 rights = (q[0] ? RT_WK : 0) | (q[1] ? RT_WQ : 0) | (q[2] ? RT_BK : 0) | (q[3] ? RT_BQ : 0);
+        st.clear();
+        env_import_one(E->v, e, boards + (size_t)e * 64, players[e], rights, move_count ? move_count[e] : 0, tick, st, &scratch);
     }
 }
 

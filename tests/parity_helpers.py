@@ -158,17 +158,10 @@ def _cmp_export(env, oracles, tag):
         assert mine == ref, "%s env %d: %s" % (tag, i, {k: (mine[k], ref[k]) for k in mine if mine[k] != ref[k]})
 
 
-def check_sampled_vs_oracle(env, opponent, color, seed, steps, auto_reset=True, boards=None, env_id_offset=0,
-                            compare_every=25, mode="sampled", rng=None, moves_max=149):
-    """Run `steps` steps on the device env and replay the SAME draws through N oracle envs; compare every output of
-    every step, the full state every `compare_every` steps, and the statistics at the end."""
+def _run_sampled(env, O, seed, steps, tot, auto_reset=True, env_id_offset=0, compare_every=25, mode="sampled", rng=None, tag=""):
+    """`steps` steps on the device env and the SAME draws through the oracle envs O; compares every output of every
+    step and the full state every `compare_every` steps; accumulates steps / reward_sum / episodes in `tot`."""
     N = env.N
-    nt = 1 if boards is None else len(boards)
-    O = [orc.OracleEnv(None if boards is None else boards[(env_id_offset + i) % nt], color, opponent, seed, env_id_offset + i,
-                       moves_max=moves_max)
-         for i in range(N)]
-    _cmp_export(env, O, "reset")
-    tot = dict(steps=0, reward_sum=0, episodes=0)
     for t in range(steps):
         words = None
         if mode == "sampled":
@@ -182,22 +175,71 @@ def check_sampled_vs_oracle(env, opponent, color, seed, steps, auto_reset=True, 
             act = o.pick(u)
             rr, dd, raised = o.step(act)
             v2 = o.view()
-            assert (rr, dd) == (int(r[i]), bool(d[i])), "step %d env %d: oracle %s device %s flags %d" % (t, i, (rr, dd), (r[i], d[i]), f[i])
+            assert (rr, dd) == (int(r[i]), bool(d[i])), "%sstep %d env %d: oracle %s device %s flags %d" % (tag, t, i, (rr, dd), (r[i], d[i]), f[i])
             if a is not None:
-                assert act == int(a[i]) and v2["last_bot_action"] == int(bot[i]), (t, i, act, a[i], v2["last_bot_action"], bot[i])
+                assert act == int(a[i]) and v2["last_bot_action"] == int(bot[i]), (tag, t, i, act, a[i], v2["last_bot_action"], bot[i])
             terminal = dd or v2["n_legal"] == 0
-            assert bool(f[i] & 32) == (terminal and auto_reset), (t, i, int(f[i]), terminal)
-            assert bool(f[i] & 16) == ((not dd) and v2["n_legal"] == 0), (t, i, int(f[i]))
+            assert bool(f[i] & 32) == (terminal and auto_reset), (tag, t, i, int(f[i]), terminal)
+            assert bool(f[i] & 16) == ((not dd) and v2["n_legal"] == 0), (tag, t, i, int(f[i]))
             tot["steps"] += 1
             tot["reward_sum"] += rr
             tot["episodes"] += int(terminal)
             if terminal and auto_reset:
                 o.reset(v2["episode"] + 1)
         if t % compare_every == 0 or t == steps - 1:
-            _cmp_export(env, O, "step %d" % t)
+            _cmp_export(env, O, "%sstep %d" % (tag, t))
+
+
+def _check_totals(env, tot):
     st = env.stats()
     assert int(st[0]) == tot["steps"] and int(np.array(st[8:9], np.uint64).view(np.int64)[0]) == tot["reward_sum"] and int(st[2]) == tot["episodes"], (st, tot)
     return st
+
+
+def check_sampled_vs_oracle(env, opponent, color, seed, steps, auto_reset=True, boards=None, env_id_offset=0,
+                            compare_every=25, mode="sampled", rng=None, moves_max=149):
+    """Run `steps` steps on the device env and replay the SAME draws through N oracle envs; compare every output of
+    every step, the full state every `compare_every` steps, and the statistics at the end."""
+    N = env.N
+    nt = 1 if boards is None else len(boards)
+    O = [orc.OracleEnv(None if boards is None else boards[(env_id_offset + i) % nt], color, opponent, seed, env_id_offset + i,
+                       moves_max=moves_max)
+         for i in range(N)]
+    _cmp_export(env, O, "reset")
+    tot = dict(steps=0, reward_sum=0, episodes=0)
+    _run_sampled(env, O, seed, steps, tot, auto_reset, env_id_offset, compare_every, mode, rng)
+    return _check_totals(env, tot)
+
+
+def check_state_import_vs_oracle(env, opponent, color, seed, rng):
+    """State import (the `state` setter for many envs): play, import harvested positions (random side to move, rights,
+    move counters incl. values next to the 150-move cap) into a masked half of the envs, keep playing -- all against the
+    oracle doing the same."""
+    N = env.N
+    O = [orc.OracleEnv(None, color, opponent, seed, i) for i in range(N)]
+    tot = dict(steps=0, reward_sum=0, episodes=0)
+    _run_sampled(env, O, seed, 40, tot, tag="before import ")
+    hb, hp, hr = harvest_positions(n_envs=24, steps=300, seed=9)
+    for rnd in range(3):
+        pick = rng.randint(0, len(hb), size=N)
+        boards, players, rights = hb[pick], hp[pick] * rng.choice([-1, 1], size=N).astype(np.int8), rng.randint(0, 2, size=(N, 4)).astype(np.uint8)
+        move_count = rng.choice([0, 7, 148, 149, 150], size=N).astype(np.int32)
+        mask = (rng.rand(N) < 0.5).astype(np.uint8)
+        env.set_state(boards, players, rights, move_count, mask)
+        for i, o in enumerate(O):
+            if mask[i]:
+                o.import_state(boards[i], int(players[i]), rights[i], int(move_count[i]), episode=o.view()["episode"] + 1)
+        _cmp_export(env, O, "import %d" % rnd)
+        _run_sampled(env, O, seed, 60, tot, tag="after import %d " % rnd)
+        # a masked reset in mid-game (ChessEnvV2.reset of some envs), the others keep their repetition windows
+        mask = (rng.rand(N) < 0.3).astype(np.uint8)
+        env.reset(mask)
+        for i, o in enumerate(O):
+            if mask[i]:
+                o.reset(o.view()["episode"] + 1)
+        _cmp_export(env, O, "masked reset %d" % rnd)
+        _run_sampled(env, O, seed, 30, tot, tag="after masked reset %d " % rnd)
+    return _check_totals(env, tot)
 
 
 def check_trajectory_replay(make_env, traj):

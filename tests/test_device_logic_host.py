@@ -26,6 +26,12 @@ class EmulAdapter:
     def export(self):
         return self.e.export()
 
+    def reset(self, mask=None):
+        return self.e.reset(mask)
+
+    def set_state(self, *a):
+        return self.e.set_state(*a)
+
     def stats(self):
         return self.e.stats()
 
@@ -155,3 +161,9 @@ def test_endgames_with_long_repetition_windows():
 
 def test_move_sets_of_the_reference_pure_python_env(golden):
     assert ph.check_v1_move_sets(_mg, golden["v1_move_sets"]) > 15000
+
+
+@pytest.mark.parametrize("opponent,color", [("none", "WHITE"), ("random", "WHITE"), ("random", "BLACK")])
+def test_state_import_vs_oracle(opponent, color):
+    env = EmulAdapter(16, opponent=opponent, player_color=color, seed=41, auto_reset=True)
+    ph.check_state_import_vs_oracle(env, opponent, color, 41, np.random.RandomState(6))

@@ -41,6 +41,12 @@ class GpuAdapter:
     def export(self):
         return self.env.export_numpy()
 
+    def reset(self, mask=None):
+        return self.env.reset(mask)
+
+    def set_state(self, *a):
+        return self.env.set_state(*a)
+
     def stats(self):
         s = self.env.stats()
         from gym_chess_b200.batched_env import STAT_NAMES
@@ -363,3 +369,9 @@ def test_multi_step_launch_equals_single_steps(opponent, color):
 
 def test_move_sets_of_the_reference_pure_python_env(eng, golden):
     assert ph.check_v1_move_sets(_mg(eng), golden["v1_move_sets"]) > 15000
+
+
+@pytest.mark.parametrize("opponent,color", [("none", "WHITE"), ("random", "WHITE"), ("random", "BLACK")])
+def test_state_import_vs_oracle(opponent, color):
+    env = GpuAdapter(96, opponent=opponent, player_color=color, seed=41, auto_reset=True)
+    ph.check_state_import_vs_oracle(env, opponent, color, 41, np.random.RandomState(6))
