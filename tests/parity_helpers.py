@@ -211,6 +211,38 @@ def check_sampled_vs_oracle(env, opponent, color, seed, steps, auto_reset=True, 
     return _check_totals(env, tot)
 
 
+def check_external_actions_vs_oracle(env, opponent, color, seed, steps, rng, auto_reset):
+    """step(actions) with caller-chosen actions: mostly a random entry of the oracle's legal list, sometimes garbage
+    (illegal squares, castles, RESIGN, repeats after done) -- the invalid / done / cap early exits of chess_v2.py:240-258
+    in every opponent mode, with and without auto-reset."""
+    N = env.N
+    O = [orc.OracleEnv(None, color, opponent, seed, i) for i in range(N)]
+    tot = dict(steps=0, reward_sum=0, episodes=0)
+    for t in range(steps):
+        acts = np.zeros(N, np.int32)
+        for i, o in enumerate(O):
+            v = o.view()
+            if v["n_legal"] > 0 and rng.rand() < 0.8:
+                acts[i] = int(v["legal"][rng.randint(v["n_legal"])])
+            else:
+                acts[i] = int(rng.choice([rng.randint(0, 4101), 4100, 4096, 4097, 4098, 4099, 0, 4095]))
+        r, d, f, _, _ = env.step(acts)
+        for i, o in enumerate(O):
+            rr, dd, raised = o.step(int(acts[i]))
+            v2 = o.view()
+            assert (rr, dd) == (int(r[i]), bool(d[i])), (t, i, int(acts[i]), (rr, dd), (int(r[i]), int(d[i])), int(f[i]))
+            terminal = dd or v2["n_legal"] == 0
+            assert bool(f[i] & 32) == (terminal and auto_reset), (t, i, int(f[i]), terminal)
+            tot["steps"] += 1
+            tot["reward_sum"] += rr
+            tot["episodes"] += int(terminal)
+            if terminal and auto_reset:
+                o.reset(v2["episode"] + 1)
+        if t % 20 == 0 or t == steps - 1:
+            _cmp_export(env, O, "step %d" % t)
+    return _check_totals(env, tot)
+
+
 def check_state_import_vs_oracle(env, opponent, color, seed, rng):
     """State import (the `state` setter for many envs): play, import harvested positions (random side to move, rights,
     move counters incl. values next to the 150-move cap) into a masked half of the envs, keep playing -- all against the

@@ -167,3 +167,11 @@ def test_move_sets_of_the_reference_pure_python_env(golden):
 def test_state_import_vs_oracle(opponent, color):
     env = EmulAdapter(16, opponent=opponent, player_color=color, seed=41, auto_reset=True)
     ph.check_state_import_vs_oracle(env, opponent, color, 41, np.random.RandomState(6))
+
+
+@pytest.mark.parametrize("opponent,color,auto_reset", [("none", "WHITE", True), ("random", "WHITE", True), ("random", "BLACK", True),
+                                                         ("none", "WHITE", False), ("random", "WHITE", False)])
+def test_external_actions_incl_invalid_vs_oracle(opponent, color, auto_reset):
+    env = EmulAdapter(10, opponent=opponent, player_color=color, seed=77, auto_reset=auto_reset)
+    st = ph.check_external_actions_vs_oracle(env, opponent, color, 77, 420, np.random.RandomState(8), auto_reset)
+    assert st[7] > 0  # invalid actions occurred
