@@ -644,8 +644,11 @@ struct ListOut {
 
 // ChessEnvV2.possible_actions (chess_v2.py:333-335) of env e: decode the slots into the reference-ordered list.
 // Handles any number of slots by chunks of GCB_SLOTS.  Returns the list length.
+// `stage` (may be NULL): GCB_SLOTS words of scratch, element r at stage[r * stage_stride] -- the chunk's slots are copied
+// there first (row by row: coalesced across the envs of a warp), so that the decode's per-piece reads do not each pay a
+// trip to L2.
 template <class Offs, class Out>
-GCB_HD int env_legal_list_one(const EnvView& v, int e, Offs& offs, Out& out) {
+GCB_HD int env_legal_list_one(const EnvView& v, int e, Offs& offs, Out& out, u64* stage = nullptr, unsigned stage_stride = 1) {
     EnvRegs s;
     ulonglong2 a = v.bb01[e], c = v.bb23[e];
     s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
@@ -661,6 +664,13 @@ GCB_HD int env_legal_list_one(const EnvView& v, int e, Offs& offs, Out& out) {
         }
         rem ^= chunk;
         SlotRef csr = {v.tgt + (size_t)r0 * v.N + e, (unsigned)v.N, v.slots - r0, false};
+        if (stage) {
+            const int np = gcb_popc(chunk);
+            TgtSink src(csr, nullptr);
+            for (int r = 0; r < np; r++) stage[(unsigned)r * stage_stride] = src.get(r);
+            SlotRef ssr = {stage, stage_stride, np, true};
+            csr = ssr;
+        }
         TgtSink slots(csr, nullptr);
         n = emit_chunk_typemajor(s.b, !s.stm_black, chunk, slots, offs, out, n);
         r0 += GCB_SLOTS;

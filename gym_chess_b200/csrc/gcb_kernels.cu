@@ -331,11 +331,12 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_export(EnvView v, int8_t* __r
 __global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_list(EnvView v, uint16_t* __restrict__ actions, int stride,
                                                               int32_t* __restrict__ counts) {
     __shared__ uint16_t s_offs[GCB_SLOTS * GCB_BLOCK];
+    __shared__ u64 s_stage[GCB_SLOTS * GCB_BLOCK];
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= v.N) return;
     SmemOffs offs = {s_offs + threadIdx.x};
     ListOut out = {actions + (size_t)e * stride, stride};
-    const int n = env_legal_list_one(v, e, offs, out);
+    const int n = env_legal_list_one(v, e, offs, out, s_stage + threadIdx.x, (unsigned)GCB_BLOCK);
     if (counts) counts[e] = n;
 }
 
