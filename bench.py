@@ -310,6 +310,29 @@ def main():
         torch.cuda.synchronize()
         line["config_65536_envs"] = {"value": 65536 * args.steps / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT}
         small.close()
+        # ---- BASELINE.json configs[0]: the reference's own CPU-runnable case -- a single env, random-vs-random self-play,
+        # ~1k games -- on ONE host thread (the reference is single-threaded), plus legal-movegen positions/s of the same
+        # code on one thread and on all of them.  The engine is the oracle port (the Rust engine cannot be built here).
+        from oracle import oracle as orc
+        t0 = time.time()
+        s1 = orc.selfplay_mt(0, 0, 1, 270000, 1)
+        dt1 = time.time() - t0
+        sample_b = env.observe()[:65536].reshape(-1, 64).cpu().numpy()
+        inf = env.info_tensor()[:65536].cpu().numpy()
+        pl, rt = inf[:, 0].astype(np.int8), inf[:, 1:5].astype(np.uint8)
+        nthreads = os.cpu_count() or 1
+        t0 = time.time()
+        orc.movegen_batch(sample_b[:16384], pl[:16384], rt[:16384], False, stride=144, threads=1)
+        dtm1 = time.time() - t0
+        t0 = time.time()
+        orc.movegen_batch(sample_b, pl, rt, False, stride=144, threads=nthreads)
+        dtma = time.time() - t0
+        line["config_1_cpu"] = {
+            "workload": "single env, random self-play (opponent none), 270,000 steps = %d games, 1 thread" % s1["episodes"],
+            "env_steps_per_sec_1_thread": s1["steps"] / dt1, "movegen_positions_per_sec_1_thread": 16384 / dtm1,
+            "movegen_positions_per_sec_all_threads": 65536 / dtma, "threads": nthreads, "kind": "port",
+            "reference_published": {"env_steps_per_sec": 3205, "movegen_positions_per_sec": 4167,
+                                    "source": "gym_chess/test/v2/test_benchmark.py:46-50, README.md:372-374 (1 thread, unspecified CPU)"}}
         # ---- CPU baseline on this box's host cores (bounded sample)
         threads = os.cpu_count() or 1
         v, dt, _ = cpu_baseline(128 * threads, 5000, threads)
