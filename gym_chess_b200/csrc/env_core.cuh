@@ -8,8 +8,9 @@
 //   meta[N]  u64                       8 B   stm | rights | check flags | done | castle bits | n_legal |
 //                                            move_count | step_in_episode | hist_len
 //   zkey[N]  u64                       8 B   Zobrist key of the current board (board only)
-//   bloom[N] ulonglong2               16 B   two 64-bit Bloom words over the repetition window: key seen once /
-//                                            seen twice; the ring is only scanned when the second one hits
+//   bloom[8][N] u64                   64 B   two 256-bit Bloom filters over the repetition window: key seen once / seen
+//                                            twice (one word of each touched per ply); the ring is only scanned when the
+//                                            second one hits
 //   episode[N] u32                     4 B
 //   cnt[N]   ulonglong2               16 B   byte r = number of legal targets of the r-th own piece (r < 16): the
 //                                            uniform draw over the ordered list finds its piece from this one record
@@ -86,7 +87,7 @@ struct EnvView {
     ulonglong2* bb23;
     u64* meta;
     u64* zkey;
-    ulonglong2* bloom;
+    u64* bloom;  // [8][N]: words 0-3 "key seen once", 4-7 "seen twice" (two 256-bit Bloom filters, one word touched per ply)
     u32* episode;
     ulonglong2* cnt;
     u64* tgt;
@@ -108,7 +109,7 @@ struct EnvView {
 
 struct EnvRegs {
     Board b;
-    u64 zk, seen1, seen2, cnt_lo, cnt_hi;
+    u64 zk, cnt_lo, cnt_hi;
     u32 rights, chk, castle;  // chk bit0 white checked, bit1 black checked; castle bit0 queen side, bit1 king side
     int stm_black, done, n_legal, move_count, step, hist_len;
 };
@@ -321,9 +322,14 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
         const u64 cur = hc.base + slot;
         // repetition count of the pre-move board over the reversible window.  The ring is read only when the
         // "seen twice" Bloom word says this key may already have occurred twice (no false negatives).
-        const u64 bbit = 1ULL << (key >> 58);
+        // Two 256-bit Bloom filters per env ("seen once", "seen twice"), one 64-bit word of each touched per ply.
+        const u64 bbit = 1ULL << ((key >> 58) & 63);
+        u64* const b1 = v.bloom + (size_t)((key >> 56) & 3) * (size_t)v.N + e;
+        u64* const b2 = b1 + 4 * (size_t)v.N;
+        u64 seen1 = 0, seen2 = 0;
+        if (s.hist_len > 0) seen1 = GCB_LDS(b1), seen2 = GCB_LDS(b2);  // (an empty window: the words are stale)
         int cnt = 0;
-        if (s.seen2 & bbit) {
+        if (seen2 & bbit) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -345,17 +351,24 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
         *rep = cnt >= 2;  // saved_boards[key] reaches 3 with this ply
         GCB_STS(&v.hist[(cur & (u64)v.hist_mask) * (u64)v.N + e], key);
         hc.cursor = slot + 1;
-        if (s.seen1 & bbit) s.seen2 |= bbit;
-        s.seen1 |= bbit;
+        const bool first_of_window = s.hist_len == 0;
 
         u32 rights = mask_rights(s.b, s.rights);  // engine entry masks by the INPUT board (Q21)
         int status;
         bool irr;
         r = apply_action(s.b, rights, !s.stm_black, action, &status, &irr, &s.zk, v.zob);
         s.rights = rights;
-        if (irr) s.hist_len = 0, s.seen1 = 0, s.seen2 = 0;
-        else if (s.hist_len < v.hist_mask) s.hist_len++;
-        else st.f += SF_HISTOVF;
+        if (irr) {
+            s.hist_len = 0;  // the window restarts empty: its Bloom words are rebuilt by the next reversible ply
+        } else {
+            if (first_of_window) {  // first key of a new window: every word of both filters starts from zero
+                for (int w = 0; w < 8; w++) GCB_STS(v.bloom + (size_t)w * (size_t)v.N + e, 0ULL);
+            }
+            if (seen1 & bbit) GCB_STS(b2, seen2 | bbit);
+            GCB_STS(b1, seen1 | bbit);
+            if (s.hist_len < v.hist_mask) s.hist_len++;
+            else st.f += SF_HISTOVF;
+        }
     }
     s.stm_black ^= 1;
     GenCtx g;
@@ -396,8 +409,8 @@ struct StepIO {
 GCB_HD void env_load(const EnvView& v, int e, EnvRegs& s, u32& ep) {
     ulonglong2 a = GCB_LDS(&v.bb01[e]), c = GCB_LDS(&v.bb23[e]);
     s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
-    ulonglong2 bl = GCB_LDS(&v.bloom[e]), ct = GCB_LDS(&v.cnt[e]);
-    s.seen1 = bl.x, s.seen2 = bl.y, s.cnt_lo = ct.x, s.cnt_hi = ct.y;
+    ulonglong2 ct = GCB_LDS(&v.cnt[e]);
+    s.cnt_lo = ct.x, s.cnt_hi = ct.y;
     unpack_meta(GCB_LDS(&v.meta[e]), s);
     s.zk = GCB_LDS(&v.zkey[e]);
     ep = GCB_LDS(&v.episode[e]);
@@ -405,7 +418,6 @@ GCB_HD void env_load(const EnvView& v, int e, EnvRegs& s, u32& ep) {
 GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
     GCB_STS(&v.bb01[e], make_ulonglong2(s.b.t0, s.b.t1));
     GCB_STS(&v.bb23[e], make_ulonglong2(s.b.t2, s.b.w));
-    GCB_STS(&v.bloom[e], make_ulonglong2(s.seen1, s.seen2));
     GCB_STS(&v.cnt[e], make_ulonglong2(s.cnt_lo, s.cnt_hi));
     GCB_STS(&v.meta[e], pack_meta(s));
     GCB_STS(&v.zkey[e], s.zk);
@@ -493,7 +505,6 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
                 unpack_meta(v.t_meta[t], s);
                 s.zk = v.t_zkey[t];
-                s.seen1 = 0, s.seen2 = 0;
                 {
                     ulonglong2 ct = v.t_cnt[t];
                     s.cnt_lo = ct.x, s.cnt_hi = ct.y;
@@ -580,7 +591,6 @@ GCB_HD void env_import_one(const EnvView& v, int e, const int8_t* board, int pla
     env_load(v, e, s, ep);
     s.b = board_from_mailbox(board);
     s.zk = zobrist_full(s.b);
-    s.seen1 = s.seen2 = 0;
     s.rights = mask_rights(s.b, rights);
     s.done = 0, s.move_count = move_count, s.step = 0, s.hist_len = 0;
     s.stm_black = player < 0 ? 0 : 1;  // ply_and_movegen(apply = false) flips the side, then generates for it
@@ -596,7 +606,7 @@ GCB_HD void env_import_one(const EnvView& v, int e, const int8_t* board, int pla
 GCB_HD void env_idle_tick(const EnvView& v, int e, u64 tick) {
     EnvRegs s;
     unpack_meta(v.meta[e], s);
-    s.seen1 = s.seen2 = 0, s.zk = 0, s.cnt_lo = s.cnt_hi = 0;  // (not touched: only meta is rewritten)
+    s.zk = 0, s.cnt_lo = s.cnt_hi = 0;  // (not touched: only meta is rewritten)
     if (s.hist_len == 0) return;
     HistCursor hc;
     hc.base = tick * (u64)v.pps, hc.cursor = 0;
@@ -613,7 +623,6 @@ GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulo
     EnvRegs s;
     s.b = b;
     s.zk = zobrist_full(b);
-    s.seen1 = s.seen2 = 0;
     s.rights = mask_rights(b, 15u);  // all four True, then engine.update_state masks them (chess_v2.py:195-204)
     s.chk = check_flags(b);
     s.stm_black = 0, s.done = 0, s.move_count = 0, s.step = 0, s.hist_len = 0;

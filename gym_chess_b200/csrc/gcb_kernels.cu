@@ -643,7 +643,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     ALLOC(v.bb23, (size_t)N * 16);
     ALLOC(v.meta, (size_t)N * 8);
     ALLOC(v.zkey, (size_t)N * 8);
-    ALLOC(v.bloom, (size_t)N * 16);
+    ALLOC(v.bloom, (size_t)N * 64);
     ALLOC(v.cnt, (size_t)N * 16);
     ALLOC(env->t_cnt, (size_t)T * 16);
     ALLOC(v.episode, (size_t)N * 4);
@@ -681,7 +681,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
             cudaMemset(v.stat_rows, 0, (size_t)((N + 31) / 32) * ST_COUNT * 8) != cudaSuccess || cudaMemset(v.episode, 0, (size_t)N * 4) != cudaSuccess ||
             cudaMemset(v.meta, 0, (size_t)N * 8) != cudaSuccess || cudaMemset(v.bb01, 0, (size_t)N * 16) != cudaSuccess ||
             cudaMemset(v.bb23, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.zkey, 0, (size_t)N * 8) != cudaSuccess ||
-            cudaMemset(v.bloom, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.cnt, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
+            cudaMemset(v.bloom, 0, (size_t)N * 64) != cudaSuccess || cudaMemset(v.cnt, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
             cudaMemset(env->t_tgt, 0, (size_t)T * S * 8) != cudaSuccess) {
             rc = fail(GCB_E_CUDA, "cudaMemcpy/cudaMemset", "env init");
             break;

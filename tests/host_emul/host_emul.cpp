@@ -117,7 +117,7 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
     EnvView& v = E->v;
     v.bb01 = (ulonglong2*)calloc(N, 16), v.bb23 = (ulonglong2*)calloc(N, 16);
     v.meta = (u64*)calloc(N, 8), v.zkey = (u64*)calloc(N, 8), v.episode = (u32*)calloc(N, 4);
-    v.bloom = (ulonglong2*)calloc(N, 16), v.cnt = (ulonglong2*)calloc(N, 16), E->t_cnt = (ulonglong2*)calloc(T, 16);
+    v.bloom = (u64*)calloc(N, 64), v.cnt = (ulonglong2*)calloc(N, 16), E->t_cnt = (ulonglong2*)calloc(T, 16);
     v.tgt = (u64*)calloc((size_t)N * slots, 8), v.hist = (u64*)calloc((size_t)N * hist_cap, 8);
     v.stats = (u64*)calloc(ST_COUNT, 8);
     E->t_bb01 = (ulonglong2*)calloc(T, 16), E->t_bb23 = (ulonglong2*)calloc(T, 16);
