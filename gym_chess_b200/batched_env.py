@@ -73,9 +73,13 @@ class BatchedChessEnv:
         self.observation_shape, self.num_actions = (8, 8), 64 * 64 + 4 + 1  # Box(-6,6,(8,8)), Discrete(4101)
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            _lib.lib().gcb_env_destroy(self._h)
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
             self._h = C.c_void_p()
+            try:
+                _lib.lib().gcb_env_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown: module globals may already be gone)
+                pass
 
     __del__ = close
 

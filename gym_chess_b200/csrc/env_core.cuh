@@ -308,6 +308,33 @@ GCB_HD bool action_is_legal(const SlotRef& sr, const EnvRegs& s, int action) {
 
 
 
+#if defined(__CUDA_ARCH__)
+// Ring scan, warp-cooperative: a scan is needed by few lanes at a time (the "seen twice" filter hit) but it is long
+// (the whole repetition window, up to hundreds of entries), so the lanes that are executing this ply together take the
+// scans one owner at a time and split each window among themselves; the owner receives the count of entries equal to
+// its key.  Opportunistic grouping (__activemask): whatever set of lanes arrives here together cooperates.
+__device__ __forceinline__ int coop_ring_count(const EnvView& v, bool need, int e, u64 cur, int len, u64 key) {
+    const unsigned mask = __activemask();
+    unsigned todo = __ballot_sync(mask, need);
+    if (!todo) return 0;
+    const int lane = threadIdx.x & 31;
+    const int nact = __popc(mask), myrank = __popc(mask & ((1u << lane) - 1u));
+    int mine = 0;
+    while (todo) {
+        const int owner = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int oe = __shfl_sync(mask, e, owner), olen = __shfl_sync(mask, len, owner);
+        const u64 ocur = __shfl_sync(mask, cur, owner), okey = __shfl_sync(mask, key, owner);
+        int c = 0;
+        for (int j = myrank + 1; j <= olen; j += nact)
+            c += (GCB_LDS(&v.hist[((ocur - (u64)j) & (u64)v.hist_mask) * (u64)v.N + oe]) == okey);
+        const int total = __reduce_add_sync(mask, c);
+        if (lane == owner) mine = total;
+    }
+    return mine;
+}
+#endif
+
 // One ply = player_move (chess_v2.py:393-412: engine.next_state + repetition count on the PRE-move
 // board) + the state setter (315-323) + switch_player (296-299) + get_possible_moves for the new
 // side to move (573-582).  apply=false only switches the side and regenerates (BLACK-agent reset
@@ -328,25 +355,15 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
         u64* const b2 = b1 + 4 * (size_t)v.N;
         u64 seen1 = 0, seen2 = 0;
         if (s.hist_len > 0) seen1 = GCB_LDS(b1), seen2 = GCB_LDS(b2);  // (an empty window: the words are stale)
+        const bool need_scan = (seen2 & bbit) != 0;
         int cnt = 0;
-        if (seen2 & bbit) {
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+        cnt = coop_ring_count(v, need_scan, e, cur, s.hist_len, key);
+#else
+        if (need_scan)
+            for (int j = 1; j <= s.hist_len; j++) cnt += (v.hist[((cur - (u64)j) & (u64)v.hist_mask) * (u64)v.N + e] == key);
 #endif
-            for (int j0 = 1; j0 <= s.hist_len; j0 += 8) {  // 8 independent loads in flight
-                u64 h[8];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int i = 0; i < 8; i++)
-                    h[i] = (j0 + i <= s.hist_len) ? GCB_LDS(&v.hist[((cur - (u64)(j0 + i)) & (u64)v.hist_mask) * (u64)v.N + e]) : 0ULL;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int i = 0; i < 8; i++) cnt += (h[i] == key);
-            }
-            st.scan += s.hist_len;
-        }
+        if (need_scan) st.scan += s.hist_len;
         st.window += s.hist_len;
         *rep = cnt >= 2;  // saved_boards[key] reaches 3 with this ply
         GCB_STS(&v.hist[(cur & (u64)v.hist_mask) * (u64)v.N + e], key);
