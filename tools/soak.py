@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""One-off soak: bigger randomized differential runs of the CUDA path against the oracle than the test-suite does."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from tests import parity_helpers as ph
+from tests.test_gpu_parity import GpuAdapter, _mg
+from gym_chess_b200 import BatchedChessEngine
+
+t0 = time.time()
+eng = BatchedChessEngine()
+rng = np.random.RandomState(123)
+b, p, r = ph.crafted_positions(rng, 150000)
+n1 = ph.check_movegen_vs_oracle(_mg(eng), b, p, r, attack=False)
+n2 = ph.check_movegen_vs_oracle(_mg(eng), b, p, r, attack=True)
+hb, hp, hr = ph.harvest_positions(n_envs=200, steps=330, seed=77)
+n3 = ph.check_movegen_vs_oracle(_mg(eng), hb, hp, hr, attack=False)
+print("movegen: %d + %d + %d moves compared, %.0f s" % (n1, n2, n3, time.time() - t0), flush=True)
+for opponent, color, seed in (("none", "WHITE", 101), ("random", "WHITE", 102), ("random", "BLACK", 103)):
+    env = GpuAdapter(600, opponent=opponent, player_color=color, seed=seed, auto_reset=True)
+    st = ph.check_sampled_vs_oracle(env, opponent, color, seed, 1200, compare_every=100)
+    print(opponent, color, "steps", int(st[0]), "episodes", int(st[2]), "mates", int(st[3]), "reps", int(st[4]), "%.0f s" % (time.time() - t0), flush=True)
+    env = GpuAdapter(300, opponent=opponent, player_color=color, seed=seed + 10, auto_reset=True)
+    ph.check_state_import_vs_oracle(env, opponent, color, seed + 10, np.random.RandomState(seed))
+    env = GpuAdapter(300, opponent=opponent, player_color=color, seed=seed + 20, auto_reset=True)
+    ph.check_external_actions_vs_oracle(env, opponent, color, seed + 20, 600, np.random.RandomState(seed + 1), True)
+    print("  import + external actions ok %.0f s" % (time.time() - t0), flush=True)
+print("soak ok")
