@@ -3,9 +3,10 @@
 // Re-design, not a translation: the reference walks an 8x8 isize mailbox with HashMap
 // attack maps and simulates every candidate move (src/lib.rs:501-677); here a position is
 // four 64-bit planes (three piece-code bit-planes + a colour plane, 32 B), slider attacks
-// come from Hyperbola-Quintessence with __brevll on arithmetic line masks (no magic
-// tables), the enemy attack map is one u64, and the legality filter is a symmetric
-// "is the king square attacked after the move" test with a provably exact fast path.
+// come from Hyperbola-Quintessence with __brevll on tabulated line masks, the enemy attack
+// map is one u64, the legality filter is a check mask + pin rays computed once per position,
+// and the legal set is one 64-bit target set per own piece (the ordered list is a decode).
+// Small geometry tables are built at compile time (constexpr) into device global memory.
 // The OBSERVABLE behaviour (move order, quirks Q1-Q23 of SURVEY.md section 9) is that of
 // the reference; each routine cites the lines whose results it reproduces.
 //

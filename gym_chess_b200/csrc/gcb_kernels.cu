@@ -1,7 +1,8 @@
 // gcb_kernels.cu -- kernels + C ABI of libgymchess_b200.so (sm_100a).  See include/gymchess_b200.h.
 //
 // The per-env logic lives in env_core.cuh / chess_core.cuh; this file holds the kernels (one thread per env or
-// position), the block-level statistics reduction and the host-side C ABI.
+// position; the sampled self-play kernel runs up to 64 steps per launch), the per-warp statistics rows and their
+// reduction, and the host-side C ABI.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
