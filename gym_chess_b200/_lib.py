@@ -91,6 +91,9 @@ SIGNATURES = {
     "gcb_env_legal_actions": (i32, [vp, vp, i32, vp, vp]),
     "gcb_env_piece_slots": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_int32)]),
     "gcb_env_positions": (i32, [vp, C.POINTER(Positions)]),
+    "gcb_env_snapshot_bytes": (i32, [vp, C.POINTER(C.c_uint64)]),
+    "gcb_env_snapshot": (i32, [vp, vp, C.POINTER(C.c_uint64), vp]),
+    "gcb_env_restore": (i32, [vp, vp, C.c_uint64, vp]),
     "gcb_env_stats": (i32, [vp, vp, vp]),
     "gcb_env_stats_reset": (i32, [vp, vp]),
     "gcb_env_stats_ptr": (i32, [vp, C.POINTER(vp), vp]),

@@ -218,6 +218,26 @@ class BatchedChessEnv:
                     black_king_castle_is_possible=bool(r[3]), black_queen_castle_is_possible=bool(r[4]),
                     white_king_is_checked=bool(r[5]), black_king_is_checked=bool(r[6]))
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def snapshot(self):
+        """-> (uint8 cuda tensor, tick): the whole resident state; `restore` resumes bit-identically (torch.save-able)."""
+        n, tick = C.c_uint64(), C.c_uint64()
+        check(_lib.lib().gcb_env_snapshot_bytes(self._h, C.byref(n)))
+        with torch.cuda.device(self.device):
+            buf = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+            check(_lib.lib().gcb_env_snapshot(self._h, C.c_void_p(buf.data_ptr()), C.byref(tick), _stream_ptr()))
+        return buf, int(tick.value)
+
+    def restore(self, snap):
+        buf, tick = snap
+        n = C.c_uint64()
+        check(_lib.lib().gcb_env_snapshot_bytes(self._h, C.byref(n)))
+        if buf.numel() != n.value or buf.dtype != torch.uint8:
+            raise ValueError("snapshot does not belong to an env of this configuration")
+        with torch.cuda.device(self.device):
+            buf = buf.to(self.device).contiguous()
+            check(_lib.lib().gcb_env_restore(self._h, C.c_void_p(buf.data_ptr()), C.c_uint64(tick), _stream_ptr()))
+
     # ------------------------------------------------------------------ statistics
     def stats(self):
         out = np.zeros(16, np.uint64)

@@ -846,6 +846,59 @@ extern "C" int gcb_env_import(gcb_env* env, const int8_t* d_boards, const int8_t
     return GCB_OK;
 }
 
+// ---- checkpoint / resume: the resident state is plain arrays; a snapshot is their concatenation in one device buffer
+struct SnapPart {
+    void* ptr;
+    size_t bytes;
+};
+static int snap_parts(gcb_env* env, SnapPart* p) {
+    const size_t N = (size_t)env->v.N, S = (size_t)env->v.slots, H = (size_t)env->v.hist_mask + 1;
+    int k = 0;
+    p[k++] = {env->v.bb01, N * 16}, p[k++] = {env->v.bb23, N * 16}, p[k++] = {env->v.meta, N * 8}, p[k++] = {env->v.zkey, N * 8};
+    p[k++] = {env->v.bloom, N * 64}, p[k++] = {env->v.cnt, N * 16}, p[k++] = {env->v.episode, N * 4};
+    p[k++] = {env->v.tgt, N * S * 8}, p[k++] = {env->v.hist, N * H * 8};
+    p[k++] = {env->v.stat_rows, ((N + 31) / 32) * ST_COUNT * 8};
+    return k;
+}
+
+extern "C" int gcb_env_snapshot_bytes(gcb_env* env, uint64_t* bytes) {
+    if (!env || !bytes) return fail(GCB_E_ARG, "gcb_env_snapshot_bytes", "null pointer");
+    SnapPart p[16];
+    const int k = snap_parts(env, p);
+    size_t tot = 0;
+    for (int i = 0; i < k; i++) tot += (p[i].bytes + 255) & ~(size_t)255;
+    *bytes = tot;
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_snapshot(gcb_env* env, void* d_buf, uint64_t* tick, void* stream) {
+    ENV_CHECK(env);
+    if (!d_buf || !tick) return fail(GCB_E_ARG, "gcb_env_snapshot", "null pointer");
+    SnapPart p[16];
+    const int k = snap_parts(env, p);
+    char* dst = reinterpret_cast<char*>(d_buf);
+    for (int i = 0; i < k; i++) {
+        CU(cudaMemcpyAsync(dst, p[i].ptr, p[i].bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        dst += (p[i].bytes + 255) & ~(size_t)255;
+    }
+    *tick = env->tick;
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_restore(gcb_env* env, const void* d_buf, uint64_t tick, void* stream) {
+    ENV_CHECK(env);
+    if (!d_buf) return fail(GCB_E_ARG, "gcb_env_restore", "null pointer");
+    SnapPart p[16];
+    const int k = snap_parts(env, p);
+    const char* src = reinterpret_cast<const char*>(d_buf);
+    for (int i = 0; i < k; i++) {
+        CU(cudaMemcpyAsync(p[i].ptr, src, p[i].bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        src += (p[i].bytes + 255) & ~(size_t)255;
+    }
+    env->tick = tick;
+    return GCB_OK;
+}
+
 extern "C" int gcb_env_export(gcb_env* env, int8_t* d_boards, int32_t* d_info, void* stream) {
     ENV_CHECK(env);
     k_env_export<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, d_boards, d_info);

@@ -186,6 +186,14 @@ int gcb_env_legal_actions(gcb_env *env, uint16_t *d_actions, int stride, int32_t
 int gcb_env_piece_slots(gcb_env *env, uint64_t **d_slots, int32_t *n_slots);
 int gcb_env_positions(gcb_env *env, gcb_positions *out);
 
+/* Checkpoint / resume (the reference has none: its whole env state is the `state` dict + saved_boards + counters).  A
+ * snapshot is the concatenation of the resident arrays (positions, meta, keys, Bloom words, legal set, Zobrist ring,
+ * statistics rows) in ONE device buffer of gcb_env_snapshot_bytes() bytes plus the ring tick; restoring it into an env
+ * created with the same configuration resumes bit-identically (same Philox counters). */
+int gcb_env_snapshot_bytes(gcb_env *env, uint64_t *bytes);
+int gcb_env_snapshot(gcb_env *env, void *d_buf, uint64_t *tick, void *stream);
+int gcb_env_restore(gcb_env *env, const void *d_buf, uint64_t tick, void *stream);
+
 /* episode statistics accumulated on the device since the last gcb_env_stats_reset:
  * out uint64[16] = steps, plies, episodes, mates, repetitions, caps, wedged, invalid, reward_sum (two's complement
  * int64), legal_sum, in_check, hist_overflow, slot_overflow, hist_scanned (ring entries actually read by the

@@ -383,3 +383,25 @@ def test_external_actions_incl_invalid_vs_oracle(opponent, color, auto_reset):
     env = GpuAdapter(48, opponent=opponent, player_color=color, seed=77, auto_reset=auto_reset)
     st = ph.check_external_actions_vs_oracle(env, opponent, color, 77, 420, np.random.RandomState(8), auto_reset)
     assert st[7] > 0  # invalid actions occurred
+
+
+def test_snapshot_restore_resumes_bit_identically():
+    """checkpoint / resume: snapshot, play on, restore, play again -> the same actions, outputs, state and statistics"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv
+
+    env = BatchedChessEnv(5000, opponent="random", player_color="BLACK", seed=55, history_cap=256)
+    env.step_sampled(130)
+    snap = env.snapshot()
+    r1, d1, f1, a1, b1 = env.step_sampled(200, record=True)
+    r1, d1, f1 = r1.clone(), d1.clone(), f1.clone()
+    s1, e1 = env.stats(), env.export_numpy()
+    env.restore(snap)
+    r2, d2, f2, a2, b2 = env.step_sampled(200, record=True)
+    assert torch.equal(a1, a2) and torch.equal(b1, b2) and torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(f1, f2)
+    s2, e2 = env.stats(), env.export_numpy()
+    assert s1 == s2 and all((x == y).all() for x, y in zip(e1, e2))
+    other = BatchedChessEnv(5000, opponent="random", player_color="BLACK", seed=55, history_cap=256)  # a fresh env of the same configuration
+    other.restore((snap[0].cpu(), snap[1]))
+    r3, d3, f3, a3, b3 = other.step_sampled(200, record=True)
+    assert torch.equal(a1, a3) and torch.equal(r1, r3) and other.stats() == s1
