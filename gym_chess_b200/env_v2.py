@@ -159,6 +159,19 @@ class ChessEnvV2:
             black_queen_castle_is_possible=self.black_queen_castle_is_possible,
             white_king_is_checked=self.white_king_is_checked, black_king_is_checked=self.black_king_is_checked)
 
+    @state.setter
+    def state(self, state):
+        """chess_v2.py:315-323 assigns the board and the six flags and nothing else (possible_moves, saved_boards and the
+        side to move keep their old values).  Here the assignment starts a new episode from that position for the side
+        currently to move: flags are re-derived by update_state, possible_moves is regenerated and the repetition window
+        is emptied (gcb_env_import) -- the consistent form of what the reference's callers do by hand."""
+        board = np.asarray(state.get("board"), np.int8).reshape(1, 64)
+        rights = np.array([[bool(state.get(k)) for k in ("white_king_castle_is_possible", "white_queen_castle_is_possible",
+                                                         "black_king_castle_is_possible", "black_queen_castle_is_possible")]], np.uint8)
+        player = np.array([1 if state.get("current_player", self.current_player) == WHITE else -1], np.int8)
+        self._env.set_state(board, player, rights, np.array([self.move_count], np.int32))
+        self._pull()
+
     @property
     def possible_moves(self):
         return self._possible_moves

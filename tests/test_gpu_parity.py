@@ -405,3 +405,21 @@ def test_snapshot_restore_resumes_bit_identically():
     other.restore((snap[0].cpu(), snap[1]))
     r3, d3, f3, a3, b3 = other.step_sampled(200, record=True)
     assert torch.equal(a1, a3) and torch.equal(r1, r3) and other.stats() == s1
+
+
+def test_compat_env_v2_state_setter():
+    """`env.state = s` on the single-env class: the position, flags and legal moves are those of the assigned state"""
+    from gym_chess_b200 import ChessEngine, ChessEnvV2
+
+    env = ChessEnvV2(opponent="none", log=False)
+    for a in (3364, 796, 4013):  # e2e4, e7e5, g1f3
+        env.step(a)
+    s = env.state
+    other = ChessEnvV2(opponent="none", log=False)
+    other.step(3364)                       # Black to move in both
+    other.state = s
+    assert other.state["board"] == s["board"] and other.current_player == env.current_player
+    assert other.possible_actions == env.possible_actions
+    eng = ChessEngine()
+    assert [codec_s for codec_s in eng.get_possible_moves(s, env.current_player)] == [env.move_to_str_code(m) for m in other.possible_moves]
+    env.close(), other.close()
