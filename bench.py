@@ -97,17 +97,20 @@ def run_reference(args, rank, world):
     sample = 8192
     from oracle import oracle as orc
 
-    for _ in range(args.warmup):
-        orc.selfplay_mt(0, 0, sample, 1, threads)
+    # the same steady-state workload as the GPU arm: a persistent pool of envs, burn-in so that game phases are mixed
+    # (episodes are ~270 plies long), W warm-up steps, then exactly K timed steps of every env of the sample
+    pool = orc.SelfplayPool(0, 0, sample)
+    pool.run(300, threads)
+    pool.run(args.warmup, threads)
     t0 = time.time()
-    st = orc.selfplay_mt(0, 0, sample, args.steps, threads)
+    st = pool.run(args.steps, threads)
     dt = time.time() - t0
     v = st["steps"] / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": WORKLOAD % ENVS_PER_GPU, "sample": "%d envs x %d steps" % (sample, args.steps)},
+        "config": {"workload": WORKLOAD % ENVS_PER_GPU, "sample": "%d envs x %d steps after a 300-step burn-in" % (sample, args.steps)},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d envs x %d steps of the same self-play workload, C oracle (restates src/lib.rs + "
                                    "chess_v2.py; the Rust engine is unbuildable here), %d pthreads" % (sample, args.steps, threads)},

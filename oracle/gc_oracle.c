@@ -627,6 +627,62 @@ void gco_selfplay_mt(uint64_t seed, uint32_t env_lo, uint32_t env_hi, uint64_t n
     free(args);
 }
 
+/* ---- a persistent pool of self-play envs (bench.py --impl reference): burn-in once, then timed steps on the same
+ * envs, so that the CPU arm measures the same steady-state mix of game phases as the GPU arm */
+struct gco_pool {
+    gco_env *envs;
+    uint32_t n;
+};
+
+typedef struct {
+    gco_pool *pool;
+    uint32_t lo, hi;
+    uint64_t nsteps;
+    gco_stats st;
+} pool_arg;
+
+static void *pool_worker(void *p) {
+    pool_arg *a = (pool_arg *)p;
+    memset(&a->st, 0, sizeof(a->st));
+    for (uint32_t i = a->lo; i < a->hi; i++) gco_selfplay(&a->pool->envs[i], a->nsteps, &a->st);
+    return NULL;
+}
+
+gco_pool *gco_pool_new(uint64_t seed, uint32_t env_lo, uint32_t env_hi) {
+    gco_pool *p = (gco_pool *)malloc(sizeof(gco_pool));
+    p->n = env_hi - env_lo;
+    p->envs = (gco_env *)malloc(sizeof(gco_env) * (size_t)p->n);
+    for (uint32_t i = 0; i < p->n; i++) gco_env_init(&p->envs[i], NULL, 0, GCO_OPP_NONE, seed, env_lo + i);
+    return p;
+}
+
+void gco_pool_run(gco_pool *p, uint64_t nsteps_per_env, int threads, gco_stats *st) {
+    if (threads < 1) threads = 1;
+    if ((uint32_t)threads > p->n) threads = (int)(p->n ? p->n : 1);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    pool_arg *args = (pool_arg *)malloc(sizeof(pool_arg) * (size_t)threads);
+    for (int t = 0; t < threads; t++) {
+        args[t].pool = p, args[t].nsteps = nsteps_per_env;
+        args[t].lo = (uint32_t)((uint64_t)p->n * (uint64_t)t / (uint64_t)threads);
+        args[t].hi = (uint32_t)((uint64_t)p->n * (uint64_t)(t + 1) / (uint64_t)threads);
+        pthread_create(&th[t], NULL, pool_worker, &args[t]);
+    }
+    memset(st, 0, sizeof(*st));
+    for (int t = 0; t < threads; t++) {
+        pthread_join(th[t], NULL);
+        stats_add(st, &args[t].st);
+    }
+    free(th);
+    free(args);
+}
+
+void gco_pool_free(gco_pool *p) {
+    if (!p) return;
+    for (uint32_t i = 0; i < p->n; i++) gco_env_free(&p->envs[i]);
+    free(p->envs);
+    free(p);
+}
+
 /* ------------------------------------------------------------------ batch wrappers (array in / array out) */
 
 /* n positions in the reference wire format: boards int8[n][64], players int8[n] (+1/-1),

@@ -262,6 +262,28 @@ def selfplay_mt(seed, env_lo, env_hi, nsteps_per_env, threads):
     return st.as_dict()
 
 
+class SelfplayPool:
+    """persistent self-play envs on the host threads (the CPU arm of bench.py)"""
+
+    def __init__(self, seed, env_lo, env_hi):
+        L = lib()
+        L.gco_pool_new.restype = C.c_void_p
+        L.gco_pool_new.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+        L.gco_pool_run.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Stats)]
+        L.gco_pool_free.argtypes = [C.c_void_p]
+        self._h = L.gco_pool_new(seed, env_lo, env_hi)
+
+    def run(self, nsteps_per_env, threads):
+        st = Stats()
+        lib().gco_pool_run(self._h, nsteps_per_env, threads, C.byref(st))
+        return st.as_dict()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().gco_pool_free(self._h)
+            self._h = None
+
+
 def draw_u32(seed, env_id, episode, step, purpose):
     return int(lib().gco_draw_u32(seed, env_id, episode, step, purpose))
 
