@@ -233,6 +233,12 @@ def main():
         if tj.get("envs") == N:  # per launch like `achieved`: a launch of the sampled kernel runs up to 64 steps
             traffic = tj["dram_bytes_per_step"] * args.steps / max(1, launches)
 
+    pipes = None  # what actually bounds the kernel (integer pipe), from the committed ncu capture
+    pp = os.path.join(ROOT, "profiles", "pipes.json")
+    if os.path.exists(pp):
+        with open(pp) as f:
+            pipes = json.load(f)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -247,7 +253,8 @@ def main():
                      "mean_hist_window": W, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_step * N * steps_per_launch, "steps_per_launch": steps_per_launch,
                      "launch_ms": ms / max(1, launches),
-                     "note": "integer-pipe (ALU) bound, not HBM bound: see DESIGN.md section 3 and profiles/"},
+                     "note": "integer-pipe (ALU) bound, not HBM bound: see DESIGN.md section 3 and profiles/",
+                     "pipes_from_profile": pipes},
         "episode_stats_all_ranks": {k: int(tot[i]) for i, k in enumerate(
             ("steps", "plies", "episodes", "mates", "repetitions", "caps", "wedged", "invalid", "reward_sum", "legal_sum",
              "in_check", "hist_overflow", "slot_overflow", "hist_scanned", "hist_window"))},
