@@ -86,6 +86,9 @@ SIGNATURES = {
     "gcb_env_step_sampled": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
     "gcb_env_step_host": (i32, [vp, vp, vp, vp, vp]),
     "gcb_env_step_index_host": (i32, [vp, vp, vp, vp, vp]),
+    "gcb_env_step_host_async": (i32, [vp, vp, vp, vp, vp, vp]),
+    "gcb_env_step_index_host_async": (i32, [vp, vp, vp, vp, vp, vp]),
+    "gcb_env_wait": (i32, [vp, vp]),
     "gcb_env_export": (i32, [vp, vp, vp, vp]),
     "gcb_env_legal_mask": (i32, [vp, vp, vp]),
     "gcb_env_legal_actions": (i32, [vp, vp, i32, vp, vp]),

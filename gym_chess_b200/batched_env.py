@@ -32,8 +32,17 @@ class _DevArray:
         self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
 
 
-def _stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream_ptr(stream=None):
+    return C.c_void_p((torch.cuda.current_stream() if stream is None else stream).cuda_stream)
+
+
+def _host_ptr(buf):
+    """address of a host buffer: numpy array, CPU torch tensor, ctypes pointer / int, or None"""
+    if buf is None or isinstance(buf, (int, C.c_void_p)):
+        return buf
+    if isinstance(buf, torch.Tensor):
+        return C.c_void_p(buf.data_ptr())
+    return C.c_void_p(buf.ctypes.data)
 
 
 class BatchedChessEnv:
@@ -152,6 +161,22 @@ class BatchedChessEnv:
     def step_index_host(self, u32, reward=None, done=None, flags=None):
         u = np.ascontiguousarray(u32, dtype=np.uint32)
         return self._host_call(_lib.lib().gcb_env_step_index_host, u, reward, done, flags)
+
+    # asynchronous host-buffer steps (page-locked numpy / torch buffers only): enqueue on the current torch stream and return;
+    # results are valid after wait().  Two env objects (shards of one device) stepped alternately on two streams keep the
+    # device busy while the host reads one shard's results and writes its next actions.
+    def step_host_async(self, actions, reward, done, flags, stream=None):
+        return self._host_async(_lib.lib().gcb_env_step_host_async, actions, reward, done, flags, stream)
+
+    def step_index_host_async(self, u32, reward, done, flags, stream=None):
+        return self._host_async(_lib.lib().gcb_env_step_index_host_async, u32, reward, done, flags, stream)
+
+    def _host_async(self, fn, inp, reward, done, flags, stream):
+        check(fn(self._h, _host_ptr(inp), _host_ptr(reward), _host_ptr(done), _host_ptr(flags), _stream_ptr(stream)))
+
+    def wait(self, stream=None):
+        """block until the steps enqueued on `stream` (default: the current torch stream) have finished"""
+        check(_lib.lib().gcb_env_wait(self._h, _stream_ptr(stream)))
 
     def _host_call(self, fn, inp, reward, done, flags):
         N = self.num_envs

@@ -835,6 +835,41 @@ extern "C" int gcb_env_step_index_host(gcb_env* env, const uint32_t* u32, int32_
     return step_host_common(env, MODE_INDEX, u32, reward, done, flags);
 }
 
+// Asynchronous host-buffer steps: page-locked buffers only (their device aliases are read / written in place by the step
+// kernel); the launch is enqueued on `stream` and the call returns.  Two or more env objects (shards of one device) can
+// be kept in flight this way: the device steps one while the host consumes the other's results and writes its actions.
+static int step_host_async(gcb_env* env, int mode, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, void* stream) {
+    void* m_in = mapped_ptr(in);
+    void* m_r = mapped_ptr(reward);
+    void* m_d = mapped_ptr(done);
+    void* m_f = mapped_ptr(flags);
+    if (!m_in || (reward && !m_r) || (done && !m_d) || (flags && !m_f))
+        return fail(GCB_E_ARG, "gcb_env_step_*_host_async", "buffers must be page-locked (cudaHostAlloc / cudaHostRegister / pin_memory)");
+    return mode == MODE_ACTION
+               ? launch_step<MODE_ACTION>(env, m_in, (int32_t*)m_r, (uint8_t*)m_d, (uint8_t*)m_f, nullptr, nullptr, 1, (cudaStream_t)stream)
+               : launch_step<MODE_INDEX>(env, m_in, (int32_t*)m_r, (uint8_t*)m_d, (uint8_t*)m_f, nullptr, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gcb_env_step_host_async(gcb_env* env, const int32_t* actions, int32_t* reward, uint8_t* done, uint8_t* flags,
+                                       void* stream) {
+    ENV_CHECK(env);
+    if (!actions) return fail(GCB_E_ARG, "gcb_env_step_host_async", "null actions");
+    return step_host_async(env, MODE_ACTION, actions, reward, done, flags, stream);
+}
+
+extern "C" int gcb_env_step_index_host_async(gcb_env* env, const uint32_t* u32, int32_t* reward, uint8_t* done, uint8_t* flags,
+                                             void* stream) {
+    ENV_CHECK(env);
+    if (!u32) return fail(GCB_E_ARG, "gcb_env_step_index_host_async", "null random words");
+    return step_host_async(env, MODE_INDEX, u32, reward, done, flags, stream);
+}
+
+extern "C" int gcb_env_wait(gcb_env* env, void* stream) {
+    ENV_CHECK(env);
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return GCB_OK;
+}
+
 extern "C" int gcb_env_import(gcb_env* env, const int8_t* d_boards, const int8_t* d_players, const uint8_t* d_rights4,
                               const int32_t* d_move_count, const uint8_t* d_mask, void* stream) {
     ENV_CHECK(env);

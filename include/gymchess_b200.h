@@ -169,6 +169,18 @@ int gcb_env_step_sampled(gcb_env *env, int nsteps, int32_t *d_reward, uint8_t *d
 int gcb_env_step_host(gcb_env *env, const int32_t *actions, int32_t *reward, uint8_t *done, uint8_t *flags);
 int gcb_env_step_index_host(gcb_env *env, const uint32_t *u32, int32_t *reward, uint8_t *done, uint8_t *flags);
 
+/* Asynchronous HOST-buffer forms: page-locked buffers ONLY (GCB_E_ARG otherwise -- nothing is staged); the step is
+ * enqueued on `stream` and the call returns; the outputs are valid once gcb_env_wait(env, stream) (or any other
+ * synchronisation of that stream) has returned, and the input buffer may be rewritten from then on.  This is how a caller
+ * keeps two or more env objects (shards of one device, gcb_env_config.env_id_offset) in flight: the device steps one
+ * shard while the host consumes the other's results and prepares its actions, so the launch / completion latency of a
+ * synchronous step() call is hidden. */
+int gcb_env_step_host_async(gcb_env *env, const int32_t *actions, int32_t *reward, uint8_t *done, uint8_t *flags,
+                            void *stream);
+int gcb_env_step_index_host_async(gcb_env *env, const uint32_t *u32, int32_t *reward, uint8_t *done, uint8_t *flags,
+                                  void *stream);
+int gcb_env_wait(gcb_env *env, void *stream);
+
 /* observation / state export (device pointers, any may be NULL):
  *   d_boards int8[N][64]   -- `state["board"]`, the Box(-6,6,(8,8)) observation
  *   d_info   int32[N][16]  -- current_player(+1/-1), wk, wq, bk, bq, wchk, bchk, done, move_count, n_legal,

@@ -319,6 +319,47 @@ def test_host_step_paths_agree():
     assert s[0] == s[1] == s[2] and s[0]["episodes"] > 0
 
 
+def test_async_host_steps_of_two_shards_in_flight():
+    """gcb_env_step_index_host_async / gcb_env_wait: two shards of one device stepped alternately on two streams
+    (one in flight while the host handles the other) == the same envs stepped synchronously as one set; pageable
+    buffers are refused (nothing is staged behind the caller's back)"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv
+    from gym_chess_b200._lib import GcbError
+
+    H, T = 33000, 80
+    whole = BatchedChessEnv(2 * H, opponent="random", seed=17)
+    shards = [BatchedChessEnv(H, opponent="random", seed=17, env_id_offset=k * H) for k in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    rng = np.random.RandomState(5)
+    words = rng.randint(0, 2 ** 32, size=(T, 2 * H), dtype=np.uint64).astype(np.uint32)
+    pin = lambda dt: torch.empty(H, dtype=dt).pin_memory()
+    bufs = [(pin(torch.int32), pin(torch.int32), pin(torch.uint8), pin(torch.uint8)) for _ in range(2)]
+    with pytest.raises(GcbError):
+        shards[0].step_index_host_async(words[0, :H].copy(), bufs[0][1], bufs[0][2], bufs[0][3], stream=streams[0])
+    torch.cuda.synchronize()
+
+    def launch(k, t):
+        w, r, d, f = bufs[k]
+        w.numpy().view(np.uint32)[:] = words[t, k * H:(k + 1) * H]
+        shards[k].step_index_host_async(w, r, d, f, stream=streams[k])
+
+    launch(0, 0)
+    for t in range(T):
+        launch(1, t)                      # shard 1 goes in flight ...
+        r, d, f = whole.step_index(torch.from_numpy(words[t].view(np.int32)).cuda())
+        r, d, f = r.cpu().numpy(), d.cpu().numpy(), f.cpu().numpy()
+        for k in range(2):                # ... while shard 0's results are consumed and its next step is issued
+            shards[k].wait(stream=streams[k])
+            _, pr, pd, pf = bufs[k]
+            sl = slice(k * H, (k + 1) * H)
+            assert (r[sl] == pr.numpy()).all() and (d[sl] == pd.numpy()).all() and (f[sl] == pf.numpy()).all(), (t, k)
+            if k == 0 and t + 1 < T:
+                launch(0, t + 1)
+    sw, sa, sb = whole.stats(), shards[0].stats(), shards[1].stats()
+    assert all(sw[k] == sa[k] + sb[k] for k in sw) and sw["episodes"] > 0
+
+
 def test_endgames_with_long_repetition_windows():
     """BASELINE.json configs[4]: repetition/promotion-heavy endgames with a 512-ply Zobrist history.  Parity against the
     oracle at a size it replays in seconds; at 1M envs the size-independent properties."""
