@@ -18,6 +18,10 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
+#ifndef GCB_PAIR
+#define GCB_PAIR 0
+#endif
+
 // The rules are plain integer code; they are marked __host__ __device__ so that tests/host_emul can
 // compile the SAME source with g++ and check the logic against the oracle on a box without a GPU.
 // The product never runs them on the host (gym_chess_b200 has no CPU path).
@@ -369,8 +373,23 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     // opponent attack map (lib.rs:669-677): pawns minus squares holding the attacker's OWN king (Q14)
     u64 eatt = pawn_set_att(bb_pawns(b) & enemy, !white_to_move) & ~ekings;
     eatt |= knight_set_att(bb_knights(b) & enemy) | king_set_att(ekings);
+#if GCB_PAIR
+    // two sliders per trip: the warp runs max-over-lanes trips anyway (2 with both rooks somewhere in the warp), and the
+    // four independent line evaluations of a pair overlap in the pipeline
+    for (u64 s = eRQ; s;) {
+        const int sq1 = gcb_take(s), sq2 = s ? gcb_msb(s) : sq1;
+        s &= ~(1ULL << sq2);
+        eatt |= rook_att(sq1, occ) | rook_att(sq2, occ);
+    }
+    for (u64 s = eBQ; s;) {
+        const int sq1 = gcb_take(s), sq2 = s ? gcb_msb(s) : sq1;
+        s &= ~(1ULL << sq2);
+        eatt |= bishop_att(sq1, occ) | bishop_att(sq2, occ);
+    }
+#else
     for (u64 s = eRQ; s;) eatt |= rook_att(gcb_take(s), occ);
     for (u64 s = eBQ; s;) eatt |= bishop_att(gcb_take(s), occ);
+#endif
     g.eatt = eatt;
 
     g.satt = 0, g.cm = ~0ULL, g.pinned = 0, g.pinrays = 0, g.ksq = 0, g.in_check = false;
@@ -420,6 +439,34 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         const u64 t__ = (T_);                                          \
         sink.put(gcb_popc(mine & ((bit_) - 1)), t__);                  \
     } while (0)
+#if GCB_PAIR
+    // two pieces of a kind per trip (see gen_prepare): same warp-level work as two trips, twice the independent chains
+#define GCB_PAIRWISE(SET_, ATT_, TGT_)                                  \
+    for (u64 s = (SET_); s;) {                                          \
+        const int sq1 = gcb_take(s);                                    \
+        const bool two = s != 0;                                        \
+        const int sq2 = two ? gcb_msb(s) : sq1;                         \
+        s &= ~(1ULL << sq2);                                            \
+        const u64 a1 = ATT_(sq1), a2 = ATT_(sq2);                       \
+        g.satt |= a1 | a2;                                              \
+        GCB_PUT(sq1, 1ULL << sq1, TGT_(sq1, a1));                       \
+        if (two) GCB_PUT(sq2, 1ULL << sq2, TGT_(sq2, a2));              \
+    }
+#define GCB_ATT_R(sq_) rook_att(sq_, occ)
+#define GCB_ATT_B(sq_) bishop_att(sq_, occ)
+#define GCB_ATT_Q(sq_) (rook_att(sq_, occ) | bishop_att(sq_, occ))
+#define GCB_ATT_N(sq_) GCB_GEOM(knight[sq_])
+#define GCB_TGT_STD(sq_, a_) ((a_) & notown & g.cm)
+    GCB_PAIRWISE(bb_rooks(b) & mine, GCB_ATT_R, GCB_TGT_STD)
+    GCB_PAIRWISE(bb_bishops(b) & mine, GCB_ATT_B, GCB_TGT_STD)
+    for (u64 s = bb_queens(b) & mine; s;) {
+        const int sq = gcb_take(s);
+        const u64 bit = 1ULL << sq, a = rook_att(sq, occ) | bishop_att(sq, occ);
+        g.satt |= a;
+        GCB_PUT(sq, bit, a & notown & g.cm);
+    }
+    GCB_PAIRWISE(bb_knights(b) & mine, GCB_ATT_N, GCB_TGT_STD)
+#else
     // rooks
     for (u64 s = bb_rooks(b) & mine; s;) {
         const int sq = gcb_take(s);
@@ -448,6 +495,7 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
+#endif
     // kings: never passed through the legality filter (lib.rs:615-619); attack map with the king on it (Q6)
     for (u64 s = bb_kings(b) & mine; s;) {
         const int sq = gcb_take(s);
@@ -461,14 +509,35 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         const u64 pw = bb_pawns(b) & mine, allp = bb_pawns(b) & own;
         g.satt |= pawn_set_att(pw, g.white) & ~(bb_kings(b) & own);  // Q14
         (void)allp;
+#if GCB_PAIR
+        for (u64 s = pw; s;) {
+            const int sq1 = gcb_take(s);
+            const bool two = s != 0;
+            const int sq2 = two ? gcb_msb(s) : sq1;
+            s &= ~(1ULL << sq2);
+            const u64 push1 = GCB_GEOM(pawn[!g.white][sq1][0]), cap1 = GCB_GEOM(pawn[!g.white][sq1][1]);
+            const u64 push2 = GCB_GEOM(pawn[!g.white][sq2][0]), cap2 = GCB_GEOM(pawn[!g.white][sq2][1]);
+            GCB_PUT(sq1, 1ULL << sq1, ((push1 & ~occ) | (cap1 & g.enemy)) & g.cm);
+            if (two) GCB_PUT(sq2, 1ULL << sq2, ((push2 & ~occ) | (cap2 & g.enemy)) & g.cm);
+        }
+#else
         for (u64 s = pw; s;) {
             const int sq = gcb_take(s);
             const u64 bit = 1ULL << sq;
             const u64 push = GCB_GEOM(pawn[!g.white][sq][0]), cap = GCB_GEOM(pawn[!g.white][sq][1]);
             GCB_PUT(sq, bit, ((push & ~occ) | (cap & g.enemy)) & g.cm);
         }
+#endif
     }
 #undef GCB_PUT
+#if GCB_PAIR
+#undef GCB_PAIRWISE
+#undef GCB_ATT_R
+#undef GCB_ATT_B
+#undef GCB_ATT_Q
+#undef GCB_ATT_N
+#undef GCB_TGT_STD
+#endif
     // pinned pieces (rare per position, but some env of a warp nearly always has one): one fix-up pass over the
     // slots instead of a pin test at every generation site
     for (u64 p = g.pinned & mine & ~bb_kings(b); p;) {

@@ -50,6 +50,9 @@ extern "C" int gcb_device_count(void) {
 #ifndef GCB_STEP_MIN_BLOCKS
 #define GCB_STEP_MIN_BLOCKS 5
 #endif
+#ifndef GCB_SAMPLED_MIN_BLOCKS
+#define GCB_SAMPLED_MIN_BLOCKS 5
+#endif
 static inline int grid_for(int n) { return (n + GCB_BLOCK - 1) / GCB_BLOCK; }
 
 // ------------------------------------------------------------------------------------------------ pack / unpack
@@ -188,10 +191,12 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions
     if (checks) checks[i] = (uint8_t)check_flags(b);
 }
 
-template <int MODE>
+// TILE (multi-step sampled launches with the default 16 piece slots): the slots live in a shared-memory tile for the whole
+// launch; a compile-time property so that slot accesses are plain LDS / STS with constant strides.
+template <int MODE, bool TILE = false>
 // measured on B200: the multi-step sampled kernel is fastest with 4 resident blocks per SM (128 registers; more warps
 // thrash the instruction cache), the single-step kernels with 5 (96 registers)
-__global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_STEP_MIN_BLOCKS - 1 : GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
+__global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_MIN_BLOCKS : GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
     __shared__ CountBytes s_counts[GCB_BLOCK];
     const int e = io.e_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -209,17 +214,17 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_STEP_MIN
     if (active) env_load(v, e, s, ep);
     // ... and its piece slots in a shared-memory tile (multi-step launches with the default 16 slots): the generation
     // writes them and the next step's draw reads one of them without a round trip through L2
-    __shared__ u64 s_slots[MODE == MODE_SAMPLED ? GCB_SLOTS * GCB_BLOCK : 1];
-    const bool tile = MODE == MODE_SAMPLED && nsteps >= 4 && v.slots <= GCB_SLOTS;
-    SlotRef sr = resident_slots(v, e < io.e_end ? e : io.e_begin);
-    if (tile) {
+    __shared__ u64 s_slots[TILE ? GCB_SLOTS * GCB_BLOCK : 1];
+    const bool tile = TILE;
+    const SlotRef gsr = resident_slots(v, e < io.e_end ? e : io.e_begin);
+    const SlotRef tsr = {s_slots + threadIdx.x, (unsigned)GCB_BLOCK, GCB_SLOTS, true};
+    if (TILE) {
         if (active) {
             const int np = gcb_popc(stm_pieces(s));
-            for (int r = 0; r < np && r < v.slots; r++) s_slots[r * GCB_BLOCK + threadIdx.x] = __ldcs(sr.base + (unsigned)r * sr.stride);
+            for (int r = 0; r < np && r < GCB_SLOTS; r++) s_slots[r * GCB_BLOCK + threadIdx.x] = __ldcs(gsr.base + (unsigned)r * gsr.stride);
         }
-        SlotRef t = {s_slots + threadIdx.x, (unsigned)GCB_BLOCK, v.slots, true};
-        sr = t;
     }
+    const SlotRef sr = TILE ? tsr : gsr;
 #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
         StepStats st;
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_STEP_MIN
         env_store(v, e, s, ep);
         if (tile) {  // slots of the side to move back to their resident place
             const int np = gcb_popc(stm_pieces(s));
-            for (int r = 0; r < np && r < v.slots; r++) __stcs(v.tgt + (size_t)r * v.N + e, s_slots[r * GCB_BLOCK + threadIdx.x]);
+            for (int r = 0; r < np && r < GCB_SLOTS; r++) __stcs(v.tgt + (size_t)r * v.N + e, s_slots[r * GCB_BLOCK + threadIdx.x]);
         }
     }
     // one coalesced read-modify-write of the warp's own row -- no atomics and no block barrier
@@ -744,7 +749,10 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
         io.in = nullptr, io.reward = d_reward, io.done = d_done, io.flags = d_flags;
         io.act_out = d_actions_out ? d_actions_out + t * N : nullptr, io.bot_out = d_bot_out ? d_bot_out + t * N : nullptr;
         io.tick = env->tick, io.ep_inc = 1, io.e_begin = 0, io.e_end = env->v.N, io.nsteps = k;
-        k_env_step<MODE_SAMPLED><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
+        if (k >= 4 && env->v.slots == GCB_SLOTS)
+            k_env_step<MODE_SAMPLED, true><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
+        else
+            k_env_step<MODE_SAMPLED, false><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
         LAUNCHED();
         env->tick += (u64)k;
         t += k;

@@ -18,7 +18,8 @@ _lib = None
 def build(force=False):
     srcs = [os.path.join(_HERE, "host_emul.cpp"), os.path.join(_CSRC, "chess_core.cuh"), os.path.join(_CSRC, "env_core.cuh")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
+        extra = os.environ.get("GCB_EMUL_CFLAGS", "").split()  # e.g. -DGCB_PAIR=1: check a kernel variant's logic on the CPU
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas"] + extra + ["-o", _SO, srcs[0]])
     return _SO
 
 
