@@ -18,10 +18,6 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-#ifndef GCB_PAIR
-#define GCB_PAIR 0
-#endif
-
 // The rules are plain integer code; they are marked __host__ __device__ so that tests/host_emul can
 // compile the SAME source with g++ and check the logic against the oracle on a box without a GPU.
 // The product never runs them on the host (gym_chess_b200 has no CPU path).
@@ -220,6 +216,32 @@ static const GeomTables g_geom_host = GeomTables();
 #else
 #define GCB_GEOM(field) (g_geom_host.field)
 #endif
+// Where the SMALL hot tables (line masks, knight / king sets, pawn spans: 5 KB) are read from.  GeomGlobal: the
+// L1-resident device-memory copy.  GeomShared (device only): a copy the multi-step kernel keeps in shared memory for the
+// whole launch -- LDS with 32-bit addresses instead of LDG with 64-bit address arithmetic on the integer pipe.
+struct GeomGlobal {
+    GCB_HD u64 line(int sq, int k) const { return GCB_GEOM(line[sq][k]); }
+    GCB_HD u64 knight(int sq) const { return GCB_GEOM(knight[sq]); }
+    GCB_HD u64 king(int sq) const { return GCB_GEOM(king[sq]); }
+    GCB_HD u64 pawn(int black, int sq, int k) const { return GCB_GEOM(pawn[black][sq][k]); }
+};
+#define GCB_SGEOM_WORDS (64 * 4 + 64 + 64 + 2 * 64 * 2)
+#if defined(__CUDACC__)
+struct GeomShared {
+    const u64* p;  // line[64][4] | knight[64] | king[64] | pawn[2][64][2]
+    __device__ __forceinline__ u64 line(int sq, int k) const { return p[sq * 4 + k]; }
+    __device__ __forceinline__ u64 knight(int sq) const { return p[256 + sq]; }
+    __device__ __forceinline__ u64 king(int sq) const { return p[320 + sq]; }
+    __device__ __forceinline__ u64 pawn(int black, int sq, int k) const { return p[384 + black * 128 + sq * 2 + k]; }
+    // word i of the shared copy, from the device-memory tables (the kernel's threads fill the copy cooperatively)
+    static __device__ __forceinline__ u64 source_word(int i) {
+        if (i < 256) return __ldg(&g_geom_dev.line[0][0] + i);
+        if (i < 320) return __ldg(&g_geom_dev.knight[0] + (i - 256));
+        if (i < 384) return __ldg(&g_geom_dev.king[0] + (i - 320));
+        return __ldg(&g_geom_dev.pawn[0][0][0] + (i - 384));
+    }
+};
+#endif
 #define GCB_RAY_DESC_MASK 0x35u  // entries 0,2,4,5: nearest square first = highest bit first
 GCB_HD int order_class(int code, int white) {
     return code == PC_KING ? 1 : code == PC_KNIGHT ? 2 : code == PC_PAWN ? (white ? 3 : 4) : 0;
@@ -247,14 +269,18 @@ GCB_HD u64 hq_line(u64 occ, u64 maskEx, u64 bit, u64 rbit) {
     u64 r = gcb_brev64(gcb_brev64(o) - rbit);
     return (f ^ r) & maskEx;
 }
-GCB_HD u64 rook_att(int sq, u64 occ) {
+template <class G>
+GCB_HD u64 rook_att(const G& geo, int sq, u64 occ) {
     u64 bit = 1ULL << sq, rbit = 1ULL << (63 - sq);
-    return hq_line(occ, GCB_GEOM(line[sq][0]), bit, rbit) | hq_line(occ, GCB_GEOM(line[sq][1]), bit, rbit);
+    return hq_line(occ, geo.line(sq, 0), bit, rbit) | hq_line(occ, geo.line(sq, 1), bit, rbit);
 }
-GCB_HD u64 bishop_att(int sq, u64 occ) {
+template <class G>
+GCB_HD u64 bishop_att(const G& geo, int sq, u64 occ) {
     u64 bit = 1ULL << sq, rbit = 1ULL << (63 - sq);
-    return hq_line(occ, GCB_GEOM(line[sq][2]), bit, rbit) | hq_line(occ, GCB_GEOM(line[sq][3]), bit, rbit);
+    return hq_line(occ, geo.line(sq, 2), bit, rbit) | hq_line(occ, geo.line(sq, 3), bit, rbit);
 }
+GCB_HD u64 rook_att(int sq, u64 occ) { return rook_att(GeomGlobal(), sq, occ); }
+GCB_HD u64 bishop_att(int sq, u64 occ) { return bishop_att(GeomGlobal(), sq, occ); }
 
 // ---- set-wise leaper attacks (all pieces of the set at once)
 GCB_HD u64 knight_set_att(u64 n) {
@@ -361,7 +387,8 @@ struct GenCtx {
     int white;
 };
 
-GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
+template <class G>
+GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g, const G& geo) {
     g.white = white_to_move;
     g.occ = bb_occ(b);
     g.own = white_to_move ? b.w : (g.occ & ~b.w);
@@ -373,23 +400,8 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     // opponent attack map (lib.rs:669-677): pawns minus squares holding the attacker's OWN king (Q14)
     u64 eatt = pawn_set_att(bb_pawns(b) & enemy, !white_to_move) & ~ekings;
     eatt |= knight_set_att(bb_knights(b) & enemy) | king_set_att(ekings);
-#if GCB_PAIR
-    // two sliders per trip: the warp runs max-over-lanes trips anyway (2 with both rooks somewhere in the warp), and the
-    // four independent line evaluations of a pair overlap in the pipeline
-    for (u64 s = eRQ; s;) {
-        const int sq1 = gcb_take(s), sq2 = s ? gcb_msb(s) : sq1;
-        s &= ~(1ULL << sq2);
-        eatt |= rook_att(sq1, occ) | rook_att(sq2, occ);
-    }
-    for (u64 s = eBQ; s;) {
-        const int sq1 = gcb_take(s), sq2 = s ? gcb_msb(s) : sq1;
-        s &= ~(1ULL << sq2);
-        eatt |= bishop_att(sq1, occ) | bishop_att(sq2, occ);
-    }
-#else
-    for (u64 s = eRQ; s;) eatt |= rook_att(gcb_take(s), occ);
-    for (u64 s = eBQ; s;) eatt |= bishop_att(gcb_take(s), occ);
-#endif
+    for (u64 s = eRQ; s;) eatt |= rook_att(geo, gcb_take(s), occ);
+    for (u64 s = eBQ; s;) eatt |= bishop_att(geo, gcb_take(s), occ);
     g.eatt = eatt;
 
     g.satt = 0, g.cm = ~0ULL, g.pinned = 0, g.pinrays = 0, g.ksq = 0, g.in_check = false;
@@ -401,11 +413,11 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     g.ksq = ksq;
     // pieces that attack the king square right now (attack sets are symmetric; an enemy pawn attacks ksq iff it
     // stands where a pawn of the MOVER's colour on ksq would attack; enemy kings count, Q22)
-    u64 chk = (GCB_GEOM(knight[ksq]) & bb_knights(b) & enemy) | (GCB_GEOM(king[ksq]) & ekings) |
-              (GCB_GEOM(pawn[!white_to_move][ksq][1]) & bb_pawns(b) & enemy);
+    u64 chk = (geo.knight(ksq) & bb_knights(b) & enemy) | (geo.king(ksq) & ekings) |
+              (geo.pawn(!white_to_move, ksq, 1) & bb_pawns(b) & enemy);
     // enemy sliders on a line through the king square that they move along: nothing in between -> checker; exactly
     // one piece in between and it is ours -> that piece is pinned to the ray (between | pinner)
-    const u64 cand = (eRQ & (GCB_GEOM(line[ksq][0]) | GCB_GEOM(line[ksq][1]))) | (eBQ & (GCB_GEOM(line[ksq][2]) | GCB_GEOM(line[ksq][3])));
+    const u64 cand = (eRQ & (geo.line(ksq, 0) | geo.line(ksq, 1))) | (eBQ & (geo.line(ksq, 2) | geo.line(ksq, 3)));
     for (u64 p = cand; p;) {
         const int psq = gcb_take(p);
         const u64 btw = GCB_GEOM(between[ksq][psq]), blockers = btw & occ;
@@ -420,6 +432,8 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) {
     (void)kbit;
 }
 
+GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g) { gen_prepare(b, white_to_move, g, GeomGlobal()); }
+
 // the squares a pinned piece on `sq` may move to: its own pin ray (between(king, pinner) | pinner)
 GCB_HD u64 pin_mask(const GenCtx& g, int sq) {
     const u64 kbit = 1ULL << g.ksq;
@@ -430,8 +444,8 @@ GCB_HD u64 pin_mask(const GenCtx& g, int sq) {
 // Targets of every own piece in `subset` (a set of squares; the caller passes all own pieces, or a
 // chunk of them when there are more pieces than slots).  sink.put(rank, targets): rank = index of the
 // piece among the own pieces of `subset` in ascending square order.
-template <class Sink>
-GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
+template <class Sink, class G>
+GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink, const G& geo) {
     const u64 occ = g.occ, own = g.own, notown = ~g.own;
     const u64 mine = own & subset;
 #define GCB_PUT(sq_, bit_, T_)                                         \
@@ -439,67 +453,38 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         const u64 t__ = (T_);                                          \
         sink.put(gcb_popc(mine & ((bit_) - 1)), t__);                  \
     } while (0)
-#if GCB_PAIR
-    // two pieces of a kind per trip (see gen_prepare): same warp-level work as two trips, twice the independent chains
-#define GCB_PAIRWISE(SET_, ATT_, TGT_)                                  \
-    for (u64 s = (SET_); s;) {                                          \
-        const int sq1 = gcb_take(s);                                    \
-        const bool two = s != 0;                                        \
-        const int sq2 = two ? gcb_msb(s) : sq1;                         \
-        s &= ~(1ULL << sq2);                                            \
-        const u64 a1 = ATT_(sq1), a2 = ATT_(sq2);                       \
-        g.satt |= a1 | a2;                                              \
-        GCB_PUT(sq1, 1ULL << sq1, TGT_(sq1, a1));                       \
-        if (two) GCB_PUT(sq2, 1ULL << sq2, TGT_(sq2, a2));              \
-    }
-#define GCB_ATT_R(sq_) rook_att(sq_, occ)
-#define GCB_ATT_B(sq_) bishop_att(sq_, occ)
-#define GCB_ATT_Q(sq_) (rook_att(sq_, occ) | bishop_att(sq_, occ))
-#define GCB_ATT_N(sq_) GCB_GEOM(knight[sq_])
-#define GCB_TGT_STD(sq_, a_) ((a_) & notown & g.cm)
-    GCB_PAIRWISE(bb_rooks(b) & mine, GCB_ATT_R, GCB_TGT_STD)
-    GCB_PAIRWISE(bb_bishops(b) & mine, GCB_ATT_B, GCB_TGT_STD)
-    for (u64 s = bb_queens(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = rook_att(sq, occ) | bishop_att(sq, occ);
-        g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & g.cm);
-    }
-    GCB_PAIRWISE(bb_knights(b) & mine, GCB_ATT_N, GCB_TGT_STD)
-#else
     // rooks
     for (u64 s = bb_rooks(b) & mine; s;) {
         const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = rook_att(sq, occ);
+        const u64 bit = 1ULL << sq, a = rook_att(geo, sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // bishops
     for (u64 s = bb_bishops(b) & mine; s;) {
         const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = bishop_att(sq, occ);
+        const u64 bit = 1ULL << sq, a = bishop_att(geo, sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // queens
     for (u64 s = bb_queens(b) & mine; s;) {
         const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = rook_att(sq, occ) | bishop_att(sq, occ);
+        const u64 bit = 1ULL << sq, a = rook_att(geo, sq, occ) | bishop_att(geo, sq, occ);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
     // knights
     for (u64 s = bb_knights(b) & mine; s;) {
         const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = GCB_GEOM(knight[sq]);
+        const u64 bit = 1ULL << sq, a = geo.knight(sq);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & g.cm);
     }
-#endif
     // kings: never passed through the legality filter (lib.rs:615-619); attack map with the king on it (Q6)
     for (u64 s = bb_kings(b) & mine; s;) {
         const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = GCB_GEOM(king[sq]);
+        const u64 bit = 1ULL << sq, a = geo.king(sq);
         g.satt |= a;
         GCB_PUT(sq, bit, a & notown & ~g.eatt);
     }
@@ -509,35 +494,14 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         const u64 pw = bb_pawns(b) & mine, allp = bb_pawns(b) & own;
         g.satt |= pawn_set_att(pw, g.white) & ~(bb_kings(b) & own);  // Q14
         (void)allp;
-#if GCB_PAIR
-        for (u64 s = pw; s;) {
-            const int sq1 = gcb_take(s);
-            const bool two = s != 0;
-            const int sq2 = two ? gcb_msb(s) : sq1;
-            s &= ~(1ULL << sq2);
-            const u64 push1 = GCB_GEOM(pawn[!g.white][sq1][0]), cap1 = GCB_GEOM(pawn[!g.white][sq1][1]);
-            const u64 push2 = GCB_GEOM(pawn[!g.white][sq2][0]), cap2 = GCB_GEOM(pawn[!g.white][sq2][1]);
-            GCB_PUT(sq1, 1ULL << sq1, ((push1 & ~occ) | (cap1 & g.enemy)) & g.cm);
-            if (two) GCB_PUT(sq2, 1ULL << sq2, ((push2 & ~occ) | (cap2 & g.enemy)) & g.cm);
-        }
-#else
         for (u64 s = pw; s;) {
             const int sq = gcb_take(s);
             const u64 bit = 1ULL << sq;
-            const u64 push = GCB_GEOM(pawn[!g.white][sq][0]), cap = GCB_GEOM(pawn[!g.white][sq][1]);
+            const u64 push = geo.pawn(!g.white, sq, 0), cap = geo.pawn(!g.white, sq, 1);
             GCB_PUT(sq, bit, ((push & ~occ) | (cap & g.enemy)) & g.cm);
         }
-#endif
     }
 #undef GCB_PUT
-#if GCB_PAIR
-#undef GCB_PAIRWISE
-#undef GCB_ATT_R
-#undef GCB_ATT_B
-#undef GCB_ATT_Q
-#undef GCB_ATT_N
-#undef GCB_TGT_STD
-#endif
     // pinned pieces (rare per position, but some env of a warp nearly always has one): one fix-up pass over the
     // slots instead of a pin test at every generation site
     for (u64 p = g.pinned & mine & ~bb_kings(b); p;) {
@@ -545,6 +509,11 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
         const u64 t = sink.get(r), t2 = t & pin_mask(g, sq);
         sink.replace(r, t, t2);
     }
+}
+
+template <class Sink>
+GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink) {
+    gen_targets(b, g, subset, sink, GeomGlobal());
 }
 
 // castles, lib.rs:578-610 + 966-1056: needs the mover's king on the board and K-right OR Q-right (Q4).

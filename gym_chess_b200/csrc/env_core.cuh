@@ -339,8 +339,9 @@ __device__ __forceinline__ int coop_ring_count(const EnvView& v, bool need, int 
 // board) + the state setter (315-323) + switch_player (296-299) + get_possible_moves for the new
 // side to move (573-582).  apply=false only switches the side and regenerates (BLACK-agent reset
 // when White has no move).  Returns the ply reward.
+template <class G>
 GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int slot, int action, bool apply, bool* rep,
-                           StepStats& st, CountBytes* scratch, const SlotRef& sr) {
+                           StepStats& st, CountBytes* scratch, const SlotRef& sr, const G& geo) {
     int r = 0;
     *rep = false;
     if (apply) {
@@ -389,9 +390,9 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, 
     }
     s.stm_black ^= 1;
     GenCtx g;
-    gen_prepare(s.b, !s.stm_black, g);
+    gen_prepare(s.b, !s.stm_black, g, geo);
     TgtSink sink(sr, scratch);
-    gen_targets(s.b, g, g.own, sink);
+    gen_targets(s.b, g, g.own, sink, geo);
     const int n = sink.total();
     if (sink.dropped) st.f += SF_SLOTOVF;
     s.cnt_lo = sink.count_lo(), s.cnt_hi = sink.count_hi();
@@ -442,9 +443,9 @@ GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
 }
 
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step), state in registers
-template <int MODE>
+template <int MODE, class G>
 GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch,
-                          const SlotRef& sr) {
+                          const SlotRef& sr, const G& geo) {
     const u32 genv = v.env_offset + (u32)e;
     HistCursor hc;
     hc.base = io.tick * (u64)v.pps, hc.cursor = 0;
@@ -551,7 +552,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             continue;
         }
         bool rep;
-        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st, scratch, sr);
+        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st, scratch, sr, geo);
         if (do_apply) st.f += SF_PLIES;
         const bool mate = s.n_legal == 0 && stm_checked(s);
         if (phase == PH_AGENT) {
@@ -594,7 +595,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     EnvRegs s;
     u32 ep;
     env_load(v, e, s, ep);
-    env_step_regs<MODE>(v, io, e, s, ep, st, scratch, resident_slots(v, e));
+    env_step_regs<MODE>(v, io, e, s, ep, st, scratch, resident_slots(v, e), GeomGlobal());
     env_store(v, e, s, ep);
 }
 
@@ -614,7 +615,7 @@ GCB_HD void env_import_one(const EnvView& v, int e, const int8_t* board, int pla
     HistCursor hc;
     hc.base = tick * (u64)v.pps, hc.cursor = 0;
     bool rep;
-    ply_and_movegen(v, e, s, hc, 0, 0, false, &rep, st, scratch, resident_slots(v, e));
+    ply_and_movegen(v, e, s, hc, 0, 0, false, &rep, st, scratch, resident_slots(v, e), GeomGlobal());
     env_store(v, e, s, ep + 1u);
 }
 

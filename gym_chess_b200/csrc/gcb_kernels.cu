@@ -225,11 +225,21 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_
         }
     }
     const SlotRef sr = TILE ? tsr : gsr;
+    // ... and the small geometry tables (5 KB) next to it
+    __shared__ u64 s_geom[TILE ? GCB_SGEOM_WORDS : 1];
+    if (TILE) {
+        for (int i = threadIdx.x; i < GCB_SGEOM_WORDS; i += GCB_BLOCK) s_geom[i] = GeomShared::source_word(i);
+        __syncthreads();
+    }
+    const GeomShared sgeo = {s_geom};
 #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
         StepStats st;
         st.clear();
-        if (active) env_step_regs<MODE>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr);
+        if (active) {
+            if (TILE) env_step_regs<MODE>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, sgeo);
+            else env_step_regs<MODE>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, GeomGlobal());
+        }
         if (MODE != MODE_RESET) {
             // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The bit-field counters are widened into
             // three words whose fields cannot overflow over 32 lanes: 7 REDUX in all instead of one per counter
