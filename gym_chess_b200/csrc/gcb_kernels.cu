@@ -573,6 +573,7 @@ struct gcb_env {
     int32_t *d_in = nullptr, *d_reward = nullptr;
     uint8_t *d_done = nullptr, *d_flags = nullptr;
     cudaStream_t streams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t events[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static const int8_t kDefaultBoard[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6, -6, -6, -6, -6, -6, -6, 0, 0, 0, 0, 0, 0,
@@ -607,6 +608,8 @@ extern "C" int gcb_env_destroy(gcb_env* env) {
     cudaFree(env->d_in), cudaFree(env->d_reward), cudaFree(env->d_done), cudaFree(env->d_flags);
     for (int c = 0; c < 8; c++)
         if (env->streams[c]) cudaStreamDestroy(env->streams[c]);
+    for (int c = 0; c < 9; c++)
+        if (env->events[c]) cudaEventDestroy(env->events[c]);
     delete env;
     return GCB_OK;
 }
@@ -748,24 +751,63 @@ extern "C" int gcb_env_step_index(gcb_env* env, const uint32_t* d_u32, int32_t* 
 }
 
 #define GCB_MAX_STEPS_PER_LAUNCH 64
+#define GCB_HOST_CHUNKS 8
+static int ensure_streams(gcb_env* env) {
+    if (!env->streams[0]) {
+        for (int c = 0; c < GCB_HOST_CHUNKS; c++) CU(cudaStreamCreateWithFlags(&env->streams[c], cudaStreamNonBlocking));
+        for (int c = 0; c <= GCB_HOST_CHUNKS; c++) CU(cudaEventCreateWithFlags(&env->events[c], cudaEventDisableTiming));
+    }
+    return GCB_OK;
+}
+
 extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward, uint8_t* d_done, uint8_t* d_flags,
                                     int32_t* d_actions_out, int32_t* d_bot_out, void* stream) {
     ENV_CHECK(env);
     if (nsteps < 0) return fail(GCB_E_ARG, "gcb_env_step_sampled", "nsteps < 0");
     const size_t N = (size_t)env->v.N;
+    // A run of several launches is issued as a few env RANGES on their own streams (forked from / joined to the caller's
+    // stream): every launch ends with a partly filled last wave of blocks (524,288 envs = 5.5 waves of 740 resident
+    // blocks), and with independent ranges the next launch of one range fills the tail of the other.  Envs never read
+    // each other, so ranges need no ordering among themselves.
+    static int want = -1;
+    if (want < 0) {
+        const char* ev = getenv("GCB_SAMPLED_RANGES");
+        want = ev ? atoi(ev) : 2;
+        if (want < 1 || want > GCB_HOST_CHUNKS) want = 2;
+    }
+    const int nlaunch = (nsteps + GCB_MAX_STEPS_PER_LAUNCH - 1) / GCB_MAX_STEPS_PER_LAUNCH;
+    const int R = (nlaunch >= 2 && N >= (size_t)want * 65536) ? want : 1;
+    const int per = (int)((((N + R - 1) / R) + GCB_BLOCK - 1) / GCB_BLOCK * GCB_BLOCK);  // whole blocks (and whole stat rows)
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (R > 1) {
+        if (int rc = ensure_streams(env)) return rc;
+        CU(cudaEventRecord(env->events[GCB_HOST_CHUNKS], cs));
+        for (int r = 0; r < R; r++) CU(cudaStreamWaitEvent(env->streams[r], env->events[GCB_HOST_CHUNKS], 0));
+    }
     for (int t = 0; t < nsteps;) {
         const int k = nsteps - t < GCB_MAX_STEPS_PER_LAUNCH ? nsteps - t : GCB_MAX_STEPS_PER_LAUNCH;
         StepIO io;
         io.in = nullptr, io.reward = d_reward, io.done = d_done, io.flags = d_flags;
         io.act_out = d_actions_out ? d_actions_out + t * N : nullptr, io.bot_out = d_bot_out ? d_bot_out + t * N : nullptr;
-        io.tick = env->tick, io.ep_inc = 1, io.e_begin = 0, io.e_end = env->v.N, io.nsteps = k;
-        if (k >= 4 && env->v.slots == GCB_SLOTS)
-            k_env_step<MODE_SAMPLED, true><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
-        else
-            k_env_step<MODE_SAMPLED, false><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
-        LAUNCHED();
+        io.tick = env->tick, io.ep_inc = 1, io.nsteps = k;
+        for (int r = 0; r < R; r++) {
+            io.e_begin = r * per, io.e_end = (r + 1) * per < (int)N ? (r + 1) * per : (int)N;
+            if (io.e_begin >= io.e_end) break;
+            cudaStream_t ls = R > 1 ? env->streams[r] : cs;
+            if (k >= 4 && env->v.slots == GCB_SLOTS)
+                k_env_step<MODE_SAMPLED, true><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
+            else
+                k_env_step<MODE_SAMPLED, false><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
+            LAUNCHED();
+        }
         env->tick += (u64)k;
         t += k;
+    }
+    if (R > 1) {
+        for (int r = 0; r < R; r++) {
+            CU(cudaEventRecord(env->events[r], env->streams[r]));
+            CU(cudaStreamWaitEvent(cs, env->events[r], 0));
+        }
     }
     return GCB_OK;
 }
@@ -774,7 +816,6 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
 // kernel of chunk k and the D2H copies of chunk k-1 overlap (PCIe is full duplex).  Envs are independent, so a step may
 // be issued range by range; all chunks share the step's ring tick.  Pass page-locked host buffers to get the overlap
 // (pageable memory still works, the copies then serialise).
-#define GCB_HOST_CHUNKS 8
 // device-visible alias of a page-locked host buffer (NULL for pageable memory)
 static void* mapped_ptr(const void* host) {
     if (!host) return nullptr;
@@ -818,8 +859,7 @@ static int step_host_common(gcb_env* env, int mode, const void* in, int32_t* rew
     }
     int chunks = N >= want * 16384 ? want : (N >= 32768 ? 2 : 1);
     int per = (((N + chunks - 1) / chunks) + GCB_BLOCK - 1) / GCB_BLOCK * GCB_BLOCK;  // whole blocks (and whole stat rows)
-    if (!env->streams[0])
-        for (int c = 0; c < GCB_HOST_CHUNKS; c++) CU(cudaStreamCreateWithFlags(&env->streams[c], cudaStreamNonBlocking));
+    if (int rc = ensure_streams(env)) return rc;
     CU(cudaStreamSynchronize(0));  // earlier work of this env on the default stream
     const char* src = reinterpret_cast<const char*>(in);
     for (int c = 0; c < chunks; c++) {
