@@ -257,19 +257,46 @@ GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, in
     }
 }
 
+#ifndef GCB_SWAR_PICK
+#define GCB_SWAR_PICK 1
+#endif
+// per byte: 0x80 where x <= y (unsigned bytes), else 0
+GCB_HD u64 swar_le_u8(u64 x, u64 y) {
+    const u64 H = 0x8080808080808080ULL;
+    const u64 t = (y | H) - (x & ~H);  // per byte (y & 127) + 128 - (x & 127): no borrow between bytes, top bit = low 7 bits of x <= those of y
+    return ((~x & y) | (~(x ^ y) & t)) & H;
+}
+
 // The action `possible_moves[idx]` of the reference-ordered list, decoded from the slots (chess_v2.py:116-127:
 // the uniform draw indexes the ORDERED list).  idx < n_legal.
 GCB_HD int action_at(const SlotRef& sr, const EnvRegs& s, int idx) {
     // which piece: prefix scan over the 16 count bytes (registers only); pieces beyond 16 (only on crafted initial
     // boards) by reading their slots
     int acc = 0, hit_r = -1, hit_idx = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
+#if GCB_SWAR_PICK
+    if (s.n_legal <= 255) {
+        // all 16 prefix sums at once: byte k of (cnt * 0x0101..01) = c0 + ... + ck (no byte overflows: the total is <= 255);
+        // the piece is the number of inclusive prefix sums <= idx (they are non-decreasing); branch-free, no unrolled scan
+        const u64 K = 0x0101010101010101ULL;
+        const u64 p_lo = s.cnt_lo * K, p_hi = (s.cnt_hi + (p_lo >> 56)) * K;
+        const u64 I = (u64)(u32)idx * K;
+        const int r = gcb_popc(swar_le_u8(p_lo, I)) + gcb_popc(swar_le_u8(p_hi, I));
+        acc = (int)(p_hi >> 56);
+        if (r < 16) {
+            const u64 q = r < 8 ? (p_lo << 8) : ((p_hi << 8) | (p_lo >> 56));  // exclusive prefix sums
+            hit_r = r, hit_idx = idx - (int)((q >> (8 * (r & 7))) & 0xFF);
+        }
+    } else
 #endif
-    for (int r = 0; r < 16; r++) {
-        const int c = (int)(((r < 8 ? s.cnt_lo : s.cnt_hi) >> (8 * (r & 7))) & 0xFF);
-        if (hit_r < 0 && idx - acc < c) hit_r = r, hit_idx = idx - acc;
-        acc += c;
+    {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int r = 0; r < 16; r++) {
+            const int c = (int)(((r < 8 ? s.cnt_lo : s.cnt_hi) >> (8 * (r & 7))) & 0xFF);
+            if (hit_r < 0 && idx - acc < c) hit_r = r, hit_idx = idx - acc;
+            acc += c;
+        }
     }
     TgtSink slots(sr, nullptr);
     u64 own = stm_pieces(s);

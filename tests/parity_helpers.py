@@ -295,6 +295,16 @@ def check_trajectory_replay(make_env, traj):
     return len(traj["steps"])
 
 
+def queen_heavy_boards():
+    """initial boards on which White has more than 255 legal moves (found by hill climbing; 266 and 271 moves).  Sixteen
+    pieces cannot get there (best found: 243), so these have 24 and 28 white pieces -> more than 16 piece slots."""
+    a = [-1, 0, 2, 0, 2, 2, 2, -3, 2, 2, 0, 0, 0, 0, 0, 2, 0, 0, 0, 2, 0, 0, 0, 2, 2, 0, 0, 0, 0, 0, 0, 2, 2, 0, 0, 0, 0, 0, 0, 2,
+         1, 0, 2, 0, 0, 0, 0, 2, 2, 0, 0, 0, 0, 0, 0, 2, 0, 2, 2, 2, 2, 2, 2, 0]
+    b = [-1, 2, 2, 2, 2, 2, 2, -3, 2, 2, 0, 0, 0, 0, 0, 2, 2, 0, 0, 0, 0, 2, 0, 2, 2, 0, 0, 0, 0, 0, 0, 2, 2, 0, 0, 0, 0, 0, 0, 1,
+         2, 0, 0, 0, 0, 0, 0, 2, 2, 0, 0, 0, 0, 0, 0, 2, 2, 2, 2, 2, 2, 2, 2, 2]
+    return np.array([a, b], np.int8)
+
+
 def endgame_boards():
     """BASELINE.json configs[4]: repetition-heavy endgames (few irreversible moves -> long repetition windows)"""
     def board(**pieces):

@@ -147,6 +147,16 @@ def test_many_piece_templates_use_more_slots():
         ph.check_sampled_vs_oracle(env, opponent, color, 11, 150, boards=boards, compare_every=10)
 
 
+def test_more_than_255_legal_moves():
+    """queen-heavy initial boards: more than 255 legal moves, beyond the byte-wise prefix sums of the ordered pick
+    (the pick then scans the count bytes one by one)"""
+    boards = ph.queen_heavy_boards()
+    n_max = max(orc.OracleEnv(b, "WHITE", "none", 1, 0).view()["n_legal"] for b in boards)
+    assert n_max > 255
+    env = EmulAdapter(8, opponent="none", seed=21, auto_reset=True, initial_boards=boards, legal_stride=512)
+    ph.check_sampled_vs_oracle(env, "none", "WHITE", 21, 60, boards=boards, compare_every=5)
+
+
 def test_endgames_with_long_repetition_windows():
     """BASELINE.json configs[4]: repetition-heavy endgames, move cap lifted, 512-slot ring: the Bloom-gated ring scan
     must find every 3-fold the reference's dict finds (windows grow to hundreds of plies here)"""

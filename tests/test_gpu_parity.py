@@ -256,6 +256,24 @@ def test_legal_views_agree_and_many_piece_templates(golden):
     assert torch.equal(pop.to(torch.int32) + castles.to(torch.int32), inf[:, 9])
 
 
+def test_more_than_255_legal_moves():
+    """queen-heavy initial boards: more than 255 legal moves (the ordered pick's byte-wise prefix sums do not apply),
+    single-step and multi-step kernels"""
+    boards = ph.queen_heavy_boards()
+    assert max(orc.OracleEnv(b, "WHITE", "none", 1, 0).view()["n_legal"] for b in boards) > 255
+    env = GpuAdapter(64, opponent="none", seed=21, auto_reset=True, initial_boards=boards, legal_stride=512)
+    ph.check_sampled_vs_oracle(env, "none", "WHITE", 21, 60, boards=boards, compare_every=5)
+    from gym_chess_b200 import BatchedChessEnv
+    a = BatchedChessEnv(64, opponent="none", seed=22, initial_boards=boards, legal_stride=512)
+    b = BatchedChessEnv(64, opponent="none", seed=22, initial_boards=boards, legal_stride=512)
+    a.step_sampled(48)
+    for _ in range(48):
+        b.step_sampled(1)
+    for x, y in zip(a.export_numpy(), b.export_numpy()):
+        assert (x == y).all()
+    assert a.stats() == b.stats()
+
+
 def test_compat_env_v2_replays_recorded_games(golden):
     """the single-env gym-style class (reference surface) against games recorded from the REAL chess_v2.py: self-play,
     and WHITE vs a callable opponent that replays the recorded bot moves (chess_v2.py:171-179 accepts callables)"""
