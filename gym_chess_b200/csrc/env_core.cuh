@@ -470,12 +470,16 @@ GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
 }
 
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step), state in registers
-template <int MODE, class G>
+// SELFPLAY = true: the caller guarantees opponent "none" (one ply per step, no bot, WHITE agent) -- the bot's branches
+// are compiled out of the self-play kernel.
+template <int MODE, bool SELFPLAY = false, class G>
 GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch,
                           const SlotRef& sr, const G& geo) {
+    const int v_pps = SELFPLAY ? 1 : v.pps;
+    const bool v_bot = SELFPLAY ? false : v.opponent == 1, v_agent_black = SELFPLAY ? false : v.agent_black != 0;
     const u32 genv = v.env_offset + (u32)e;
     HistCursor hc;
-    hc.base = io.tick * (u64)v.pps, hc.cursor = 0;
+    hc.base = io.tick * (u64)v_pps, hc.cursor = 0;
 
     int action = ACT_RESIGN, bot_action = -1, R = 0, phase;
     u32 fl = 0;
@@ -561,7 +565,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                     for (int r = 0; r < np && r < sr.slots; r++) dst.st(r, ts[r]);
                 }
                 ep += (u32)io.ep_inc;
-                if (v.agent_black) {
+                if (v_agent_black) {
                     // the bot opens for White (chess_v2.py:208-216)
                     if (s.n_legal > 0) {
                         u32 u = philox_draw(v.seed, genv, ep, 0u, 2u);
@@ -570,7 +574,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                     } else {
                         do_apply = false;
                     }
-                    slot = v.pps - 1;
+                    slot = v_pps - 1;
                     phase = PH_RESETBOT;
                     continue;
                 }
@@ -588,7 +592,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             s.done = rep;
             if (rep) fl |= EF_REPETITION;
             if (mate) s.done = 1, R += 100, fl |= EF_MATE;  // chess_v2.py:270-272
-            if (!s.done && v.opponent == 1) {
+            if (!s.done && v_bot) {
                 if (s.n_legal > 0) {  // chess_v2.py:277-288
                     u32 u = philox_draw(v.seed, genv, ep, step_idx, 1u);
                     bot_action = action_at(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
@@ -613,7 +617,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             phase = PH_END;
         }
     }
-    hist_skip_to(v, e, s, hc, v.pps, st);
+    hist_skip_to(v, e, s, hc, v_pps, st);
     if (MODE != MODE_RESET && io.bot_out) io.bot_out[e] = bot_action;
 }
 
@@ -622,7 +626,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     EnvRegs s;
     u32 ep;
     env_load(v, e, s, ep);
-    env_step_regs<MODE>(v, io, e, s, ep, st, scratch, resident_slots(v, e), GeomGlobal());
+    env_step_regs<MODE, false>(v, io, e, s, ep, st, scratch, resident_slots(v, e), GeomGlobal());
     env_store(v, e, s, ep);
 }
 

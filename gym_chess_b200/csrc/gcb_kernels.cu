@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions
 
 // TILE (multi-step sampled launches with the default 16 piece slots): the slots live in a shared-memory tile for the whole
 // launch; a compile-time property so that slot accesses are plain LDS / STS with constant strides.
-template <int MODE, bool TILE = false>
+// SELFPLAY: opponent "none" is a launch-time fact, so the self-play kernel carries no bot code (a smaller hot loop: the
+// kernel's instruction footprint is what it waits for most).
+template <int MODE, bool TILE = false, bool SELFPLAY = false>
 // measured on B200: the multi-step sampled kernel is fastest with 4 resident blocks per SM (128 registers; more warps
 // thrash the instruction cache), the single-step kernels with 5 (96 registers)
 __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_MIN_BLOCKS : GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
@@ -237,8 +239,8 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_
         StepStats st;
         st.clear();
         if (active) {
-            if (TILE) env_step_regs<MODE>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, sgeo);
-            else env_step_regs<MODE>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, GeomGlobal());
+            if (TILE) env_step_regs<MODE, SELFPLAY>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, sgeo);
+            else env_step_regs<MODE, SELFPLAY>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, GeomGlobal());
         }
         if (MODE != MODE_RESET) {
             // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The bit-field counters are widened into
@@ -586,7 +588,10 @@ static int launch_range(gcb_env* env, const void* in, int32_t* reward, uint8_t* 
     StepIO io;
     io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
     io.tick = env->tick, io.ep_inc = ep_inc, io.e_begin = e_begin, io.e_end = e_end, io.nsteps = 1;
-    k_env_step<MODE><<<grid_for(e_end - e_begin), GCB_BLOCK, 0, s>>>(env->v, io);
+    if (MODE != MODE_RESET && env->v.opponent == 0 && !env->v.agent_black)
+        k_env_step<MODE, false, (MODE != MODE_RESET)><<<grid_for(e_end - e_begin), GCB_BLOCK, 0, s>>>(env->v, io);
+    else
+        k_env_step<MODE><<<grid_for(e_end - e_begin), GCB_BLOCK, 0, s>>>(env->v, io);
     LAUNCHED();
     return GCB_OK;
 }
@@ -794,7 +799,9 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
             io.e_begin = r * per, io.e_end = (r + 1) * per < (int)N ? (r + 1) * per : (int)N;
             if (io.e_begin >= io.e_end) break;
             cudaStream_t ls = R > 1 ? env->streams[r] : cs;
-            if (k >= 4 && env->v.slots == GCB_SLOTS)
+            if (k >= 4 && env->v.slots == GCB_SLOTS && env->v.opponent == 0 && !env->v.agent_black)
+                k_env_step<MODE_SAMPLED, true, true><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
+            else if (k >= 4 && env->v.slots == GCB_SLOTS)
                 k_env_step<MODE_SAMPLED, true><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
             else
                 k_env_step<MODE_SAMPLED, false><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
