@@ -359,6 +359,34 @@ def main():
         torch.cuda.synchronize()
         line["step_plus_action_list"] = {"value": N * ksteps / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT,
                                          "note": "k_env_step + k_env_legal_list (uint16[N][144] list + count) per step"}
+        # ---- the learner-facing legal-action BIT mask (uint64[N][65], 520 B per env): a pure streaming kernel, the one
+        # HBM-bound kernel of the path -- algorithmic bytes = 520 written + 40 state + 8 per own piece (slots) read
+        bits = torch.empty((N, 65), dtype=torch.int64, device=dev)
+        for _ in range(3):
+            check(L.gcb_env_legal_bitmask(env._h, bits.data_ptr(), 65, None))
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(20):
+            check(L.gcb_env_legal_bitmask(env._h, bits.data_ptr(), 65, None))
+        ev1.record()
+        torch.cuda.synchronize()
+        bm_ms = ev0.elapsed_time(ev1) / 20
+        own_pieces = float(((env.observe().reshape(N, 64) != 0).sum(1).float().mean() / 2).item())
+        bm_bytes = 520 + 40 + 8 * own_pieces
+        line["legal_bitmask"] = {"kernel": "k_env_legal_bits", "envs": N, "ms_per_launch": bm_ms, "bytes_per_env": bm_bytes,
+                                 "achieved_gbs": bm_bytes * N / (bm_ms * 1e-3) / 1e9, "peak_gbs": peak,
+                                 "hbm_frac": bm_bytes * N / (bm_ms * 1e-3) / 1e9 / peak,
+                                 "note": "bound: hbm; every other kernel of the path is integer-pipe bound"}
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(ksteps):
+            env.step_sampled(1)
+            check(L.gcb_env_legal_bitmask(env._h, bits.data_ptr(), 65, None))
+        ev1.record()
+        torch.cuda.synchronize()
+        line["step_plus_bitmask"] = {"value": N * ksteps / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT,
+                                     "note": "k_env_step (one step per launch) + k_env_legal_bits (uint64[N][65] mask) per step"}
+        del bits
         # ---- BASELINE.json configs[2]: 65,536 envs on one GPU
         small = BatchedChessEnv(65536, opponent="none", seed=2, device=local_rank)
         small.step_sampled(args.burn_in)

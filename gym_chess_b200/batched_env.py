@@ -227,6 +227,21 @@ class BatchedChessEnv:
             check(_lib.lib().gcb_env_legal_mask(self._h, C.c_void_p(m.data_ptr()), _stream_ptr()))
         return m
 
+    def legal_bitmask(self, out=None):
+        """int64 [N, 65] bit mask of possible_actions: bit (a & 63) of word (a >> 6); word `from` = the legal targets of the
+        piece on that square, word 64 = castles (actions 4096..4099 in bits 0..3).  520 B per env: the per-step form."""
+        with torch.cuda.device(self.device):
+            m = torch.empty((self.num_envs, 65), dtype=torch.int64, device=self.device) if out is None else out
+            check(_lib.lib().gcb_env_legal_bitmask(self._h, C.c_void_p(m.data_ptr()), int(m.stride(0)), _stream_ptr()))
+        return m
+
+    @staticmethod
+    def unpack_bitmask(bits):
+        """int64 [N, 65] bit mask -> bool [N, 4101] (torch ops; for tests and small batches)"""
+        sh = torch.arange(64, device=bits.device, dtype=torch.int64)
+        full = ((bits[:, :, None] >> sh) & 1).to(torch.bool).reshape(bits.shape[0], 65 * 64)
+        return full[:, :4101]
+
     def export_numpy(self):
         """(boards int8[N,64], info int32[N,16], legal uint16[N,stride]) on the host -- test / debug helper."""
         boards = self.observe().reshape(self.num_envs, 64).cpu().numpy()

@@ -371,6 +371,48 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_mask(EnvView v, uint8_t
     env_legal_list_one(v, e, offs, mo);
 }
 
+// possible_actions as a BIT mask: bit a of a 4101-bit vector per env, in 65 little-endian 64-bit words -- word `from`
+// (0..63) is exactly the resident legal-target set of the piece on that square, word 64 holds the four castle actions
+// (bit a - 4096).  A streaming kernel (HBM-bound): the thread that owns an env stages its piece slots in shared memory,
+// then the warp writes the 32 rows one after the other, lane = from-square, as coalesced 256-byte stores.
+__global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_bits(EnvView v, u64* __restrict__ out, int stride_words) {
+    __shared__ u64 s_slots[GCB_SLOTS * GCB_BLOCK];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    u64 own = 0;
+    u32 cword = 0;
+    if (e < v.N) {
+        EnvRegs s;
+        ulonglong2 a = __ldcs(&v.bb01[e]), c = __ldcs(&v.bb23[e]);
+        s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
+        unpack_meta(__ldcs(&v.meta[e]), s);
+        own = stm_pieces(s);
+        const int np = gcb_popc(own);
+        for (int r = 0; r < np && r < GCB_SLOTS; r++) s_slots[r * GCB_BLOCK + threadIdx.x] = __ldcs(v.tgt + (size_t)r * v.N + e);
+        // castle bits of meta (bit0 queen side, bit1 king side, of the side to move) -> bit (action - 4096)
+        if (s.castle & 1u) cword |= 1u << (castle_action(!s.stm_black, 0) - 4096);
+        if (s.castle & 2u) cword |= 1u << (castle_action(!s.stm_black, 1) - 4096);
+    }
+    __syncwarp();
+    const int e0 = e - lane;
+#pragma unroll 1
+    for (int p = 0; p < 32 && e0 + p < v.N; p++) {
+        const u64 own_p = __shfl_sync(0xffffffffu, own, p);
+        const u32 c_p = __shfl_sync(0xffffffffu, cword, p);
+        u64* row = out + (size_t)(e0 + p) * (size_t)stride_words;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int sq = lane + 32 * h;
+            u64 T = 0;
+            if ((own_p >> sq) & 1ULL) {
+                const int r = gcb_popc(own_p & ((1ULL << sq) - 1));
+                T = r < GCB_SLOTS ? s_slots[r * GCB_BLOCK + wbase + p] : (r < v.slots ? __ldcs(v.tgt + (size_t)r * v.N + e0 + p) : 0ULL);
+            }
+            __stcs(row + sq, T);
+        }
+        if (lane == 0) __stcs(row + 64, (u64)c_p);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int need_gpu() {
     int n = 0;
@@ -1011,6 +1053,14 @@ extern "C" int gcb_env_legal_mask(gcb_env* env, uint8_t* d_mask, void* stream) {
     if (!d_mask) return fail(GCB_E_ARG, "gcb_env_legal_mask", "null mask");
     CU(cudaMemsetAsync(d_mask, 0, (size_t)env->v.N * 4101, (cudaStream_t)stream));
     k_env_legal_mask<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, d_mask);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_legal_bitmask(gcb_env* env, uint64_t* d_bits, int stride_words, void* stream) {
+    ENV_CHECK(env);
+    if (!d_bits || stride_words < 65) return fail(GCB_E_ARG, "gcb_env_legal_bitmask", "null pointer or stride_words < 65");
+    k_env_legal_bits<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, reinterpret_cast<u64*>(d_bits), stride_words);
     LAUNCHED();
     return GCB_OK;
 }

@@ -188,6 +188,11 @@ int gcb_env_wait(gcb_env *env, void *stream);
 int gcb_env_export(gcb_env *env, int8_t *d_boards, int32_t *d_info, void *stream);
 /* legal action mask uint8[N][4101] (possible_actions as a mask) */
 int gcb_env_legal_mask(gcb_env *env, uint8_t *d_mask, void *stream);
+/* the same mask as BITS: d_bits uint64[N][stride_words], stride_words >= 65; bit (a & 63) of word (a >> 6) is set iff
+ * action a is in possible_actions -- word `from` (0..63) is the legal-target set of the piece standing on that square,
+ * word 64 holds the castle actions 4096..4099 in bits 0..3.  520 B per env instead of 4101: the form a learner should
+ * read every step (one streaming kernel, HBM-bound). */
+int gcb_env_legal_bitmask(gcb_env *env, uint64_t *d_bits, int stride_words, void *stream);
 /* ChessEnvV2.possible_actions (chess_v2.py:333-335) of every env: d_actions uint16[N][stride] receives the list in
  * the reference's order (normal moves in generation order, then castles), d_counts int32[N] (may be NULL) the true
  * count.  Like the reference's property, the list is DERIVED on access: the resident form of possible_moves is one

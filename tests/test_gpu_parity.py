@@ -243,6 +243,8 @@ def test_legal_views_agree_and_many_piece_templates(golden):
     assert (cnt == info[:, 9]).all()
     for i in range(24):
         assert sorted(int(a) for a in legal[i, : cnt[i]]) == [int(a) for a in np.nonzero(mask[i])[0]]
+    bits = e.unpack_bitmask(e.legal_bitmask()).cpu().numpy()          # the bit mask is the byte mask, bit for byte
+    assert (bits == (mask != 0)).all()
     # default start position: slots are per-piece target sets whose sizes add up to n_legal
     e2 = BatchedChessEnv(512, opponent="none", seed=3)
     e2.step_sampled(40)
@@ -254,6 +256,9 @@ def test_legal_views_agree_and_many_piece_templates(golden):
     live = torch.arange(slots.shape[0], device=slots.device)[:, None] < stm_pieces[None, :]
     pop = (sum(((slots >> k) & 1) for k in range(64)) * live).sum(0)
     assert torch.equal(pop.to(torch.int32) + castles.to(torch.int32), inf[:, 9])
+    e3 = BatchedChessEnv(70001, opponent="none", seed=5)                # ragged last warp, castles, both colours to move
+    e3.step_sampled(91)
+    assert torch.equal(e3.unpack_bitmask(e3.legal_bitmask()), e3.legal_mask() != 0)
 
 
 def test_more_than_255_legal_moves():

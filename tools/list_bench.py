@@ -27,3 +27,12 @@ torch.cuda.synchronize(); e0.record()
 for _ in range(5): L.gcb_env_legal_mask(env._h, m.data_ptr(), None)
 e1.record(); torch.cuda.synchronize()
 print("legal_mask (memset 2.1 GB + scatter): %.1f us" % (e0.elapsed_time(e1) / 5 * 1e3))
+bits = torch.empty((N, 65), dtype=torch.int64, device="cuda")
+for _ in range(3): L.gcb_env_legal_bitmask(env._h, bits.data_ptr(), 65, None)
+torch.cuda.synchronize(); e0.record()
+for _ in range(20): L.gcb_env_legal_bitmask(env._h, bits.data_ptr(), 65, None)
+e1.record(); torch.cuda.synchronize()
+us = e0.elapsed_time(e1) / 20 * 1e3
+np_mean = (env.observe().reshape(N, 64) != 0).sum(1).float().mean().item() / 2
+byt = N * (520 + 40 + 8 * np_mean)
+print("legal_bitmask (520 B per env): %.1f us, %.0f GB/s algorithmic (write 520 B + read 40 B state + %.1f slots)" % (us, byt / us / 1e3, np_mean))
