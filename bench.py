@@ -12,8 +12,9 @@ steps of all ranks / max-over-ranks device time, state resident in HBM.  `e2e` =
 host-buffer C ABI calls (what a binding of the reference env would call): per step the caller's random words cross
 PCIe host->device from pinned memory and reward/done/flags device->host, inside the timed region (the kernel reads /
 writes the page-locked buffers in place).  The envs of a rank are stepped as two shards with the asynchronous calls
-(gcb_env_step_index_host_async / gcb_env_wait), one in flight while the host handles the other; the synchronous
-one-call-per-step figure (gcb_env_step_index_host) is reported as e2e.sync_call_value.
+(gcb_env_step_index_packed / gcb_env_wait: 16-bit words in, 16-bit result records out), one in flight while the host
+handles the other; the same with the wide int32 / uint8 arrays (e2e.wide_records_value) and the synchronous
+one-call-per-step figure (gcb_env_step_index_host, e2e.sync_call_value) are reported next to it.
 """
 import argparse
 import json
@@ -230,28 +231,43 @@ def main():
         with torch.cuda.stream(streams[k]):
             shards[k].step_sampled(args.burn_in)
 
-    def e2e_loop(steps):
-        # a step = both shards stepped once (N env steps, 4N bytes in, 6N bytes out)
-        shards[0].step_index_host_async(*ptrs[0][0], stream=streams[0])
+    words16 = torch.empty((8, N), dtype=torch.int16).pin_memory()
+    words16.random_(-2 ** 15, 2 ** 15 - 1)
+    h_res = torch.empty(N, dtype=torch.int16).pin_memory()
+    ptrs16 = [[(vp(words16[j, k * H:].data_ptr()), vp(h_res[k * H:].data_ptr())) for j in range(8)] for k in range(2)]
+
+    def e2e_loop(steps, packed):
+        # a step = both shards stepped once (N env steps).  packed: uint16 words in, uint16 records out (2 + 2 bytes per
+        # env step); else uint32 words in, int32 reward + uint8 done + uint8 flags out (4 + 6 bytes)
+        if packed:
+            issue = lambda k, i: shards[k].step_index_packed(*ptrs16[k][i % 8], stream=streams[k])
+        else:
+            issue = lambda k, i: shards[k].step_index_host_async(*ptrs[k][i % 8], stream=streams[k])
+        issue(0, 0)
         for i in range(steps):
-            shards[1].step_index_host_async(*ptrs[1][i % 8], stream=streams[1])
+            issue(1, i)
             shards[0].wait(stream=streams[0])   # shard 0's results of step i are in host memory
             if i + 1 < steps:
-                shards[0].step_index_host_async(*ptrs[0][(i + 1) % 8], stream=streams[0])
+                issue(0, i + 1)
             shards[1].wait(stream=streams[1])   # shard 1's results of step i are in host memory
 
-    e2e_loop(3)
-    barrier()
-    ev0.record(streams[0])
-    t0 = time.perf_counter()
-    e2e_loop(e2e_steps)
-    t1 = time.perf_counter()
-    ev1.record(streams[1])
-    barrier()
-    # device events (first launch .. last completion) and the host's wall clock around the same loop: the slower one counts
-    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (t1 - t0) * 1e3))
-    clk = clocks.stop() if rank == 0 else None  # sampled over both timed regions (kernel-only and end-to-end)
+    def timed(packed):
+        e2e_loop(3, packed)
+        barrier()
+        ev0.record(streams[0])
+        t0 = time.perf_counter()
+        e2e_loop(e2e_steps, packed)
+        t1 = time.perf_counter()
+        ev1.record(streams[1])
+        barrier()
+        # device events (first launch .. last completion) and the host's wall clock around the same loop: the slower one counts
+        return max_over_ranks(max(ev0.elapsed_time(ev1), (t1 - t0) * 1e3))
+
+    wide_ms = timed(False)
+    e2e_ms = timed(True)
+    clk = clocks.stop() if rank == 0 else None  # sampled over the timed regions (kernel-only and end-to-end)
     e2e_value = world * N * e2e_steps / (e2e_ms * 1e-3)
+    wide_value = world * N * e2e_steps / (wide_ms * 1e-3)
     e2e_launches = 2 * e2e_steps
     for sh in shards:
         sh.close()
@@ -289,13 +305,17 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD % N, "envs_per_gpu": N, "total_envs": world * N, "burn_in_steps": args.burn_in,
                    "l2": "inputs larger than L2 (2.2 GB resident state per GPU vs 126 MB L2), no flush"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 6 * N,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N, "d2h_bytes_per_step": 2 * N,
                 "steps": e2e_steps, "launches": e2e_launches,
-                "api": "gcb_env_step_index_host_async + gcb_env_wait (BatchedChessEnv.step_index_host_async / wait), pinned "
-                       "host buffers; the rank's envs as two shards stepped alternately (one in flight while the host "
-                       "handles the other)",
+                "api": "gcb_env_step_index_packed + gcb_env_wait (BatchedChessEnv.step_index_packed / wait): uint16 random words "
+                       "in, uint16 result records (reward int8 | flags | done) out, page-locked host buffers read / written in "
+                       "place by the step kernel; the rank's envs as two shards stepped alternately (one in flight while the "
+                       "host handles the other)",
+                "wide_records_value": wide_value,
+                "wide_records_api": "gcb_env_step_index_host_async: uint32 words in, int32 reward + uint8 done + uint8 flags out "
+                                    "(4 + 6 bytes per env step), same two shards",
                 "sync_call_value": sync_value,
-                "sync_call_api": "gcb_env_step_index_host: one synchronous call per step for all envs of the rank"},
+                "sync_call_api": "gcb_env_step_index_host: one synchronous call per step for all envs of the rank (4 + 6 bytes)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "k_env_step<MODE_SAMPLED>", "bytes_per_unit": bytes_per_step,

@@ -89,6 +89,8 @@ SIGNATURES = {
     "gcb_env_step_host_async": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_step_index_host_async": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_wait": (i32, [vp, vp]),
+    "gcb_env_step_packed": (i32, [vp, vp, vp, vp]),
+    "gcb_env_step_index_packed": (i32, [vp, vp, vp, vp]),
     "gcb_env_export": (i32, [vp, vp, vp, vp]),
     "gcb_env_legal_mask": (i32, [vp, vp, vp]),
     "gcb_env_legal_bitmask": (i32, [vp, vp, i32, vp]),

@@ -174,6 +174,20 @@ class BatchedChessEnv:
     def _host_async(self, fn, inp, reward, done, flags, stream):
         check(fn(self._h, _host_ptr(inp), _host_ptr(reward), _host_ptr(done), _host_ptr(flags), _stream_ptr(stream)))
 
+    # packed 16-bit records (2 bytes in, 2 bytes out per env): uint16 actions / random words, uint16 results; buffers are
+    # cuda tensors or page-locked host tensors / arrays; asynchronous like the calls above
+    def step_packed(self, actions16, result16, stream=None):
+        check(_lib.lib().gcb_env_step_packed(self._h, _host_ptr(actions16), _host_ptr(result16), _stream_ptr(stream)))
+
+    def step_index_packed(self, u16, result16, stream=None):
+        check(_lib.lib().gcb_env_step_index_packed(self._h, _host_ptr(u16), _host_ptr(result16), _stream_ptr(stream)))
+
+    @staticmethod
+    def unpack_result(result16):
+        """uint16 records -> (reward int32, done uint8, flags uint8); numpy array or torch tensor (viewed as int16/int32)"""
+        r = np.asarray(result16).view(np.uint16) if not isinstance(result16, torch.Tensor) else result16.cpu().numpy().view(np.uint16)
+        return (r & 0xFF).astype(np.uint8).view(np.int8).astype(np.int32), (r >> 15).astype(np.uint8), ((r >> 8) & 63).astype(np.uint8)
+
     def wait(self, stream=None):
         """block until the steps enqueued on `stream` (default: the current torch stream) have finished"""
         check(_lib.lib().gcb_env_wait(self._h, _stream_ptr(stream)))

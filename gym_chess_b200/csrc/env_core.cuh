@@ -448,7 +448,15 @@ struct StepIO {
     int ep_inc;
     int e_begin, e_end;  // env range of this launch (host-buffer steps are pipelined in chunks)
     int nsteps;          // MODE_SAMPLED: consecutive steps run by ONE launch (envs are independent: no grid-wide sync needed)
+    // packed 16-bit records (host-buffer steps are bound by the bytes that cross PCIe): in16 != 0 -> `in` holds uint16
+    // actions / uint16 random words (a word w draws like the 32-bit word w << 16); packed != NULL -> one uint16 result
+    // per env: bits 0-7 reward (int8; a reward is always within [-120, 100]), bits 8-13 flags, bit 15 done
+    uint16_t* packed = nullptr;
+    int in16 = 0;
 };
+GCB_HD uint16_t pack_result(int reward, bool done, u32 flags) {
+    return (uint16_t)((u32)(reward & 0xFF) | ((flags & 63u) << 8) | (done ? 0x8000u : 0u));
+}
 
 // resident state of env e <-> registers
 GCB_HD void env_load(const EnvView& v, int e, EnvRegs& s, u32& ep) {
@@ -493,10 +501,11 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
     } else {
         bool valid = false;
         if (MODE == MODE_ACTION) {
-            action = reinterpret_cast<const int32_t*>(io.in)[e];
+            action = io.in16 ? (int)reinterpret_cast<const uint16_t*>(io.in)[e] : reinterpret_cast<const int32_t*>(io.in)[e];
             valid = action_is_legal(sr, s, action);  // action in possible_actions
         } else {
-            u32 u = (MODE == MODE_INDEX) ? reinterpret_cast<const u32*>(io.in)[e] : philox_draw(v.seed, genv, ep, step_idx, 0u);
+            u32 u = (MODE == MODE_INDEX) ? (io.in16 ? (u32)reinterpret_cast<const uint16_t*>(io.in)[e] << 16 : reinterpret_cast<const u32*>(io.in)[e])
+                                         : philox_draw(v.seed, genv, ep, step_idx, 0u);
             if (n0 > 0) {
                 action = action_at(sr, s, (int)gcb_umulhi(u, (u32)n0));
                 valid = true;
@@ -545,6 +554,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 if (io.reward) io.reward[e] = R;
                 if (io.done) io.done[e] = d_out ? 1 : 0;
                 if (io.flags) io.flags[e] = (uint8_t)fl;
+                if (io.packed) io.packed[e] = pack_result(R, d_out, fl);
                 if (io.act_out) io.act_out[e] = action;
             }
             if ((MODE == MODE_RESET) || (v.auto_reset && terminal)) {

@@ -971,6 +971,45 @@ extern "C" int gcb_env_step_index_host_async(gcb_env* env, const uint32_t* u32, 
     return step_host_async(env, MODE_INDEX, u32, reward, done, flags, stream);
 }
 
+// Packed 16-bit records: the same step with 2 bytes in and 2 bytes out per env (10 with the int32 / uint8 arrays).  The
+// pointers may be device memory or page-locked host memory (the device alias is used: read / written in place through PCIe).
+static void* device_view(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return const_cast<void*>(p);
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+template <int MODE>
+static int step_packed(gcb_env* env, const uint16_t* in16, uint16_t* result16, void* stream) {
+    void* d_in = device_view(in16);
+    void* d_out = device_view(result16);
+    if (!d_in || (result16 && !d_out))
+        return fail(GCB_E_ARG, "gcb_env_step_*_packed", "buffers must be device memory or page-locked host memory");
+    StepIO io;
+    io.in = d_in, io.in16 = 1, io.packed = (uint16_t*)d_out;
+    io.reward = nullptr, io.done = nullptr, io.flags = nullptr, io.act_out = nullptr, io.bot_out = nullptr;
+    io.tick = env->tick, io.ep_inc = 1, io.e_begin = 0, io.e_end = env->v.N, io.nsteps = 1;
+    if (env->v.opponent == 0 && !env->v.agent_black)
+        k_env_step<MODE, false, true><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
+    else
+        k_env_step<MODE><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
+    LAUNCHED();
+    env->tick++;
+    return GCB_OK;
+}
+extern "C" int gcb_env_step_packed(gcb_env* env, const uint16_t* actions16, uint16_t* result16, void* stream) {
+    ENV_CHECK(env);
+    return step_packed<MODE_ACTION>(env, actions16, result16, stream);
+}
+extern "C" int gcb_env_step_index_packed(gcb_env* env, const uint16_t* u16, uint16_t* result16, void* stream) {
+    ENV_CHECK(env);
+    return step_packed<MODE_INDEX>(env, u16, result16, stream);
+}
+
 extern "C" int gcb_env_wait(gcb_env* env, void* stream) {
     ENV_CHECK(env);
     CU(cudaStreamSynchronize((cudaStream_t)stream));

@@ -181,6 +181,16 @@ int gcb_env_step_index_host_async(gcb_env *env, const uint32_t *u32, int32_t *re
                                   void *stream);
 int gcb_env_wait(gcb_env *env, void *stream);
 
+/* Packed 16-bit records (asynchronous, enqueued on `stream` like the device-pointer forms): 2 bytes in and 2 bytes out
+ * per env instead of 4 + 6 -- host-buffer steps are bound by the bytes that cross PCIe, and with 8 GPUs by the host's
+ * memory fabric.  actions16 uint16[N] (an action code is < 4101); u16 uint16[N]: word w draws like the 32-bit word
+ * w << 16 of gcb_env_step_index, i.e. possible_actions[(w * n_legal) >> 16]; result16 uint16[N]: bits 0-7 the reward as
+ * int8 (a step's reward is always within [-120, 100]: -10, a capture <= 10, +-100 for a mate, minus the bot's capture),
+ * bits 8-13 the GCB_F_* flags, bit 15 done.  Each pointer may be device memory or page-locked host memory (read / written
+ * in place through its device alias); results are valid after gcb_env_wait / a synchronisation of the stream. */
+int gcb_env_step_packed(gcb_env *env, const uint16_t *actions16, uint16_t *result16, void *stream);
+int gcb_env_step_index_packed(gcb_env *env, const uint16_t *u16, uint16_t *result16, void *stream);
+
 /* observation / state export (device pointers, any may be NULL):
  *   d_boards int8[N][64]   -- `state["board"]`, the Box(-6,6,(8,8)) observation
  *   d_info   int32[N][16]  -- current_player(+1/-1), wk, wq, bk, bq, wchk, bchk, done, move_count, n_legal,

@@ -383,6 +383,48 @@ def test_async_host_steps_of_two_shards_in_flight():
     assert all(sw[k] == sa[k] + sb[k] for k in sw) and sw["episodes"] > 0
 
 
+@pytest.mark.parametrize("opponent,color", [("none", "WHITE"), ("random", "BLACK")])
+def test_packed_16_bit_records_equal_the_wide_arrays(opponent, color):
+    """gcb_env_step_index_packed / gcb_env_step_packed (uint16 in, uint16 result, device or page-locked host buffers) ==
+    the int32 / uint8 array forms, step by step: word w draws like the 32-bit word w << 16"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv
+
+    N = 20011
+    wide = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=9)
+    pk_host = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=9)
+    pk_dev = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=9)
+    rng = np.random.RandomState(3)
+    h_in, h_out = torch.empty(N, dtype=torch.int16).pin_memory(), torch.empty(N, dtype=torch.int16).pin_memory()
+    d_out = torch.empty(N, dtype=torch.int16, device="cuda")
+    for t in range(70):
+        w = rng.randint(0, 1 << 16, size=N).astype(np.uint16)
+        r, d, f = wide.step_index(torch.from_numpy((w.astype(np.uint32) << 16).view(np.int32)).cuda())
+        r, d, f = r.cpu().numpy(), d.cpu().numpy(), f.cpu().numpy()
+        h_in.numpy().view(np.uint16)[:] = w
+        pk_host.step_index_packed(h_in, h_out)
+        pk_host.wait()
+        pk_dev.step_index_packed(torch.from_numpy(w.view(np.int16)).cuda(), d_out)
+        for res in (h_out, d_out):
+            pr, pd, pf = BatchedChessEnv.unpack_result(res)
+            assert (pr == r).all() and (pd == d).all() and (pf == (f & 63)).all(), t
+    assert wide.stats() == pk_host.stats() == pk_dev.stats() and wide.stats()["episodes"] > 0
+    # external actions as uint16 (incl. invalid ones) against the int32 form
+    a_env = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=4)
+    b_env = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=4)
+    for t in range(30):
+        legal, cnt = a_env.legal_actions()
+        legal, cnt = legal.cpu().numpy().view(np.uint16), cnt.cpu().numpy()
+        pick = (rng.randint(0, 1 << 30, size=N) % np.maximum(cnt, 1))
+        acts = legal[np.arange(N), pick].astype(np.int32)
+        acts[rng.rand(N) < 0.05] = rng.randint(0, 4101)           # some arbitrary (mostly invalid) actions
+        r, d, f = a_env.step(torch.from_numpy(acts).cuda())
+        b_env.step_packed(torch.from_numpy(acts.astype(np.uint16).view(np.int16)).cuda(), d_out)
+        pr, pd, pf = BatchedChessEnv.unpack_result(d_out)
+        assert (pr == r.cpu().numpy()).all() and (pd == d.cpu().numpy()).all() and (pf == (f.cpu().numpy() & 63)).all(), t
+    assert a_env.stats() == b_env.stats()
+
+
 def test_endgames_with_long_repetition_windows():
     """BASELINE.json configs[4]: repetition/promotion-heavy endgames with a 512-ply Zobrist history.  Parity against the
     oracle at a size it replays in seconds; at 1M envs the size-independent properties."""
