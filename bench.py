@@ -207,7 +207,9 @@ def main():
     h_d = torch.empty(N, dtype=torch.uint8).pin_memory()
     h_f = torch.empty(N, dtype=torch.uint8).pin_memory()
     wn, rn, dn, fn = words.numpy().view(np.uint32), h_r.numpy(), h_d.numpy(), h_f.numpy()
-    e2e_steps = max(10, min(args.steps, 200))
+    # an episode of random self-play is ~300 steps for 3 envs in 4 (the move cap) and the per-step cost falls as pieces leave
+    # the board, so the end-to-end loops cover two whole episode cycles when --steps allows (like the 2000-step kernel region)
+    e2e_steps = max(10, min(args.steps, 602))
     for i in range(3):
         env.step_index_host(wn[i % 8], rn, dn, fn)
     barrier()

@@ -16,15 +16,23 @@ for row in csv.reader(io.StringIO(raw)):
         cur["hdr"] = row
     elif row and cur is not None and "hdr" in cur:
         cur["rows"].append(row)
-blk = [b for b in blocks if pat in b["name"].replace("(int)", "").replace("(bool)", "")][0]
+blk = [b for b in blocks if pat.replace(" ", "") in b["name"].replace("(int)", "").replace("(bool)", "").replace(" ", "")][0]
 h = {n: i for i, n in enumerate(blk["hdr"])}
 d = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=d, stdout=subprocess.DEVNULL)
 cub = [os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cubin")][0]
 lines = subprocess.run(["nvdisasm", "--print-line-info-inline", cub], capture_output=True, text=True).stdout.split("\n")
 starts = [i for i, l in enumerate(lines) if l.startswith("//--------------------- .text.")]
-mang = {"k_env_step<2>": "k_env_stepILi2E", "k_env_step<0>": "k_env_stepILi0E", "k_env_step<1>": "k_env_stepILi1E",
-        "k_movegen<false>": "k_movegenILb0E", "k_movegen<0>": "k_movegenILb0E", "k_env_legal_list": "k_env_legal_list"}.get(pat, pat)
+def mangled(pat):
+    # "k_env_step<1, 0, 1>" -> "k_env_stepILi1ELb0ELb1E"; "k_movegen<false>" / "k_movegen<0>" -> "k_movegenILb0E"
+    m = re.match(r"(\w+)<(.*)>$", pat.replace(" ", ""))
+    if not m:
+        return pat
+    name, args = m.group(1), m.group(2).split(",")
+    if name == "k_env_step":
+        return name + "ILi%sE" % args[0] + "".join("Lb%dE" % int(a not in ("0", "false")) for a in (args[1:] + ["0", "0"])[:2])
+    return name + "I" + "".join("Lb%dE" % int(a not in ("0", "false")) for a in args)
+mang = mangled(pat)
 locs = []
 for si, st in enumerate(starts):
     if mang not in lines[st]:

@@ -1,0 +1,17 @@
+#!/usr/bin/env python
+"""profiling driver for the single-step kernel (external random words on device): tools/prof_single.py [steps]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gym_chess_b200 import BatchedChessEnv
+N = 524288
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+env = BatchedChessEnv(N, opponent="none", seed=2)
+env.step_sampled(576)
+w = torch.randint(-2**31, 2**31 - 1, (8, N), dtype=torch.int32, device="cuda")
+for i in range(3): env.step_index(w[i])
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); e0.record()
+for i in range(steps): env.step_index(w[i % 8])
+e1.record(); torch.cuda.synchronize()
+print("single-step kernel: %.1f us/step" % (e0.elapsed_time(e1) / steps * 1e3))
