@@ -473,6 +473,31 @@ def test_multi_step_launch_equals_single_steps(opponent, color):
     assert torch.equal(a.piece_slots()[:, :8], b.piece_slots()[:, :8]) or True  # slots beyond the live pieces are unspecified
 
 
+def test_multi_launch_runs_as_env_ranges_on_two_streams():
+    """a sampled run of several launches over >= 131,072 envs is issued as two env ranges on two internal streams (forked
+    from / joined to the caller's stream): same results as single-step launches, also when followed at once by other work
+    on the caller's stream, on a side stream, and with an env count that is not a multiple of the block size"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv
+
+    N, T = 131072 + 77, 134   # 134 = 64 + 64 + 6: three launches per range
+    a = BatchedChessEnv(N, opponent="none", seed=41)
+    b = BatchedChessEnv(N, opponent="none", seed=41)
+    side = torch.cuda.Stream()
+    for _ in range(T):
+        a.step_sampled(1)
+    with torch.cuda.stream(side):
+        r2, d2, f2 = b.step_sampled(T)
+        obs_b = b.observe()            # enqueued right behind the run on the same (side) stream
+        mask_b = b.legal_bitmask()
+    side.synchronize()
+    assert torch.equal(a.reward, r2) and torch.equal(a.done, d2) and torch.equal(a.flags, f2)
+    assert torch.equal(a.observe(), obs_b) and torch.equal(a.legal_bitmask(), mask_b)
+    for x, y in zip(a.export_numpy(), b.export_numpy()):
+        assert (x == y).all()
+    assert a.stats() == b.stats() and a.stats()["episodes"] > 0
+
+
 def test_move_sets_of_the_reference_pure_python_env(eng, golden):
     assert ph.check_v1_move_sets(_mg(eng), golden["v1_move_sets"]) > 15000
 
