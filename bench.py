@@ -419,6 +419,24 @@ def main():
         torch.cuda.synchronize()
         line["config_65536_envs"] = {"value": 65536 * args.steps / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT}
         small.close()
+        # ---- BASELINE.json configs[4]: repetition / promotion-heavy endgames, 512-slot Zobrist ring, 1M envs (the regime in
+        # which the repetition windows are long: mean window ~80 plies, ~13 ring entries actually read per ply)
+        from gym_chess_b200.boards import endgame_boards
+        eg = BatchedChessEnv(1 << 20, opponent="none", seed=5, device=local_rank, initial_boards=endgame_boards(), moves_max=250,
+                             history_cap=512)
+        eg.step_sampled(600)
+        eg.reset_stats()
+        torch.cuda.synchronize()
+        ev0.record()
+        eg.step_sampled(200)
+        ev1.record()
+        torch.cuda.synchronize()
+        egs = eg.stats()
+        line["config_endgames_1M_envs"] = {"value": (1 << 20) * 200 / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT,
+                                           "mean_hist_window": egs["hist_window"] / max(1, egs["plies"]),
+                                           "ring_entries_read_per_ply": egs["hist_scanned"] / max(1, egs["plies"]),
+                                           "repetitions": egs["repetitions"], "history_cap": 512}
+        eg.close()
         # ---- BASELINE.json configs[0]: the reference's own CPU-runnable case -- a single env, random-vs-random self-play,
         # ~1k games -- on ONE host thread (the reference is single-threaded), plus legal-movegen positions/s of the same
         # code on one thread and on all of them.  The engine is the oracle port (the Rust engine cannot be built here).

@@ -306,22 +306,9 @@ def queen_heavy_boards():
 
 
 def endgame_boards():
-    """BASELINE.json configs[4]: repetition-heavy endgames (few irreversible moves -> long repetition windows)"""
-    def board(**pieces):
-        b = np.zeros(64, np.int8)
-        for sq, p in pieces.items():
-            b[int(sq[1:])] = p
-        return b
-    K, Q, R, B, N, P = 1, 2, 3, 4, 5, 6
-    return np.array([
-        board(s60=K, s4=-K),                        # K v K
-        board(s60=K, s59=R, s4=-K),                 # KR v K
-        board(s60=K, s58=B, s57=N, s4=-K),          # KBN v K
-        board(s60=K, s59=Q, s4=-K, s3=-R),          # KQ v KR
-        board(s60=K, s62=N, s4=-K, s1=-N),          # KN v KN
-        board(s60=K, s52=P, s4=-K, s12=-P),         # KP v KP (pawns stall on the last rank: no promotion, Q1)
-        board(s60=K, s61=B, s4=-K, s2=-B),          # KB v KB
-    ], np.int8)
+    """BASELINE.json configs[4]: repetition-heavy endgames (the presets live in the package: gym_chess_b200/boards.py)"""
+    from gym_chess_b200.boards import endgame_boards as eb
+    return eb()
 
 
 def check_v1_move_sets(movegen_fn, records):

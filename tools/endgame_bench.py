@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gym_chess_b200 import BatchedChessEnv
-from tests.parity_helpers import endgame_boards
+from gym_chess_b200.boards import endgame_boards
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 env = BatchedChessEnv(N, opponent="none", seed=5, initial_boards=endgame_boards(), moves_max=250, history_cap=512)
