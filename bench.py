@@ -233,34 +233,41 @@ def main():
         with torch.cuda.stream(streams[k]):
             shards[k].step_sampled(args.burn_in)
 
-    words16 = torch.empty((8, N), dtype=torch.int16).pin_memory()
+    from gym_chess_b200 import PipelinedChessEnv
+    pipe = PipelinedChessEnv(N, shards=2, device=local_rank, env_id_offset=off, opponent="none", seed=2, auto_reset=True)
+    pipe.burn_in(args.burn_in)
+    words16 = torch.empty((8, 2, H), dtype=torch.int16).pin_memory()   # this rank's inputs of 8 steps, page-locked
     words16.random_(-2 ** 15, 2 ** 15 - 1)
-    h_res = torch.empty(N, dtype=torch.int16).pin_memory()
-    ptrs16 = [[(vp(words16[j, k * H:].data_ptr()), vp(h_res[k * H:].data_ptr())) for j in range(8)] for k in range(2)]
+    src16 = [[words16[j, k] for k in range(2)] for j in range(8)]
 
     def e2e_loop(steps, packed):
-        # a step = both shards stepped once (N env steps).  packed: uint16 words in, uint16 records out (2 + 2 bytes per
-        # env step); else uint32 words in, int32 reward + uint8 done + uint8 flags out (4 + 6 bytes)
+        # a step = both shards stepped once (N env steps).  packed: the public pipelined API (PipelinedChessEnv.send_words
+        # / recv: uint16 words read from page-locked host memory, uint16 records written back to it; 2 + 2 bytes per env
+        # step); else the wide arrays through the asynchronous calls: uint32 words in, int32 reward + uint8 done + uint8
+        # flags out (4 + 6 bytes)
         if packed:
-            issue = lambda k, i: shards[k].step_index_packed(*ptrs16[k][i % 8], stream=streams[k])
+            issue = lambda k, i: pipe.send_words(k, src=src16[i % 8][k])
+            wait = pipe.recv
         else:
             issue = lambda k, i: shards[k].step_index_host_async(*ptrs[k][i % 8], stream=streams[k])
+            wait = lambda k: shards[k].wait(stream=streams[k])
         issue(0, 0)
         for i in range(steps):
             issue(1, i)
-            shards[0].wait(stream=streams[0])   # shard 0's results of step i are in host memory
+            wait(0)   # shard 0's results of step i are in host memory
             if i + 1 < steps:
                 issue(0, i + 1)
-            shards[1].wait(stream=streams[1])   # shard 1's results of step i are in host memory
+            wait(1)   # shard 1's results of step i are in host memory
 
     def timed(packed):
         e2e_loop(3, packed)
         barrier()
-        ev0.record(streams[0])
+        s0, s1 = (pipe.streams[0], pipe.streams[1]) if packed else (streams[0], streams[1])
+        ev0.record(s0)
         t0 = time.perf_counter()
         e2e_loop(e2e_steps, packed)
         t1 = time.perf_counter()
-        ev1.record(streams[1])
+        ev1.record(s1)
         barrier()
         # device events (first launch .. last completion) and the host's wall clock around the same loop: the slower one counts
         return max_over_ranks(max(ev0.elapsed_time(ev1), (t1 - t0) * 1e3))
@@ -273,6 +280,7 @@ def main():
     e2e_launches = 2 * e2e_steps
     for sh in shards:
         sh.close()
+    pipe.close()
 
     # ---- roofline of the dominant kernel (k_env_step<sampled>): algorithmic bytes per env step, SURVEY.md 8(d):
     # 40 B state read + 40 B state write + 4 B action + 4 B reward + 1 B done + 8 B history append + 8 B x W scanned
@@ -309,7 +317,7 @@ def main():
                    "l2": "inputs larger than L2 (2.2 GB resident state per GPU vs 126 MB L2), no flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N, "d2h_bytes_per_step": 2 * N,
                 "steps": e2e_steps, "launches": e2e_launches,
-                "api": "gcb_env_step_index_packed + gcb_env_wait (BatchedChessEnv.step_index_packed / wait): uint16 random words "
+                "api": "PipelinedChessEnv.send_words / recv (gcb_env_step_index_packed + gcb_env_wait): uint16 random words "
                        "in, uint16 result records (reward int8 | flags | done) out, page-locked host buffers read / written in "
                        "place by the step kernel; the rank's envs as two shards stepped alternately (one in flight while the "
                        "host handles the other)",

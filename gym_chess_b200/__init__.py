@@ -2,6 +2,7 @@
 
 Public surface:
   BatchedChessEnv   N envs resident in HBM; reset / step / step_index / step_sampled / observe / legal_actions
+  PipelinedChessEnv the envs of a device as shards stepped alternately through page-locked 16-bit records (send / recv)
   ChessEngine       drop-in for the reference's PyO3 `ChessEngine` (4 methods, dict/str wire format)
   BatchedChessEngine  the same 4 operations over numpy arrays of positions
   ChessEnvV2        single-env gym-style compat class (reset/step/render/possible_moves/...)
@@ -17,6 +18,9 @@ def __getattr__(name):  # lazy: keeps `import gym_chess_b200` cheap (torch is im
     if name in ("BatchedChessEnv",):
         from .batched_env import BatchedChessEnv
         return BatchedChessEnv
+    if name == "PipelinedChessEnv":
+        from .pipelined import PipelinedChessEnv
+        return PipelinedChessEnv
     if name in ("ChessEngine", "BatchedChessEngine"):
         from . import engine
         return getattr(engine, name)

@@ -425,6 +425,41 @@ def test_packed_16_bit_records_equal_the_wide_arrays(opponent, color):
     assert a_env.stats() == b_env.stats()
 
 
+def test_pipelined_env_send_recv():
+    """PipelinedChessEnv (two shards, page-locked 16-bit records, asynchronous send / recv) == one env set stepped with the
+    same words / actions through the wide device-pointer calls"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv, PipelinedChessEnv
+
+    N, T = 40000, 60
+    whole = BatchedChessEnv(N, opponent="random", seed=23)
+    pipe = PipelinedChessEnv(N, shards=2, opponent="random", seed=23)
+    H = pipe.shard_envs
+    rng = np.random.RandomState(8)
+    for t in range(T):
+        if t % 3 == 2:   # external actions (legal ones from the list, some arbitrary)
+            legal, cnt = whole.legal_actions()
+            legal, cnt = legal.cpu().numpy().view(np.uint16), cnt.cpu().numpy()
+            acts = legal[np.arange(N), rng.randint(0, 1 << 30, size=N) % np.maximum(cnt, 1)].astype(np.uint16)
+            acts[rng.rand(N) < 0.03] = 4100
+            r, d, f = whole.step(torch.from_numpy(acts.astype(np.int32)).cuda())
+            for k in range(2):
+                pipe.inputs[k][:] = acts[k * H:(k + 1) * H]
+                pipe.send_actions(k)
+        else:
+            w = rng.randint(0, 1 << 16, size=N).astype(np.uint16)
+            r, d, f = whole.step_index(torch.from_numpy((w.astype(np.uint32) << 16).view(np.int32)).cuda())
+            for k in range(2):
+                pipe.inputs[k][:] = w[k * H:(k + 1) * H]
+                pipe.send_words(k)
+        r, d, f = r.cpu().numpy(), d.cpu().numpy(), f.cpu().numpy()
+        for k in range(2):
+            pr, pd, pf = pipe.unpack(pipe.recv(k))
+            sl = slice(k * H, (k + 1) * H)
+            assert (pr == r[sl]).all() and (pd == d[sl]).all() and (pf == (f[sl] & 63)).all(), (t, k)
+    assert pipe.stats() == whole.stats() and whole.stats()["episodes"] > 0
+
+
 def test_endgames_with_long_repetition_windows():
     """BASELINE.json configs[4]: repetition/promotion-heavy endgames with a 512-ply Zobrist history.  Parity against the
     oracle at a size it replays in seconds; at 1M envs the size-independent properties."""
