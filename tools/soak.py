@@ -25,4 +25,19 @@ for opponent, color, seed in (("none", "WHITE", 101), ("random", "WHITE", 102), 
     env = GpuAdapter(300, opponent=opponent, player_color=color, seed=seed + 20, auto_reset=True)
     ph.check_external_actions_vs_oracle(env, opponent, color, seed + 20, 600, np.random.RandomState(seed + 1), True)
     print("  import + external actions ok %.0f s" % (time.time() - t0), flush=True)
+# multi-step launches (shared-memory tile, self-play specialisation, env ranges) against single-step launches, long runs
+import torch
+from gym_chess_b200 import BatchedChessEnv
+for opponent, color, seed, N in (("none", "WHITE", 201, 140000), ("random", "WHITE", 202, 20000), ("random", "BLACK", 203, 20000)):
+    a = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=seed)
+    b = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=seed)
+    T = 1500
+    for _ in range(T):
+        a.step_sampled(1)
+    b.step_sampled(T)
+    for x, y in zip(a.export_numpy(), b.export_numpy()):
+        assert (x == y).all()
+    assert a.stats() == b.stats(), (a.stats(), b.stats())
+    assert torch.equal(a.legal_bitmask(), b.legal_bitmask())
+    print("multi-step == single-step:", opponent, color, N, "envs x", T, "steps, episodes", a.stats()["episodes"], "%.0f s" % (time.time() - t0), flush=True)
 print("soak ok")
