@@ -484,6 +484,32 @@ def test_endgames_with_long_repetition_windows():
     assert (bb[:4096] == bs).all() and (ib[:4096] == is_).all()
 
 
+def test_ring_overflow_is_defined_and_identical_on_every_path():
+    """a repetition window that outgrows a small ring (history_cap = 8 on endgame boards) can miss a repetition -- defined
+    behaviour, counted in hist_overflow: the single-step kernel, the multi-step kernel and the host-compiled build of
+    the same device code agree bit for bit on it"""
+    from gym_chess_b200 import BatchedChessEnv
+    from tests.host_emul import emul
+
+    boards = ph.endgame_boards()
+    N, T = 96, 220
+    kw = dict(opponent="none", seed=61, initial_boards=boards, moves_max=250, history_cap=8)
+    a, b = BatchedChessEnv(N, **kw), BatchedChessEnv(N, **kw)
+    h = emul.EmulEnv(N, **kw)
+    for _ in range(T):
+        a.step_sampled(1)
+        h.step_sampled()
+    b.step_sampled(T)
+    ea, eb, eh = a.export_numpy(), b.export_numpy(), h.export()
+    for x, y, z in zip(ea, eb, eh):
+        assert (x == y).all() and (x == z).all()
+    sa, sb = a.stats(), b.stats()
+    assert sa == sb and sa["hist_overflow"] > 0
+    hs = h.stats()
+    from gym_chess_b200.batched_env import STAT_NAMES
+    assert all(int(np.array(sa[k], np.int64).astype(np.uint64)) == int(hs[i]) for i, k in enumerate(STAT_NAMES))
+
+
 @pytest.mark.parametrize("opponent,color", [("none", "WHITE"), ("random", "WHITE"), ("random", "BLACK")])
 def test_multi_step_launch_equals_single_steps(opponent, color):
     """step_sampled(T) runs up to 64 steps per launch with the state in registers and the piece slots in shared
