@@ -175,8 +175,8 @@ def main():
     env.step_sampled(args.burn_in)
     env.step_sampled(args.warmup)
     env.reset_stats()
-    # ---- timed region 1: kernel-only, state resident in HBM.  Working set (68 B state + 128 B piece slots + 4 KB
-    # history ring per env = 2.2 GB at 524,288 envs) is far larger than the 126 MB L2: no flush needed.
+    # ---- timed region 1: kernel-only, state resident in HBM.  Working set (72 B state + 128 B piece slots + 8 KB
+    # repetition table per env = 4.4 GB at 524,288 envs) is far larger than the 126 MB L2: no flush needed.
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -285,7 +285,7 @@ def main():
     # ---- roofline of the dominant kernel (k_env_step<sampled>): algorithmic bytes per env step, SURVEY.md 8(d):
     # 40 B state read + 40 B state write + 4 B action + 4 B reward + 1 B done + 8 B history append + 8 B x W scanned
     # W = mean repetition window (plies since the last pawn move / capture) the algorithm has to cover; the kernel
-    # reads far fewer ring entries (Bloom pre-filter, "hist_scanned") -- the algorithmic figure stays the survey's.
+    # reads about one hash-table entry per ply instead -- the algorithmic figure stays the survey's.
     W = st["hist_window"] / max(1, st["plies"])
     bytes_per_step = 97.0 + 8.0 * W
     # the step kernel is the only kernel in the timed region; one launch runs up to 64 consecutive steps
@@ -314,7 +314,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD % N, "envs_per_gpu": N, "total_envs": world * N, "burn_in_steps": args.burn_in,
-                   "l2": "inputs larger than L2 (2.2 GB resident state per GPU vs 126 MB L2), no flush"},
+                   "l2": "inputs larger than L2 (4.4 GB resident state per GPU vs 126 MB L2), no flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N, "d2h_bytes_per_step": 2 * N,
                 "steps": e2e_steps, "launches": e2e_launches,
                 "api": "PipelinedChessEnv.send_words / recv (gcb_env_step_index_packed + gcb_env_wait): uint16 random words "
@@ -427,8 +427,8 @@ def main():
         torch.cuda.synchronize()
         line["config_65536_envs"] = {"value": 65536 * args.steps / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT}
         small.close()
-        # ---- BASELINE.json configs[4]: repetition / promotion-heavy endgames, 512-slot Zobrist ring, 1M envs (the regime in
-        # which the repetition windows are long: mean window ~80 plies, ~13 ring entries actually read per ply)
+        # ---- BASELINE.json configs[4]: repetition / promotion-heavy endgames, 512-slot Zobrist-hash history, 1M envs (the
+        # regime in which the repetition windows are long: mean window ~80 plies)
         from gym_chess_b200.boards import endgame_boards
         eg = BatchedChessEnv(1 << 20, opponent="none", seed=5, device=local_rank, initial_boards=endgame_boards(), moves_max=250,
                              history_cap=512)
@@ -442,7 +442,7 @@ def main():
         egs = eg.stats()
         line["config_endgames_1M_envs"] = {"value": (1 << 20) * 200 / (ev0.elapsed_time(ev1) * 1e-3), "unit": UNIT,
                                            "mean_hist_window": egs["hist_window"] / max(1, egs["plies"]),
-                                           "ring_entries_read_per_ply": egs["hist_scanned"] / max(1, egs["plies"]),
+                                           "extra_table_probes_per_ply": egs["hist_scanned"] / max(1, egs["plies"]),
                                            "repetitions": egs["repetitions"], "history_cap": 512}
         eg.close()
         # ---- BASELINE.json configs[0]: the reference's own CPU-runnable case -- a single env, random-vs-random self-play,

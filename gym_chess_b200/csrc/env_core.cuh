@@ -8,9 +8,8 @@
 //   meta[N]  u64                       8 B   stm | rights | check flags | done | castle bits | n_legal |
 //                                            move_count | step_in_episode | hist_len
 //   zkey[N]  u64                       8 B   Zobrist key of the current board (board only)
-//   bloom[8][N] u64                   64 B   two 256-bit Bloom filters over the repetition window: key seen once / seen
-//                                            twice (one word of each touched per ply); the ring is only scanned when the
-//                                            second one hits
+//   gen[N]   u32                       4 B   generation of the repetition window (bumped by every irreversible ply and
+//                                            every new episode): table entries of older generations are dead
 //   episode[N] u32                     4 B
 //   cnt[N]   ulonglong2               16 B   byte r = number of legal targets of the r-th own piece (r < 16): the
 //                                            uniform draw over the ordered list finds its piece from this one record
@@ -19,8 +18,9 @@
 //                                            targets of the r-th own piece of the side to move (ascending square
 //                                            order = the reference's scan order); castles are two bits of meta.
 //                                            The ordered action list is a pure decode of (board, slots).
-//   hist[H][N] u64                           Zobrist ring; slot = global tick * plies-per-step + k, so that
-//                                            appends and window scans are coalesced across envs
+//   rep[N][H] ulonglong2                     the Zobrist-hash history of the repetition window as an open-addressing
+//                                            table: {key, generation << 2 | count}; slot = key bits, linear probing;
+//                                            one 16-byte entry read and written per ply
 #pragma once
 #include "chess_core.cuh"
 
@@ -87,11 +87,11 @@ struct EnvView {
     ulonglong2* bb23;
     u64* meta;
     u64* zkey;
-    u64* bloom;  // [8][N]: words 0-3 "key seen once", 4-7 "seen twice" (two 256-bit Bloom filters, one word touched per ply)
+    u32* gen;         // [N] generation of the current repetition window
+    ulonglong2* rep;  // [N][H] {key, generation << 2 | count}: the window's keys, open addressing (H = history_cap slots)
     u32* episode;
     ulonglong2* cnt;
     u64* tgt;
-    u64* hist;
     const ulonglong2* t_bb01;
     const ulonglong2* t_bb23;
     const u64* t_meta;
@@ -112,6 +112,7 @@ struct EnvRegs {
     u64 zk, cnt_lo, cnt_hi;
     u32 rights, chk, castle;  // chk bit0 white checked, bit1 black checked; castle bit0 queen side, bit1 king side
     int stm_black, done, n_legal, move_count, step, hist_len;
+    u32 gen;
 };
 
 GCB_HD void unpack_meta(u64 m, EnvRegs& s) {
@@ -239,22 +240,39 @@ struct StepStats {
 #define SF_HISTOVF (1u << 10)
 #define SF_SLOTOVF (1u << 13)
 
-// history ring bookkeeping: `cursor` = next slot of this tick; hist_len = length of the contiguous
-// window of slots behind the cursor that may hold an equal board (reset by irreversible plies)
-struct HistCursor {
-    u64 base;    // tick * pps
-    int cursor;  // 0..pps
-};
-
-GCB_HD void hist_skip_to(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int k, StepStats& st) {
-    while (hc.cursor < k) {
-        if (s.hist_len > 0) {
-            GCB_STS(&v.hist[((hc.base + hc.cursor) & (u64)v.hist_mask) * (u64)v.N + e], 0ULL);  // "no ply in this slot"
-            if (s.hist_len < v.hist_mask) s.hist_len++;
-            else st.f += SF_HISTOVF;
-        }
-        hc.cursor++;
+// Repetition table (the Zobrist-hash history of chess_v2.py:404-407's saved_boards, restricted to the window since the
+// last pawn move / capture: an older board cannot recur).  Open addressing over H = history_cap slots of 16 bytes per env,
+// slot = bits of the key, linear probing.  An entry is alive iff its generation is the env's current one: an irreversible
+// ply or a new episode bumps the generation and thereby empties the table without touching it.  One ply = one probe
+// sequence (almost always a single 16-byte load) + one store; nothing is read when the window is empty and nothing is
+// written by an irreversible ply.  Returns how often `key` has now occurred in the window, this ply included.
+GCB_HD int rep_lookup_insert(const EnvView& v, int e, const EnvRegs& s, u64 key, bool insert, StepStats& st) {
+    const unsigned mask = (unsigned)v.hist_mask;
+    unsigned i = (unsigned)(key >> 24) & mask;
+    const u64 live_tag = (u64)s.gen << 2;
+    // env-major: the H entries of an env are contiguous (16 * H bytes), so the 32 envs of a warp touch one small span
+    ulonglong2* const tab = v.rep + (size_t)e * ((size_t)mask + 1);
+    if (s.hist_len == 0) {  // empty window: every entry is dead, the first slot is free
+        if (insert) GCB_STS(&tab[i], make_ulonglong2(key, live_tag | 1ULL));
+        return 1;
     }
+    for (unsigned probes = 0; probes <= mask; probes++, i = (i + 1) & mask) {
+        ulonglong2* const p = &tab[i];
+        const ulonglong2 en = GCB_LDS(p);
+        const bool alive = (en.y >> 2) == (u64)s.gen && (en.y & 3ULL) != 0;
+        if (!alive) {
+            if (insert) GCB_STS(p, make_ulonglong2(key, live_tag | 1ULL));
+            return 1;
+        }
+        if (en.x == key) {
+            const u64 c = (en.y & 3ULL) < 3ULL ? (en.y & 3ULL) + 1ULL : 3ULL;
+            if (insert) GCB_STS(p, make_ulonglong2(key, live_tag | c));
+            return (int)c;
+        }
+        st.scan++;  // a further probe
+    }
+    st.f += SF_HISTOVF;  // the window has outgrown the table: this ply is not recorded (a later repetition of it can be missed)
+    return 1;
 }
 
 #ifndef GCB_SWAR_PICK
@@ -335,84 +353,29 @@ GCB_HD bool action_is_legal(const SlotRef& sr, const EnvRegs& s, int action) {
 
 
 
-#if defined(__CUDA_ARCH__)
-// Ring scan, warp-cooperative: a scan is needed by few lanes at a time (the "seen twice" filter hit) but it is long
-// (the whole repetition window, up to hundreds of entries), so the lanes that are executing this ply together take the
-// scans one owner at a time and split each window among themselves; the owner receives the count of entries equal to
-// its key.  Opportunistic grouping (__activemask): whatever set of lanes arrives here together cooperates.
-__device__ __forceinline__ int coop_ring_count(const EnvView& v, bool need, int e, u64 cur, int len, u64 key) {
-    const unsigned mask = __activemask();
-    unsigned todo = __ballot_sync(mask, need);
-    if (!todo) return 0;
-    const int lane = threadIdx.x & 31;
-    const int nact = __popc(mask), myrank = __popc(mask & ((1u << lane) - 1u));
-    int mine = 0;
-    while (todo) {
-        const int owner = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int oe = __shfl_sync(mask, e, owner), olen = __shfl_sync(mask, len, owner);
-        const u64 ocur = __shfl_sync(mask, cur, owner), okey = __shfl_sync(mask, key, owner);
-        int c = 0;
-        for (int j = myrank + 1; j <= olen; j += nact)
-            c += (GCB_LDS(&v.hist[((ocur - (u64)j) & (u64)v.hist_mask) * (u64)v.N + oe]) == okey);
-        const int total = __reduce_add_sync(mask, c);
-        if (lane == owner) mine = total;
-    }
-    return mine;
-}
-#endif
-
 // One ply = player_move (chess_v2.py:393-412: engine.next_state + repetition count on the PRE-move
 // board) + the state setter (315-323) + switch_player (296-299) + get_possible_moves for the new
 // side to move (573-582).  apply=false only switches the side and regenerates (BLACK-agent reset
 // when White has no move).  Returns the ply reward.
 template <class G>
-GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, HistCursor& hc, int slot, int action, bool apply, bool* rep,
+GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, int action, bool apply, bool* rep,
                            StepStats& st, CountBytes* scratch, const SlotRef& sr, const G& geo) {
     int r = 0;
     *rep = false;
     if (apply) {
-        hist_skip_to(v, e, s, hc, slot, st);
-        const u64 key = hist_key(s.zk);
-        const u64 cur = hc.base + slot;
-        // repetition count of the pre-move board over the reversible window.  The ring is read only when the
-        // "seen twice" Bloom word says this key may already have occurred twice (no false negatives).
-        // Two 256-bit Bloom filters per env ("seen once", "seen twice"), one 64-bit word of each touched per ply.
-        const u64 bbit = 1ULL << ((key >> 58) & 63);
-        u64* const b1 = v.bloom + (size_t)((key >> 56) & 3) * (size_t)v.N + e;
-        u64* const b2 = b1 + 4 * (size_t)v.N;
-        u64 seen1 = 0, seen2 = 0;
-        if (s.hist_len > 0) seen1 = GCB_LDS(b1), seen2 = GCB_LDS(b2);  // (an empty window: the words are stale)
-        const bool need_scan = (seen2 & bbit) != 0;
-        int cnt = 0;
-#if defined(__CUDA_ARCH__)
-        cnt = coop_ring_count(v, need_scan, e, cur, s.hist_len, key);
-#else
-        if (need_scan)
-            for (int j = 1; j <= s.hist_len; j++) cnt += (v.hist[((cur - (u64)j) & (u64)v.hist_mask) * (u64)v.N + e] == key);
-#endif
-        if (need_scan) st.scan += s.hist_len;
-        st.window += s.hist_len;
-        *rep = cnt >= 2;  // saved_boards[key] reaches 3 with this ply
-        GCB_STS(&v.hist[(cur & (u64)v.hist_mask) * (u64)v.N + e], key);
-        hc.cursor = slot + 1;
-        const bool first_of_window = s.hist_len == 0;
-
+        const u64 key = hist_key(s.zk);  // the board BEFORE the move (chess_v2.py:404-407)
         u32 rights = mask_rights(s.b, s.rights);  // engine entry masks by the INPUT board (Q21)
         int status;
         bool irr;
         r = apply_action(s.b, rights, !s.stm_black, action, &status, &irr, &s.zk, v.zob);
         s.rights = rights;
+        st.window += s.hist_len;
+        // saved_boards[key] += 1; done when it reaches 3.  An irreversible ply only looks the key up: its window dies with it.
+        *rep = rep_lookup_insert(v, e, s, key, !irr, st) >= 3;
         if (irr) {
-            s.hist_len = 0;  // the window restarts empty: its Bloom words are rebuilt by the next reversible ply
+            s.hist_len = 0, s.gen++;  // the window restarts empty
         } else {
-            if (first_of_window) {  // first key of a new window: every word of both filters starts from zero
-                for (int w = 0; w < 8; w++) GCB_STS(v.bloom + (size_t)w * (size_t)v.N + e, 0ULL);
-            }
-            if (seen1 & bbit) GCB_STS(b2, seen2 | bbit);
-            GCB_STS(b1, seen1 | bbit);
-            if (s.hist_len < v.hist_mask) s.hist_len++;
-            else st.f += SF_HISTOVF;
+            if (s.hist_len < 0x3FF) s.hist_len++;  // (10-bit field of meta; statistics only)
         }
     }
     s.stm_black ^= 1;
@@ -444,7 +407,7 @@ struct StepIO {
     uint8_t* flags;
     int32_t* act_out;
     int32_t* bot_out;
-    u64 tick;
+    u64 tick;            // launch counter (kept for the snapshot ABI; the repetition table needs no clock)
     int ep_inc;
     int e_begin, e_end;  // env range of this launch (host-buffer steps are pipelined in chunks)
     int nsteps;          // MODE_SAMPLED: consecutive steps run by ONE launch (envs are independent: no grid-wide sync needed)
@@ -467,6 +430,7 @@ GCB_HD void env_load(const EnvView& v, int e, EnvRegs& s, u32& ep) {
     unpack_meta(GCB_LDS(&v.meta[e]), s);
     s.zk = GCB_LDS(&v.zkey[e]);
     ep = GCB_LDS(&v.episode[e]);
+    s.gen = GCB_LDS(&v.gen[e]);
 }
 GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
     GCB_STS(&v.bb01[e], make_ulonglong2(s.b.t0, s.b.t1));
@@ -475,6 +439,7 @@ GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
     GCB_STS(&v.meta[e], pack_meta(s));
     GCB_STS(&v.zkey[e], s.zk);
     GCB_STS(&v.episode[e], ep);
+    GCB_STS(&v.gen[e], s.gen);
 }
 
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step), state in registers
@@ -483,19 +448,14 @@ GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
 template <int MODE, bool SELFPLAY = false, class G>
 GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch,
                           const SlotRef& sr, const G& geo) {
-    const int v_pps = SELFPLAY ? 1 : v.pps;
     const bool v_bot = SELFPLAY ? false : v.opponent == 1, v_agent_black = SELFPLAY ? false : v.agent_black != 0;
     const u32 genv = v.env_offset + (u32)e;
-    HistCursor hc;
-    hc.base = io.tick * (u64)v_pps, hc.cursor = 0;
-
     int action = ACT_RESIGN, bot_action = -1, R = 0, phase;
     u32 fl = 0;
     bool d_out = false, agent_ply = false;
     const int n0 = s.n_legal;
     const bool was_done = s.done, capped = s.move_count > v.moves_max;
     const u32 step_idx = (u32)s.step;
-
     if (MODE == MODE_RESET) {
         phase = PH_FINAL;
     } else {
@@ -529,7 +489,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
     }
 
     bool do_apply = true;
-    int slot = 0, cur = action;  // cur = the action of the ply being executed
+    int cur = action;  // cur = the action of the ply being executed
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -564,6 +524,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
                 unpack_meta(v.t_meta[t], s);
                 s.zk = v.t_zkey[t];
+                s.gen++;  // a new episode: the repetition table starts empty
                 {
                     ulonglong2 ct = v.t_cnt[t];
                     s.cnt_lo = ct.x, s.cnt_hi = ct.y;
@@ -584,7 +545,6 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                     } else {
                         do_apply = false;
                     }
-                    slot = v_pps - 1;
                     phase = PH_RESETBOT;
                     continue;
                 }
@@ -593,7 +553,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             continue;
         }
         bool rep;
-        const int r = ply_and_movegen(v, e, s, hc, slot, cur, do_apply, &rep, st, scratch, sr, geo);
+        const int r = ply_and_movegen(v, e, s, cur, do_apply, &rep, st, scratch, sr, geo);
         if (do_apply) st.f += SF_PLIES;
         const bool mate = s.n_legal == 0 && stm_checked(s);
         if (phase == PH_AGENT) {
@@ -606,7 +566,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 if (s.n_legal > 0) {  // chess_v2.py:277-288
                     u32 u = philox_draw(v.seed, genv, ep, step_idx, 1u);
                     bot_action = action_at(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
-                    cur = bot_action, slot = 1, phase = PH_BOT;
+                    cur = bot_action, phase = PH_BOT;
                     continue;
                 }
                 // bot without moves and not in check: the reference raises TypeError (Q9); stop here
@@ -627,7 +587,6 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             phase = PH_END;
         }
     }
-    hist_skip_to(v, e, s, hc, v_pps, st);
     if (MODE != MODE_RESET && io.bot_out) io.bot_out[e] = bot_action;
 }
 
@@ -643,7 +602,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
 // A new episode of env e from an arbitrary position in the reference's wire format (the `state` setter of
 // chess_v2.py:315-323 + engine.update_state + get_possible_moves for the side to move): rights masked by king presence,
 // both check flags, legal set, empty repetition window, episode counter + 1.
-GCB_HD void env_import_one(const EnvView& v, int e, const int8_t* board, int player, u32 rights, int move_count, u64 tick,
+GCB_HD void env_import_one(const EnvView& v, int e, const int8_t* board, int player, u32 rights, int move_count,
                            StepStats& st, CountBytes* scratch) {
     EnvRegs s;
     u32 ep;
@@ -652,27 +611,11 @@ GCB_HD void env_import_one(const EnvView& v, int e, const int8_t* board, int pla
     s.zk = zobrist_full(s.b);
     s.rights = mask_rights(s.b, rights);
     s.done = 0, s.move_count = move_count, s.step = 0, s.hist_len = 0;
+    s.gen++;  // a new episode: the repetition table starts empty
     s.stm_black = player < 0 ? 0 : 1;  // ply_and_movegen(apply = false) flips the side, then generates for it
-    HistCursor hc;
-    hc.base = tick * (u64)v.pps, hc.cursor = 0;
     bool rep;
-    ply_and_movegen(v, e, s, hc, 0, 0, false, &rep, st, scratch, resident_slots(v, e), GeomGlobal());
+    ply_and_movegen(v, e, s, 0, false, &rep, st, scratch, resident_slots(v, e), GeomGlobal());
     env_store(v, e, s, ep + 1u);
-}
-
-// Launches that do not step every env (masked reset / import) still consume a ring tick: the envs they leave alone
-// mark the tick's slots "no ply" so that their repetition window stays contiguous in the ring.
-GCB_HD void env_idle_tick(const EnvView& v, int e, u64 tick) {
-    EnvRegs s;
-    unpack_meta(v.meta[e], s);
-    s.zk = 0, s.cnt_lo = s.cnt_hi = 0;  // (not touched: only meta is rewritten)
-    if (s.hist_len == 0) return;
-    HistCursor hc;
-    hc.base = tick * (u64)v.pps, hc.cursor = 0;
-    StepStats st;
-    st.clear();
-    hist_skip_to(v, e, s, hc, v.pps, st);
-    v.meta[e] = pack_meta(s);
 }
 
 // initial state of one template board (ChessEnvV2.reset up to the first movegen, chess_v2.py:188-206)

@@ -203,10 +203,7 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_
     const int e = io.e_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool active = e < io.e_end;
-    if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) {
-        env_idle_tick(v, e, io.tick);  // a masked reset leaves this env alone, but the launch consumes a ring tick
-        active = false;
-    }
+    if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;  // masked reset
     // Sampled self-play runs `nsteps` consecutive steps in one launch: every env only depends on its own previous step,
     // so a block simply keeps stepping its envs -- no launch gap, no wave tail between steps.
     const int nsteps = MODE == MODE_SAMPLED ? io.nsteps : 1;
@@ -307,10 +304,7 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_import(EnvView v, const int8_
     __shared__ CountBytes s_counts[GCB_BLOCK];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= v.N) return;
-    if (mask && !mask[e]) {
-        env_idle_tick(v, e, tick);
-        return;
-    }
+    if (mask && !mask[e]) return;
     alignas(16) int8_t m[64];
     const int4* src = reinterpret_cast<const int4*>(boards + (size_t)e * 64);
 #pragma unroll
@@ -319,7 +313,7 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_import(EnvView v, const int8_
     const u32 rights = (q.x ? RT_WK : 0) | (q.y ? RT_WQ : 0) | (q.z ? RT_BK : 0) | (q.w ? RT_BQ : 0);
     StepStats st;
     st.clear();
-    env_import_one(v, e, m, players[e], rights, move_count ? move_count[e] : 0, tick, st, &s_counts[threadIdx.x]);
+    env_import_one(v, e, m, players[e], rights, move_count ? move_count[e] : 0, st, &s_counts[threadIdx.x]);
 }
 
 __global__ void k_init_zobrist(u64* tab) {
@@ -649,8 +643,8 @@ static int launch_step(gcb_env* env, const void* in, int32_t* reward, uint8_t* d
 extern "C" int gcb_env_destroy(gcb_env* env) {
     if (!env) return GCB_OK;
     cudaSetDevice(env->cfg.device);
-    cudaFree(env->v.bb01), cudaFree(env->v.bb23), cudaFree(env->v.meta), cudaFree(env->v.zkey), cudaFree(env->v.bloom), cudaFree(env->v.cnt), cudaFree(env->t_cnt);
-    cudaFree(env->v.episode), cudaFree(env->v.tgt), cudaFree(env->v.hist), cudaFree(env->v.stats), cudaFree(env->v.stat_rows);
+    cudaFree(env->v.bb01), cudaFree(env->v.bb23), cudaFree(env->v.meta), cudaFree(env->v.zkey), cudaFree(env->v.gen), cudaFree(env->v.cnt), cudaFree(env->t_cnt);
+    cudaFree(env->v.episode), cudaFree(env->v.tgt), cudaFree(env->v.rep), cudaFree(env->v.stats), cudaFree(env->v.stat_rows);
     cudaFree(env->t_bb01), cudaFree(env->t_bb23), cudaFree(env->t_meta), cudaFree(env->t_zkey), cudaFree(env->t_tgt), cudaFree(env->zob);
     cudaFree(env->d_in), cudaFree(env->d_reward), cudaFree(env->d_done), cudaFree(env->d_flags);
     for (int c = 0; c < 8; c++)
@@ -709,12 +703,12 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     ALLOC(v.bb23, (size_t)N * 16);
     ALLOC(v.meta, (size_t)N * 8);
     ALLOC(v.zkey, (size_t)N * 8);
-    ALLOC(v.bloom, (size_t)N * 64);
+    ALLOC(v.gen, (size_t)N * 4);
     ALLOC(v.cnt, (size_t)N * 16);
     ALLOC(env->t_cnt, (size_t)T * 16);
     ALLOC(v.episode, (size_t)N * 4);
     ALLOC(v.tgt, (size_t)N * S * 8);
-    ALLOC(v.hist, (size_t)N * H * 8);
+    ALLOC(v.rep, (size_t)N * H * 16);
     ALLOC(v.stats, ST_COUNT * 8);
     ALLOC(v.stat_rows, (size_t)((N + 31) / 32) * ST_COUNT * 8);
     ALLOC(env->t_bb01, (size_t)T * 16);
@@ -747,7 +741,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
             cudaMemset(v.stat_rows, 0, (size_t)((N + 31) / 32) * ST_COUNT * 8) != cudaSuccess || cudaMemset(v.episode, 0, (size_t)N * 4) != cudaSuccess ||
             cudaMemset(v.meta, 0, (size_t)N * 8) != cudaSuccess || cudaMemset(v.bb01, 0, (size_t)N * 16) != cudaSuccess ||
             cudaMemset(v.bb23, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.zkey, 0, (size_t)N * 8) != cudaSuccess ||
-            cudaMemset(v.bloom, 0, (size_t)N * 64) != cudaSuccess || cudaMemset(v.cnt, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
+            cudaMemset(v.gen, 0, (size_t)N * 4) != cudaSuccess || cudaMemset(v.rep, 0, (size_t)N * H * 16) != cudaSuccess || cudaMemset(v.cnt, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
             cudaMemset(env->t_tgt, 0, (size_t)T * S * 8) != cudaSuccess) {
             rc = fail(GCB_E_CUDA, "cudaMemcpy/cudaMemset", "env init");
             break;
@@ -1036,8 +1030,8 @@ static int snap_parts(gcb_env* env, SnapPart* p) {
     const size_t N = (size_t)env->v.N, S = (size_t)env->v.slots, H = (size_t)env->v.hist_mask + 1;
     int k = 0;
     p[k++] = {env->v.bb01, N * 16}, p[k++] = {env->v.bb23, N * 16}, p[k++] = {env->v.meta, N * 8}, p[k++] = {env->v.zkey, N * 8};
-    p[k++] = {env->v.bloom, N * 64}, p[k++] = {env->v.cnt, N * 16}, p[k++] = {env->v.episode, N * 4};
-    p[k++] = {env->v.tgt, N * S * 8}, p[k++] = {env->v.hist, N * H * 8};
+    p[k++] = {env->v.gen, N * 4}, p[k++] = {env->v.cnt, N * 16}, p[k++] = {env->v.episode, N * 4};
+    p[k++] = {env->v.tgt, N * S * 8}, p[k++] = {env->v.rep, N * H * 16};
     p[k++] = {env->v.stat_rows, ((N + 31) / 32) * ST_COUNT * 8};
     return k;
 }

@@ -123,7 +123,8 @@ typedef struct {
     int32_t auto_reset;     /* reset an env in the same step in which it terminates (done | cap | wedged) */
     int32_t piece_slots;    /* slots of the per-env legal set (one 64-bit target set per own piece of the side to
                                move); 0 = auto = max(16, most pieces of one colour on any initial board) */
-    int32_t history_cap;    /* slots of the per-env Zobrist ring (power of two; default 512 when 0) */
+    int32_t history_cap;    /* slots of the per-env repetition table = longest repetition window it can hold
+                               (power of two in [8, 1024]; default 512 when 0); 16 bytes per slot */
     int32_t moves_max;      /* 149 in the reference (chess_v2.py:141); <0 selects 149 */
     int32_t n_templates;    /* number of initial boards (0 = the default start position) */
     const int8_t *template_boards; /* HOST int8[n_templates][64]; env i starts from template (global id % n) */
@@ -214,8 +215,8 @@ int gcb_env_piece_slots(gcb_env *env, uint64_t **d_slots, int32_t *n_slots);
 int gcb_env_positions(gcb_env *env, gcb_positions *out);
 
 /* Checkpoint / resume (the reference has none: its whole env state is the `state` dict + saved_boards + counters).  A
- * snapshot is the concatenation of the resident arrays (positions, meta, keys, Bloom words, legal set, Zobrist ring,
- * statistics rows) in ONE device buffer of gcb_env_snapshot_bytes() bytes plus the ring tick; restoring it into an env
+ * snapshot is the concatenation of the resident arrays (positions, meta, keys, generations, legal set, repetition
+ * tables, statistics rows) in ONE device buffer of gcb_env_snapshot_bytes() bytes plus the launch counter `tick`; restoring it into an env
  * created with the same configuration resumes bit-identically (same Philox counters). */
 int gcb_env_snapshot_bytes(gcb_env *env, uint64_t *bytes);
 int gcb_env_snapshot(gcb_env *env, void *d_buf, uint64_t *tick, void *stream);
@@ -223,8 +224,8 @@ int gcb_env_restore(gcb_env *env, const void *d_buf, uint64_t tick, void *stream
 
 /* episode statistics accumulated on the device since the last gcb_env_stats_reset:
  * out uint64[16] = steps, plies, episodes, mates, repetitions, caps, wedged, invalid, reward_sum (two's complement
- * int64), legal_sum, in_check, hist_overflow, slot_overflow, hist_scanned (ring entries actually read by the
- * repetition scans), hist_window (sum over plies of the repetition window length), 0.   Synchronises the stream. */
+ * int64), legal_sum, in_check, hist_overflow, slot_overflow, hist_scanned (repetition-table probes beyond
+ * the first one of a ply), hist_window (sum over plies of the repetition window length), 0.   Synchronises the stream. */
 int gcb_env_stats(gcb_env *env, uint64_t *out16, void *stream);
 int gcb_env_stats_reset(gcb_env *env, void *stream);
 /* device pointer to the 16 counters (for an NCCL reduce by the caller); the totals are brought up to date by a small

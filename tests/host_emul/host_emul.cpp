@@ -102,8 +102,8 @@ struct EmulEnv {
 
 void emul_env_destroy(EmulEnv* E) {
     if (!E) return;
-    free(E->v.bb01), free(E->v.bb23), free(E->v.meta), free(E->v.zkey), free(E->v.bloom), free(E->v.cnt), free(E->t_cnt), free(E->v.episode), free(E->v.tgt);
-    free(E->v.hist), free(E->v.stats), free(E->t_bb01), free(E->t_bb23), free(E->t_meta), free(E->t_zkey), free(E->t_tgt), free(E->zob);
+    free(E->v.bb01), free(E->v.bb23), free(E->v.meta), free(E->v.zkey), free(E->v.gen), free(E->v.cnt), free(E->t_cnt), free(E->v.episode), free(E->v.tgt);
+    free(E->v.rep), free(E->v.stats), free(E->t_bb01), free(E->t_bb23), free(E->t_meta), free(E->t_zkey), free(E->t_tgt), free(E->zob);
     free(E);
 }
 
@@ -117,8 +117,8 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
     EnvView& v = E->v;
     v.bb01 = (ulonglong2*)calloc(N, 16), v.bb23 = (ulonglong2*)calloc(N, 16);
     v.meta = (u64*)calloc(N, 8), v.zkey = (u64*)calloc(N, 8), v.episode = (u32*)calloc(N, 4);
-    v.bloom = (u64*)calloc(N, 64), v.cnt = (ulonglong2*)calloc(N, 16), E->t_cnt = (ulonglong2*)calloc(T, 16);
-    v.tgt = (u64*)calloc((size_t)N * slots, 8), v.hist = (u64*)calloc((size_t)N * hist_cap, 8);
+    v.gen = (u32*)calloc(N, 4), v.cnt = (ulonglong2*)calloc(N, 16), E->t_cnt = (ulonglong2*)calloc(T, 16);
+    v.tgt = (u64*)calloc((size_t)N * slots, 8), v.rep = (ulonglong2*)calloc((size_t)N * hist_cap, 16);
     v.stats = (u64*)calloc(ST_COUNT, 8);
     E->t_bb01 = (ulonglong2*)calloc(T, 16), E->t_bb23 = (ulonglong2*)calloc(T, 16);
     E->t_meta = (u64*)calloc(T, 8), E->t_zkey = (u64*)calloc(T, 8), E->t_tgt = (u64*)calloc((size_t)T * slots, 8);
@@ -158,7 +158,6 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
         case 2: env_step_one<MODE_SAMPLED>(E->v, io, e, st, &scratch); break;
         default:
             if (!in || ((const uint8_t*)in)[e]) env_step_one<MODE_RESET>(E->v, io, e, st, &scratch);
-            else env_idle_tick(E->v, e, io.tick);
         }
         if (mode != 3)
             for (int k = 0; k < ST_USED; k++) E->v.stats[k] += (u64)(long long)st.get(k);
@@ -169,16 +168,13 @@ void emul_env_import(EmulEnv* E, const int8_t* boards, const int8_t* players, co
                      const uint8_t* mask) {
     StepStats st;
     CountBytes scratch;
-    const u64 tick = E->tick++;
+    E->tick++;
     for (int e = 0; e < E->v.N; e++) {
-        if (mask && !mask[e]) {
-            env_idle_tick(E->v, e, tick);
-            continue;
-        }
+        if (mask && !mask[e]) continue;
         const uint8_t* q = rights4 + (size_t)e * 4;
         u32 rights = (q[0] ? RT_WK : 0) | (q[1] ? RT_WQ : 0) | (q[2] ? RT_BK : 0) | (q[3] ? RT_BQ : 0);
         st.clear();
-        env_import_one(E->v, e, boards + (size_t)e * 64, players[e], rights, move_count ? move_count[e] : 0, tick, st, &scratch);
+        env_import_one(E->v, e, boards + (size_t)e * 64, players[e], rights, move_count ? move_count[e] : 0, st, &scratch);
     }
 }
 

@@ -14,5 +14,5 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 torch.cuda.synchronize(); e0.record(); env.step_sampled(200); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 200
 s = env.stats()
-print("endgames: %d envs, %.3f ms/step, %.3e env steps/s, mean window %.1f, ring entries read per ply %.2f, repetitions %d"
+print("endgames: %d envs, %.3f ms/step, %.3e env steps/s, mean window %.1f, extra table probes per ply %.2f, repetitions %d"
       % (N, ms, N / ms * 1e3, s["hist_window"] / s["plies"], s["hist_scanned"] / s["plies"], s["repetitions"]))
