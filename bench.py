@@ -175,8 +175,8 @@ def main():
     env.step_sampled(args.burn_in)
     env.step_sampled(args.warmup)
     env.reset_stats()
-    # ---- timed region 1: kernel-only, state resident in HBM.  Working set (72 B state + 128 B piece slots + 8 KB
-    # repetition table per env = 4.4 GB at 524,288 envs) is far larger than the 126 MB L2: no flush needed.
+    # ---- timed region 1: kernel-only, state resident in HBM.  Working set (72 B state + 128 B piece slots + 16 KB
+    # repetition table per env = 8.7 GB at 524,288 envs) is far larger than the 126 MB L2: no flush needed.
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -314,7 +314,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD % N, "envs_per_gpu": N, "total_envs": world * N, "burn_in_steps": args.burn_in,
-                   "l2": "inputs larger than L2 (4.4 GB resident state per GPU vs 126 MB L2), no flush"},
+                   "l2": "inputs larger than L2 (8.7 GB resident state per GPU vs 126 MB L2), no flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N, "d2h_bytes_per_step": 2 * N,
                 "steps": e2e_steps, "launches": e2e_launches,
                 "api": "PipelinedChessEnv.send_words / recv (gcb_env_step_index_packed + gcb_env_wait): uint16 random words "

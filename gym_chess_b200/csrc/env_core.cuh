@@ -18,7 +18,7 @@
 //                                            targets of the r-th own piece of the side to move (ascending square
 //                                            order = the reference's scan order); castles are two bits of meta.
 //                                            The ordered action list is a pure decode of (board, slots).
-//   rep[N][H] ulonglong2                     the Zobrist-hash history of the repetition window as an open-addressing
+//   rep[N][2H] ulonglong2                    the Zobrist-hash history of the repetition window as an open-addressing
 //                                            table: {key, generation << 2 | count}; slot = key bits, linear probing;
 //                                            one 16-byte entry read and written per ply
 #pragma once
@@ -88,7 +88,7 @@ struct EnvView {
     u64* meta;
     u64* zkey;
     u32* gen;         // [N] generation of the current repetition window
-    ulonglong2* rep;  // [N][H] {key, generation << 2 | count}: the window's keys, open addressing (H = history_cap slots)
+    ulonglong2* rep;  // [N][2H] {key, generation << 2 | count}: the window's keys, open addressing (H = history_cap; hist_mask = 2H - 1)
     u32* episode;
     ulonglong2* cnt;
     u64* tgt;
@@ -246,6 +246,9 @@ struct StepStats {
 // ply or a new episode bumps the generation and thereby empties the table without touching it.  One ply = one probe
 // sequence (almost always a single 16-byte load) + one store; nothing is read when the window is empty and nothing is
 // written by an irreversible ply.  Returns how often `key` has now occurred in the window, this ply included.
+// The table has 2 * history_cap slots, so while the window fits history_cap the load factor stays <= 1/2 and a probe
+// sequence of 128 slots cannot be exhausted in practice (expected length 1.5 - 2.5).
+#define GCB_REP_MAX_PROBES 128
 GCB_HD int rep_lookup_insert(const EnvView& v, int e, const EnvRegs& s, u64 key, bool insert, StepStats& st) {
     const unsigned mask = (unsigned)v.hist_mask;
     unsigned i = (unsigned)(key >> 24) & mask;
@@ -256,7 +259,8 @@ GCB_HD int rep_lookup_insert(const EnvView& v, int e, const EnvRegs& s, u64 key,
         if (insert) GCB_STS(&tab[i], make_ulonglong2(key, live_tag | 1ULL));
         return 1;
     }
-    for (unsigned probes = 0; probes <= mask; probes++, i = (i + 1) & mask) {
+    const unsigned home = i;
+    for (unsigned probes = 0; probes <= mask && probes < GCB_REP_MAX_PROBES; probes++, i = (i + 1) & mask) {
         ulonglong2* const p = &tab[i];
         const ulonglong2 en = GCB_LDS(p);
         const bool alive = (en.y >> 2) == (u64)s.gen && (en.y & 3ULL) != 0;
@@ -271,7 +275,11 @@ GCB_HD int rep_lookup_insert(const EnvView& v, int e, const EnvRegs& s, u64 key,
         }
         st.scan++;  // a further probe
     }
-    st.f += SF_HISTOVF;  // the window has outgrown the table: this ply is not recorded (a later repetition of it can be missed)
+    // The window has outgrown the table (only an uncapped BLACK-agent episode can get here): the key replaces whatever
+    // sits in its home slot -- replacing a live entry by a live entry keeps every probe chain intact -- so the most recent
+    // boards, the likely ones to recur, stay findable; the displaced board's later repetition can be missed.
+    st.f += SF_HISTOVF;
+    if (insert) GCB_STS(&tab[home], make_ulonglong2(key, live_tag | 1ULL));
     return 1;
 }
 

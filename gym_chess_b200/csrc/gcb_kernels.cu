@@ -708,7 +708,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     ALLOC(env->t_cnt, (size_t)T * 16);
     ALLOC(v.episode, (size_t)N * 4);
     ALLOC(v.tgt, (size_t)N * S * 8);
-    ALLOC(v.rep, (size_t)N * H * 16);
+    ALLOC(v.rep, (size_t)N * 2 * H * 16);  // twice history_cap slots: load factor <= 1/2 while the window fits
     ALLOC(v.stats, ST_COUNT * 8);
     ALLOC(v.stat_rows, (size_t)((N + 31) / 32) * ST_COUNT * 8);
     ALLOC(env->t_bb01, (size_t)T * 16);
@@ -730,7 +730,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     }
     v.t_bb01 = env->t_bb01, v.t_bb23 = env->t_bb23, v.t_meta = env->t_meta, v.t_zkey = env->t_zkey, v.t_tgt = env->t_tgt;
     v.zob = env->zob, v.t_cnt = env->t_cnt;
-    v.seed = cfg.seed, v.N = N, v.slots = S, v.hist_mask = H - 1, v.n_templates = T, v.env_offset = cfg.env_id_offset;
+    v.seed = cfg.seed, v.N = N, v.slots = S, v.hist_mask = 2 * H - 1, v.n_templates = T, v.env_offset = cfg.env_id_offset;
     v.moves_max = cfg.moves_max, v.opponent = cfg.opponent, v.agent_black = cfg.agent_black, v.auto_reset = cfg.auto_reset;
     v.pps = 1 + (cfg.opponent == 1 ? 1 : 0);  // ring slots per step: agent ply, bot ply (a reset-bot ply reuses the bot slot)
     int rc = GCB_OK;
@@ -741,7 +741,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
             cudaMemset(v.stat_rows, 0, (size_t)((N + 31) / 32) * ST_COUNT * 8) != cudaSuccess || cudaMemset(v.episode, 0, (size_t)N * 4) != cudaSuccess ||
             cudaMemset(v.meta, 0, (size_t)N * 8) != cudaSuccess || cudaMemset(v.bb01, 0, (size_t)N * 16) != cudaSuccess ||
             cudaMemset(v.bb23, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.zkey, 0, (size_t)N * 8) != cudaSuccess ||
-            cudaMemset(v.gen, 0, (size_t)N * 4) != cudaSuccess || cudaMemset(v.rep, 0, (size_t)N * H * 16) != cudaSuccess || cudaMemset(v.cnt, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
+            cudaMemset(v.gen, 0, (size_t)N * 4) != cudaSuccess || cudaMemset(v.rep, 0, (size_t)N * 2 * H * 16) != cudaSuccess || cudaMemset(v.cnt, 0, (size_t)N * 16) != cudaSuccess || cudaMemset(v.tgt, 0, (size_t)N * S * 8) != cudaSuccess ||
             cudaMemset(env->t_tgt, 0, (size_t)T * S * 8) != cudaSuccess) {
             rc = fail(GCB_E_CUDA, "cudaMemcpy/cudaMemset", "env init");
             break;

@@ -123,8 +123,9 @@ typedef struct {
     int32_t auto_reset;     /* reset an env in the same step in which it terminates (done | cap | wedged) */
     int32_t piece_slots;    /* slots of the per-env legal set (one 64-bit target set per own piece of the side to
                                move); 0 = auto = max(16, most pieces of one colour on any initial board) */
-    int32_t history_cap;    /* slots of the per-env repetition table = longest repetition window it can hold
-                               (power of two in [8, 1024]; default 512 when 0); 16 bytes per slot */
+    int32_t history_cap;    /* longest repetition window (plies since the last pawn move / capture) that is
+                               tracked exactly (power of two in [8, 1024]; default 512 when 0); the per-env hash
+                               table has twice as many 16-byte slots */
     int32_t moves_max;      /* 149 in the reference (chess_v2.py:141); <0 selects 149 */
     int32_t n_templates;    /* number of initial boards (0 = the default start position) */
     const int8_t *template_boards; /* HOST int8[n_templates][64]; env i starts from template (global id % n) */

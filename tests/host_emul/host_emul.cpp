@@ -118,14 +118,14 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
     v.bb01 = (ulonglong2*)calloc(N, 16), v.bb23 = (ulonglong2*)calloc(N, 16);
     v.meta = (u64*)calloc(N, 8), v.zkey = (u64*)calloc(N, 8), v.episode = (u32*)calloc(N, 4);
     v.gen = (u32*)calloc(N, 4), v.cnt = (ulonglong2*)calloc(N, 16), E->t_cnt = (ulonglong2*)calloc(T, 16);
-    v.tgt = (u64*)calloc((size_t)N * slots, 8), v.rep = (ulonglong2*)calloc((size_t)N * hist_cap, 16);
+    v.tgt = (u64*)calloc((size_t)N * slots, 8), v.rep = (ulonglong2*)calloc((size_t)N * 2 * hist_cap, 16);
     v.stats = (u64*)calloc(ST_COUNT, 8);
     E->t_bb01 = (ulonglong2*)calloc(T, 16), E->t_bb23 = (ulonglong2*)calloc(T, 16);
     E->t_meta = (u64*)calloc(T, 8), E->t_zkey = (u64*)calloc(T, 8), E->t_tgt = (u64*)calloc((size_t)T * slots, 8);
     E->zob = (u64*)calloc(GCB_ZOB_ENTRIES, 8);
     for (int i = 0; i < GCB_ZOB_ENTRIES; i++) fill_zobrist_entry(E->zob, i);
     v.t_bb01 = E->t_bb01, v.t_bb23 = E->t_bb23, v.t_meta = E->t_meta, v.t_zkey = E->t_zkey, v.t_tgt = E->t_tgt, v.zob = E->zob, v.t_cnt = E->t_cnt;
-    v.seed = seed, v.N = N, v.slots = slots, v.hist_mask = hist_cap - 1, v.n_templates = T, v.env_offset = env_offset;
+    v.seed = seed, v.N = N, v.slots = slots, v.hist_mask = 2 * hist_cap - 1, v.n_templates = T, v.env_offset = env_offset;
     v.moves_max = moves_max, v.opponent = opponent, v.agent_black = agent_black, v.auto_reset = auto_reset;
     v.pps = 1 + (opponent == 1);
     for (int i = 0; i < T; i++)
