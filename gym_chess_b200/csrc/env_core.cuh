@@ -201,6 +201,39 @@ struct TgtSink {
     }
 };
 
+// The same sink for a thread that KNOWS its env has at most 16 pieces of either colour and 16 plain (shared-memory)
+// slots: no bounds tests, no overflow bookkeeping (multi-step launches check this once per launch).
+struct TgtSinkFast {
+    u64* base;
+    unsigned N;
+    int dropped;
+    uint8_t* cb;
+    GCB_HD TgtSinkFast(const SlotRef& sr, CountBytes* scratch) : base(sr.base), N(sr.stride), dropped(0), cb(scratch->c) {
+        u64* z = reinterpret_cast<u64*>(scratch);
+        z[0] = 0, z[1] = 0;
+    }
+    GCB_HD void put(int r, u64 t) {
+        base[(unsigned)r * N] = t;
+        cb[r] = (uint8_t)gcb_popc(t);
+    }
+    GCB_HD u64 get(int r) const { return base[(unsigned)r * N]; }
+    GCB_HD void replace(int r, u64, u64 tnew) {
+        base[(unsigned)r * N] = tnew;
+        cb[r] = (uint8_t)gcb_popc(tnew);
+    }
+    GCB_HD u64 count_lo() const { return reinterpret_cast<const u64*>(cb)[0]; }
+    GCB_HD u64 count_hi() const { return reinterpret_cast<const u64*>(cb)[1]; }
+    GCB_HD int total() const {
+        u64 a = count_lo(), b = count_hi();
+        a = (a & 0x00FF00FF00FF00FFULL) + ((a >> 8) & 0x00FF00FF00FF00FFULL);
+        b = (b & 0x00FF00FF00FF00FFULL) + ((b >> 8) & 0x00FF00FF00FF00FFULL);
+        a += b;
+        a += a >> 32;
+        a += a >> 16;
+        return (int)(a & 0xFFFF);
+    }
+};
+
 // per-thread statistics of one step: the small counters live as bit fields of ONE register (fewer live registers in
 // the step kernel), the wide ones in four ints
 struct StepStats {
@@ -361,11 +394,14 @@ GCB_HD bool action_is_legal(const SlotRef& sr, const EnvRegs& s, int action) {
 
 
 
+template <bool FAST> struct SinkOf { typedef TgtSink type; };
+template <> struct SinkOf<true> { typedef TgtSinkFast type; };
+
 // One ply = player_move (chess_v2.py:393-412: engine.next_state + repetition count on the PRE-move
 // board) + the state setter (315-323) + switch_player (296-299) + get_possible_moves for the new
 // side to move (573-582).  apply=false only switches the side and regenerates (BLACK-agent reset
 // when White has no move).  Returns the ply reward.
-template <class G>
+template <bool FAST = false, class G>
 GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, int action, bool apply, bool* rep,
                            StepStats& st, CountBytes* scratch, const SlotRef& sr, const G& geo) {
     int r = 0;
@@ -389,7 +425,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, int action, bool
     s.stm_black ^= 1;
     GenCtx g;
     gen_prepare(s.b, !s.stm_black, g, geo);
-    TgtSink sink(sr, scratch);
+    typename SinkOf<FAST>::type sink(sr, scratch);
     gen_targets(s.b, g, g.own, sink, geo);
     const int n = sink.total();
     if (sink.dropped) st.f += SF_SLOTOVF;
@@ -453,7 +489,7 @@ GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step), state in registers
 // SELFPLAY = true: the caller guarantees opponent "none" (one ply per step, no bot, WHITE agent) -- the bot's branches
 // are compiled out of the self-play kernel.
-template <int MODE, bool SELFPLAY = false, class G>
+template <int MODE, bool SELFPLAY = false, bool FAST = false, class G>
 GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch,
                           const SlotRef& sr, const G& geo) {
     const bool v_bot = SELFPLAY ? false : v.opponent == 1, v_agent_black = SELFPLAY ? false : v.agent_black != 0;
@@ -561,7 +597,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             continue;
         }
         bool rep;
-        const int r = ply_and_movegen(v, e, s, cur, do_apply, &rep, st, scratch, sr, geo);
+        const int r = ply_and_movegen<FAST>(v, e, s, cur, do_apply, &rep, st, scratch, sr, geo);
         if (do_apply) st.f += SF_PLIES;
         const bool mate = s.n_legal == 0 && stm_checked(s);
         if (phase == PH_AGENT) {
@@ -603,7 +639,7 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     EnvRegs s;
     u32 ep;
     env_load(v, e, s, ep);
-    env_step_regs<MODE, false>(v, io, e, s, ep, st, scratch, resident_slots(v, e), GeomGlobal());
+    env_step_regs<MODE, false, false>(v, io, e, s, ep, st, scratch, resident_slots(v, e), GeomGlobal());
     env_store(v, e, s, ep);
 }
 

@@ -50,6 +50,9 @@ extern "C" int gcb_device_count(void) {
 #ifndef GCB_STEP_MIN_BLOCKS
 #define GCB_STEP_MIN_BLOCKS 5
 #endif
+#ifndef GCB_FAST_SINK
+#define GCB_FAST_SINK 1
+#endif
 #ifndef GCB_SAMPLED_MIN_BLOCKS
 #define GCB_SAMPLED_MIN_BLOCKS 5
 #endif
@@ -231,13 +234,23 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_
         __syncthreads();
     }
     const GeomShared sgeo = {s_geom};
+    // at most 16 pieces of either colour (always, from the standard start position: pieces only leave the board): the
+    // generation then stores its slots without bounds tests for the whole launch
+    const bool small = TILE && active && gcb_popc(s.b.w) <= GCB_SLOTS && gcb_popc(bb_occ(s.b) & ~s.b.w) <= GCB_SLOTS;
+    (void)small;
 #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
         StepStats st;
         st.clear();
         if (active) {
-            if (TILE) env_step_regs<MODE, SELFPLAY>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, sgeo);
-            else env_step_regs<MODE, SELFPLAY>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, GeomGlobal());
+            if (TILE) {
+#if GCB_FAST_SINK
+                if (small) env_step_regs<MODE, SELFPLAY, true>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, sgeo);
+                else
+#endif
+                    env_step_regs<MODE, SELFPLAY, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, sgeo);
+            } else
+                env_step_regs<MODE, SELFPLAY, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, GeomGlobal());
         }
         if (MODE != MODE_RESET) {
             // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The bit-field counters are widened into

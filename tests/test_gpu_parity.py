@@ -484,6 +484,39 @@ def test_endgames_with_long_repetition_windows():
     assert (bb[:4096] == bs).all() and (ib[:4096] == is_).all()
 
 
+def test_multi_step_launch_with_more_pieces_than_slots():
+    """16 piece slots (default boards) but some envs are IMPORTED with more than 16 pieces of one colour: those threads
+    of a multi-step launch keep the bounds-checked slot stores (slot_overflow is counted), their neighbours in the same
+    warp use the unchecked ones -- same results as single-step launches"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv
+
+    N, T = 256, 48
+    rng = np.random.RandomState(12)
+    boards = np.zeros((N, 64), np.int8)
+    players, rights = np.ones(N, np.int8), np.zeros((N, 4), np.uint8)
+    from gym_chess_b200.boards import DEFAULT_BOARD
+    for i in range(N):
+        if i % 3 == 0:    # 20 white pieces + king against a few black ones
+            sq = rng.permutation(64)
+            boards[i, sq[:20]] = rng.choice([2, 3, 4, 5, 6], size=20)
+            boards[i, sq[20:26]] = -rng.choice([2, 3, 4, 5, 6], size=6)
+            boards[i, sq[26]], boards[i, sq[27]] = 1, -1
+        else:
+            boards[i] = DEFAULT_BOARD
+            rights[i] = 1
+    envs = [BatchedChessEnv(N, opponent="none", seed=77) for _ in range(2)]
+    for e in envs:
+        e.set_state(boards, players, rights)
+    for _ in range(T):
+        envs[0].step_sampled(1)
+    envs[1].step_sampled(T)
+    for x, y in zip(envs[0].export_numpy(), envs[1].export_numpy()):
+        assert (x == y).all()
+    sa, sb = envs[0].stats(), envs[1].stats()
+    assert sa == sb and sa["slot_overflow"] > 0
+
+
 def test_ring_overflow_is_defined_and_identical_on_every_path():
     """a repetition window that outgrows a small ring (history_cap = 8 on endgame boards) can miss a repetition -- defined
     behaviour, counted in hist_overflow: the single-step kernel, the multi-step kernel and the host-compiled build of
