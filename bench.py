@@ -341,7 +341,7 @@ def main():
     if clk is not None:
         line["clocks"] = clk
 
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:  # the secondary configs and the CPU baseline: single-GPU runs only
         import ctypes as C
         from gym_chess_b200._lib import Positions, check
 
