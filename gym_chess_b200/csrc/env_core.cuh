@@ -237,41 +237,46 @@ struct TgtSinkFast {
 // per-thread statistics of one step: the small counters live as bit fields of ONE register (fewer live registers in
 // the step kernel), the wide ones in four ints
 struct StepStats {
-    u32 f;  // bit 0 steps, 1-2 plies, 3 episodes, 4 mates, 5 repetitions, 6 caps, 7 wedged, 8 invalid, 9 in_check,
-            // 10-12 hist_overflow, 13-14 slot_overflow
+    // f: the three counters EVERY step touches as 7/8-bit fields (bits 0-6 steps, 7-14 plies, 15-21 in_check: their sum
+    // over the 32 lanes of a warp fits the field, so one warp reduction of the masked word adds all three), then the rare
+    // events: bit 22 episodes, 23 mates, 24 repetitions, 25 caps, 26 wedged, 27 invalid, 28-29 hist_overflow, 30-31
+    // slot_overflow (the kernel looks at them only when some lane of the warp has one)
+    u32 f;
     int reward, legal, scan, window;
     GCB_HD void clear() { f = 0, reward = 0, legal = 0, scan = 0, window = 0; }
     GCB_HD int get(int k) const {
         switch (k) {
-        case ST_STEPS: return (int)(f & 1u);
-        case ST_PLIES: return (int)((f >> 1) & 3u);
-        case ST_EPISODES: return (int)((f >> 3) & 1u);
-        case ST_MATES: return (int)((f >> 4) & 1u);
-        case ST_REPS: return (int)((f >> 5) & 1u);
-        case ST_CAPS: return (int)((f >> 6) & 1u);
-        case ST_WEDGED: return (int)((f >> 7) & 1u);
-        case ST_INVALID: return (int)((f >> 8) & 1u);
+        case ST_STEPS: return (int)(f & 127u);
+        case ST_PLIES: return (int)((f >> 7) & 255u);
+        case ST_EPISODES: return (int)((f >> 22) & 1u);
+        case ST_MATES: return (int)((f >> 23) & 1u);
+        case ST_REPS: return (int)((f >> 24) & 1u);
+        case ST_CAPS: return (int)((f >> 25) & 1u);
+        case ST_WEDGED: return (int)((f >> 26) & 1u);
+        case ST_INVALID: return (int)((f >> 27) & 1u);
         case ST_REWARD: return reward;
         case ST_LEGAL: return legal;
-        case ST_INCHECK: return (int)((f >> 9) & 1u);
-        case ST_HISTOVF: return (int)((f >> 10) & 7u);
-        case ST_SLOTOVF: return (int)((f >> 13) & 3u);
+        case ST_INCHECK: return (int)((f >> 15) & 127u);
+        case ST_HISTOVF: return (int)((f >> 28) & 3u);
+        case ST_SLOTOVF: return (int)((f >> 30) & 3u);
         case ST_HISTSCAN: return scan;
         default: return window;
         }
     }
 };
 #define SF_STEPS 1u
-#define SF_PLIES (1u << 1)
-#define SF_EPISODES (1u << 3)
-#define SF_MATES (1u << 4)
-#define SF_REPS (1u << 5)
-#define SF_CAPS (1u << 6)
-#define SF_WEDGED (1u << 7)
-#define SF_INVALID (1u << 8)
-#define SF_INCHECK (1u << 9)
-#define SF_HISTOVF (1u << 10)
-#define SF_SLOTOVF (1u << 13)
+#define SF_PLIES (1u << 7)
+#define SF_INCHECK (1u << 15)
+#define SF_HOT_MASK 0x3FFFFFu
+#define SF_RARE_SHIFT 22
+#define SF_EPISODES (1u << 22)
+#define SF_MATES (1u << 23)
+#define SF_REPS (1u << 24)
+#define SF_CAPS (1u << 25)
+#define SF_WEDGED (1u << 26)
+#define SF_INVALID (1u << 27)
+#define SF_HISTOVF (1u << 28)
+#define SF_SLOTOVF (1u << 30)
 
 // Repetition table (the Zobrist-hash history of chess_v2.py:404-407's saved_boards, restricted to the window since the
 // last pawn move / capture: an older board cannot recur).  Open addressing over H = history_cap slots of 16 bytes per env,

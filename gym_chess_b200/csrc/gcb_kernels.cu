@@ -253,23 +253,27 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_
                 env_step_regs<MODE, SELFPLAY, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, GeomGlobal());
         }
         if (MODE != MODE_RESET) {
-            // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The bit-field counters are widened into
-            // three words whose fields cannot overflow over 32 lanes: 7 REDUX in all instead of one per counter
+            // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The three counters every step touches are
+            // fields of one word wide enough for a warp sum (one REDUX for all three); the rare events (an episode ends,
+            // an invalid action, an overflow) are only looked at when some lane of the warp has one
             const u32 f = st.f;
-            const u32 w0 = (f & 1u) | (((f >> 1) & 3u) << 6) | (((f >> 3) & 1u) << 13) | (((f >> 4) & 1u) << 19) | (((f >> 5) & 1u) << 25);
-            const u32 w1 = ((f >> 6) & 1u) | (((f >> 7) & 1u) << 6) | (((f >> 8) & 1u) << 12) | (((f >> 9) & 1u) << 18) | (((f >> 13) & 3u) << 24);
-            const u32 r0 = __reduce_add_sync(0xffffffffu, w0), r1 = __reduce_add_sync(0xffffffffu, w1);
-            const u32 r2 = __reduce_add_sync(0xffffffffu, (f >> 10) & 7u);
+            const u32 hot = __reduce_add_sync(0xffffffffu, f & SF_HOT_MASK);
             const int t_reward = __reduce_add_sync(0xffffffffu, st.reward), t_legal = __reduce_add_sync(0xffffffffu, st.legal);
             const int t_scan = __reduce_add_sync(0xffffffffu, st.scan), t_window = __reduce_add_sync(0xffffffffu, st.window);
-            // lane k picks counter k: a chain of selects (a switch on the lane id would run its 15 cases one by one)
+            // lane k picks counter k: a chain of selects (a switch on the lane id would run its cases one by one)
             long long mine = 0;
 #define GCB_PICK(k_, v_) mine = lane == (k_) ? (long long)(v_) : mine
-            GCB_PICK(ST_STEPS, r0 & 63u), GCB_PICK(ST_PLIES, (r0 >> 6) & 127u), GCB_PICK(ST_EPISODES, (r0 >> 13) & 63u);
-            GCB_PICK(ST_MATES, (r0 >> 19) & 63u), GCB_PICK(ST_REPS, (r0 >> 25) & 63u), GCB_PICK(ST_CAPS, r1 & 63u);
-            GCB_PICK(ST_WEDGED, (r1 >> 6) & 63u), GCB_PICK(ST_INVALID, (r1 >> 12) & 63u), GCB_PICK(ST_REWARD, t_reward);
-            GCB_PICK(ST_LEGAL, t_legal), GCB_PICK(ST_INCHECK, (r1 >> 18) & 63u), GCB_PICK(ST_HISTOVF, r2);
-            GCB_PICK(ST_SLOTOVF, (r1 >> 24) & 127u), GCB_PICK(ST_HISTSCAN, t_scan), GCB_PICK(ST_WINDOW, t_window);
+            GCB_PICK(ST_STEPS, hot & 127u), GCB_PICK(ST_PLIES, (hot >> 7) & 255u), GCB_PICK(ST_INCHECK, (hot >> 15) & 127u);
+            GCB_PICK(ST_REWARD, t_reward), GCB_PICK(ST_LEGAL, t_legal), GCB_PICK(ST_HISTSCAN, t_scan), GCB_PICK(ST_WINDOW, t_window);
+            if (__any_sync(0xffffffffu, (f >> SF_RARE_SHIFT) != 0u)) {
+                const u32 r = f >> SF_RARE_SHIFT;  // episodes, mates, repetitions, caps | wedged, invalid, hist_overflow(2), slot_overflow(2)
+                const u32 w0 = (r & 1u) | ((r & 2u) << 7) | ((r & 4u) << 14) | ((r & 8u) << 21);
+                const u32 w1 = ((r >> 4) & 1u) | (((r >> 5) & 1u) << 8) | (((r >> 6) & 3u) << 16) | (((r >> 8) & 3u) << 24);
+                const u32 r0 = __reduce_add_sync(0xffffffffu, w0), r1 = __reduce_add_sync(0xffffffffu, w1);
+                GCB_PICK(ST_EPISODES, r0 & 255u), GCB_PICK(ST_MATES, (r0 >> 8) & 255u), GCB_PICK(ST_REPS, (r0 >> 16) & 255u);
+                GCB_PICK(ST_CAPS, r0 >> 24), GCB_PICK(ST_WEDGED, r1 & 255u), GCB_PICK(ST_INVALID, (r1 >> 8) & 255u);
+                GCB_PICK(ST_HISTOVF, (r1 >> 16) & 255u), GCB_PICK(ST_SLOTOVF, r1 >> 24);
+            }
 #undef GCB_PICK
             acc += mine;
         }
