@@ -30,15 +30,25 @@ def sources():
     ]
 
 
-def build(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> gym_chess_b200/libgymchess_b200.so"""
+# test-support builds of the same sources (tests/test_memory_safety.py): index checks compiled in; the self-test build
+# re-introduces a known out-of-bounds access to prove that the checks see that class of bug
+VARIANTS = {"checked": ["-DGCB_CHECKED"], "checked_selftest": ["-DGCB_CHECKED", "-DGCB_SELFTEST_OOB"]}
+
+
+def variant_path(name):
+    return os.path.join(_PKG, "libgymchess_b200_%s.so" % name)
+
+
+def build(force=False, verbose=False, variant=None):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> gym_chess_b200/libgymchess_b200.so (or a VARIANTS build)"""
     srcs = sources()
-    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= max(os.path.getmtime(s) for s in srcs):
-        return SO_PATH
+    out = SO_PATH if variant is None else variant_path(variant)
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(s) for s in srcs):
+        return out
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, srcs[0]]
+    cmd = [nvcc] + NVCC_FLAGS + (VARIANTS[variant] if variant else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, srcs[0]]
     subprocess.check_call(cmd)
-    return SO_PATH
+    return out
 
 
 class Positions(C.Structure):
@@ -83,9 +93,10 @@ SIGNATURES = {
     "gcb_env_import": (i32, [vp, vp, vp, vp, vp, vp, vp]),
     "gcb_env_step": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_step_index": (i32, [vp, vp, vp, vp, vp, vp]),
+    "gcb_env_bot_ply": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_step_sampled": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
-    "gcb_env_step_host": (i32, [vp, vp, vp, vp, vp]),
-    "gcb_env_step_index_host": (i32, [vp, vp, vp, vp, vp]),
+    "gcb_env_step_host": (i32, [vp, vp, vp, vp, vp, vp]),
+    "gcb_env_step_index_host": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_step_host_async": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_step_index_host_async": (i32, [vp, vp, vp, vp, vp, vp]),
     "gcb_env_wait": (i32, [vp, vp]),
@@ -103,6 +114,9 @@ SIGNATURES = {
     "gcb_env_stats": (i32, [vp, vp, vp]),
     "gcb_env_stats_reset": (i32, [vp, vp]),
     "gcb_env_stats_ptr": (i32, [vp, C.POINTER(vp), vp]),
+    "gcb_env_check_guards": (i32, [vp, C.POINTER(C.c_uint64)]),
+    "gcb_debug_violations": (i32, [C.POINTER(C.c_uint64), i32]),
+    "gcb_build_is_checked": (i32, []),
 }
 
 _lib = None

@@ -17,7 +17,8 @@ from ._lib import EnvConfig, Positions, check
 
 WHITE, BLACK = "WHITE", "BLACK"
 
-F_INVALID, F_MATE, F_REPETITION, F_CAP, F_WEDGED, F_RESET = 1, 2, 4, 8, 16, 32
+F_INVALID, F_MATE, F_REPETITION, F_CAP, F_WEDGED, F_RESET, F_BOT_PENDING = 1, 2, 4, 8, 16, 32, 64
+_OPPONENTS = {"none": 0, "random": 1, "external": 2}
 STAT_NAMES = ("steps", "plies", "episodes", "mates", "repetitions", "caps", "wedged", "invalid", "reward_sum",
               "legal_sum", "in_check", "hist_overflow", "slot_overflow", "hist_scanned", "hist_window")
 INFO_NAMES = ("current_player", "white_king_castle_is_possible", "white_queen_castle_is_possible",
@@ -49,22 +50,24 @@ class BatchedChessEnv:
     def __init__(self, num_envs, opponent="random", player_color=WHITE, seed=0, device=0, auto_reset=True,
                  initial_boards=None, env_id_offset=0, legal_stride=144, history_cap=512, moves_max=149, piece_slots=0):
         """
-        opponent      "random" (the bot replies inside step, chess_v2.py:277-288) or "none" (self-play)
+        opponent      "random" (the bot replies inside step, chess_v2.py:277-288; drawn on the device), "none" (self-play)
+                      or "external" (a callable opponent, chess_v2.py:171-179: step() stops with F_BOT_PENDING where the
+                      bot would move and the caller supplies its ply with bot_ply())
         player_color  "WHITE" | "BLACK" (BLACK needs opponent="random", like the reference: Q23)
         initial_boards  None (DEFAULT_BOARD) or int8 [T,8,8] / [8,8]; env with global id g starts from board g % T
         env_id_offset   global id of local env 0 -- shards of one job use disjoint id ranges so that the
                         Philox draws (counter = global env id, episode, step) do not depend on the sharding
         """
         _lib.require_gpu()
-        if opponent not in ("random", "none"):
-            raise ValueError("opponent must be 'random' or 'none' (callables: see gym_chess_b200.ChessEnvV2)")
+        if opponent not in _OPPONENTS:
+            raise ValueError("opponent must be 'random', 'none' or 'external' (callables: see gym_chess_b200.ChessEnvV2)")
         self.num_envs, self.opponent, self.player_color = int(num_envs), opponent, player_color
         self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
         self.auto_reset, self.seed, self.env_id_offset = bool(auto_reset), int(seed), int(env_id_offset)
         self.legal_stride = int(legal_stride)
         cfg = EnvConfig()
         cfg.num_envs, cfg.env_id_offset, cfg.seed = self.num_envs, self.env_id_offset, self.seed
-        cfg.opponent, cfg.agent_black, cfg.auto_reset = int(opponent == "random"), int(player_color == BLACK), int(auto_reset)
+        cfg.opponent, cfg.agent_black, cfg.auto_reset = _OPPONENTS[opponent], int(player_color == BLACK), int(auto_reset)
         cfg.piece_slots, cfg.history_cap, cfg.moves_max = piece_slots, history_cap, moves_max
         self._templates = None
         if initial_boards is not None:
@@ -125,6 +128,14 @@ class BatchedChessEnv:
         a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
         with torch.cuda.device(self.device):
             check(_lib.lib().gcb_env_step(self._h, C.c_void_p(a.data_ptr()), *self._outs(), _stream_ptr()))
+        return self.reward, self.done, self.flags
+
+    def bot_ply(self, bot_actions):
+        """opponent="external": the bot's ply of every env that owes one (F_BOT_PENDING / after a BLACK-agent reset), applied
+        like the reference applies opponent_policy(env).  -> (reward to ADD, done, flags), valid for the envs that owed a ply."""
+        a = torch.as_tensor(bot_actions, device=self.device).to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gcb_env_bot_ply(self._h, C.c_void_p(a.data_ptr()), *self._outs(), _stream_ptr()))
         return self.reward, self.done, self.flags
 
     def step_index(self, u32):
@@ -198,7 +209,8 @@ class BatchedChessEnv:
         reward = np.empty(N, np.int32) if reward is None else reward
         done = np.empty(N, np.uint8) if done is None else done
         flags = np.empty(N, np.uint8) if flags is None else flags
-        check(fn(self._h, inp.ctypes.data, reward.ctypes.data, done.ctypes.data, flags.ctypes.data))
+        with torch.cuda.device(self.device):
+            check(fn(self._h, inp.ctypes.data, reward.ctypes.data, done.ctypes.data, flags.ctypes.data, _stream_ptr()))
         return reward, done, flags
 
     # ------------------------------------------------------------------ observation / state

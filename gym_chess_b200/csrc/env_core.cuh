@@ -34,6 +34,24 @@ static inline ulonglong2 make_ulonglong2(u64 x, u64 y) {
 }
 #endif
 
+// Memory-safety net for a pool without compute-sanitizer: the CHECKED build (-DGCB_CHECKED,
+// libgymchess_b200_checked.so) verifies the index of every indexed global access of the env kernels against the extent of
+// its array and records violations here; gcb_debug_violations() reads the word.  The product build compiles the checks out.
+#if defined(__CUDACC__)
+__device__ unsigned long long g_violations = 0ULL;
+#endif
+#if defined(GCB_CHECKED) && defined(__CUDA_ARCH__)
+#define GCB_CHK(cond, code)                                                   \
+    do {                                                                      \
+        if (!(cond)) atomicOr(&g_violations, 1ULL << (code));                 \
+    } while (0)
+#else
+#define GCB_CHK(cond, code) \
+    do {                    \
+    } while (0)
+#endif
+enum { CHK_STAT_ROW = 0, CHK_ENV_INDEX = 1, CHK_SLOT_INDEX = 2, CHK_REP_INDEX = 3, CHK_IO_INDEX = 4, CHK_LIST_INDEX = 5 };
+
 // The resident state is touched once per step: stream it past L1 (ld.global.cs / st.global.cs, evict-first) so that
 // the geometry tables the generation hammers stay L1-resident.
 #if defined(__CUDA_ARCH__)
@@ -51,6 +69,7 @@ static inline ulonglong2 make_ulonglong2(u64 x, u64 y) {
 #define EF_CAP 8u
 #define EF_WEDGED 16u
 #define EF_RESET 32u
+#define EF_BOT_PENDING 64u
 
 // ordered move list -> global memory, two 16-bit entries per 32-bit store
 struct ListWriter {
@@ -71,7 +90,9 @@ struct ListWriter {
     }
 };
 
-// meta word: bit 0 stm, 1-4 rights, 5-6 check flags, 7 done, 8-9 castle (queen side, king side)
+// meta word: bit 0 stm, 1-4 rights, 5-6 check flags, 7 done, 8-9 castle (queen side, king side), 10-21 n_legal,
+// 22-37 move_count, 38-53 step_in_episode, 54-62 hist_len (saturates at 511; only its being zero matters, the rest is
+// statistics), 63 bot_pending (opponent "external": the caller owes this env the bot's ply, gcb_env_bot_ply)
 #define M_RIGHTS_SHIFT 1
 #define M_CASTLE_SHIFT 8
 #define M_NLEGAL_SHIFT 10
@@ -102,7 +123,7 @@ struct EnvView {
     u64* stats;      // [ST_COUNT] totals (written by the reduction of stat_rows)
     u64* stat_rows;  // [ceil(N/32)][ST_COUNT] per-warp accumulators: no atomics, no block barrier in the step kernel
     u64 seed;
-    int N, slots, hist_mask, n_templates;
+    int N, slots, hist_mask, n_templates, stat_nrows;
     u32 env_offset;
     int moves_max, opponent, agent_black, auto_reset, pps;
 };
@@ -111,7 +132,7 @@ struct EnvRegs {
     Board b;
     u64 zk, cnt_lo, cnt_hi;
     u32 rights, chk, castle;  // chk bit0 white checked, bit1 black checked; castle bit0 queen side, bit1 king side
-    int stm_black, done, n_legal, move_count, step, hist_len;
+    int stm_black, done, n_legal, move_count, step, hist_len, pending;
     u32 gen;
 };
 
@@ -124,13 +145,14 @@ GCB_HD void unpack_meta(u64 m, EnvRegs& s) {
     s.n_legal = (int)(m >> M_NLEGAL_SHIFT) & 0xFFF;
     s.move_count = (int)(m >> M_MOVECOUNT_SHIFT) & 0xFFFF;
     s.step = (int)(m >> M_STEP_SHIFT) & 0xFFFF;
-    s.hist_len = (int)(m >> M_HIST_SHIFT) & 0x3FF;
+    s.hist_len = (int)(m >> M_HIST_SHIFT) & 0x1FF;
+    s.pending = (int)(m >> 63);
 }
 GCB_HD u64 pack_meta(const EnvRegs& s) {
     return (u64)(s.stm_black & 1) | ((u64)(s.rights & 15u) << M_RIGHTS_SHIFT) | ((u64)(s.chk & 3u) << 5) |
            ((u64)(s.done & 1) << 7) | ((u64)(s.castle & 3u) << M_CASTLE_SHIFT) | ((u64)(s.n_legal & 0xFFF) << M_NLEGAL_SHIFT) |
            ((u64)(s.move_count & 0xFFFF) << M_MOVECOUNT_SHIFT) | ((u64)(s.step & 0xFFFF) << M_STEP_SHIFT) |
-           ((u64)(s.hist_len & 0x3FF) << M_HIST_SHIFT);
+           ((u64)(s.hist_len & 0x1FF) << M_HIST_SHIFT) | ((u64)(s.pending & 1) << 63);
 }
 
 GCB_HD bool stm_checked(const EnvRegs& s) { return (s.chk >> s.stm_black) & 1u; }
@@ -175,6 +197,7 @@ struct TgtSink {
         else extra += c;
     }
     GCB_HD void st(int r, u64 t) {
+        GCB_CHK((unsigned)r < (unsigned)slots, CHK_SLOT_INDEX);
         if (plain) base[(unsigned)r * N] = t;
         else GCB_STS(&base[(unsigned)r * N], t);
     }
@@ -213,11 +236,13 @@ struct TgtSinkFast {
         z[0] = 0, z[1] = 0;
     }
     GCB_HD void put(int r, u64 t) {
+        GCB_CHK((unsigned)r < 16u, CHK_SLOT_INDEX);
         base[(unsigned)r * N] = t;
         cb[r] = (uint8_t)gcb_popc(t);
     }
     GCB_HD u64 get(int r) const { return base[(unsigned)r * N]; }
     GCB_HD void replace(int r, u64, u64 tnew) {
+        GCB_CHK((unsigned)r < 16u, CHK_SLOT_INDEX);
         base[(unsigned)r * N] = tnew;
         cb[r] = (uint8_t)gcb_popc(tnew);
     }
@@ -293,6 +318,7 @@ GCB_HD int rep_lookup_insert(const EnvView& v, int e, const EnvRegs& s, u64 key,
     const u64 live_tag = (u64)s.gen << 2;
     // env-major: the H entries of an env are contiguous (16 * H bytes), so the 32 envs of a warp touch one small span
     ulonglong2* const tab = v.rep + (size_t)e * ((size_t)mask + 1);
+    GCB_CHK((unsigned)e < (unsigned)v.N && i <= mask, CHK_REP_INDEX);
     if (s.hist_len == 0) {  // empty window: every entry is dead, the first slot is free
         if (insert) GCB_STS(&tab[i], make_ulonglong2(key, live_tag | 1ULL));
         return 1;
@@ -424,7 +450,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, int action, bool
         if (irr) {
             s.hist_len = 0, s.gen++;  // the window restarts empty
         } else {
-            if (s.hist_len < 0x3FF) s.hist_len++;  // (10-bit field of meta; statistics only)
+            if (s.hist_len < 0x1FF) s.hist_len++;  // (9-bit field of meta; statistics only)
         }
     }
     s.stm_black ^= 1;
@@ -446,7 +472,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, int action, bool
     return r;
 }
 
-enum { MODE_ACTION = 0, MODE_INDEX = 1, MODE_SAMPLED = 2, MODE_RESET = 3 };
+enum { MODE_ACTION = 0, MODE_INDEX = 1, MODE_SAMPLED = 2, MODE_RESET = 3, MODE_BOTPLY = 4 };
 enum { PH_AGENT = 0, PH_BOT = 1, PH_FINAL = 2, PH_RESETBOT = 3, PH_END = 4 };
 
 struct StepIO {
@@ -472,6 +498,7 @@ GCB_HD uint16_t pack_result(int reward, bool done, u32 flags) {
 
 // resident state of env e <-> registers
 GCB_HD void env_load(const EnvView& v, int e, EnvRegs& s, u32& ep) {
+    GCB_CHK((unsigned)e < (unsigned)v.N, CHK_ENV_INDEX);
     ulonglong2 a = GCB_LDS(&v.bb01[e]), c = GCB_LDS(&v.bb23[e]);
     s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
     ulonglong2 ct = GCB_LDS(&v.cnt[e]);
@@ -482,6 +509,7 @@ GCB_HD void env_load(const EnvView& v, int e, EnvRegs& s, u32& ep) {
     s.gen = GCB_LDS(&v.gen[e]);
 }
 GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
+    GCB_CHK((unsigned)e < (unsigned)v.N, CHK_ENV_INDEX);
     GCB_STS(&v.bb01[e], make_ulonglong2(s.b.t0, s.b.t1));
     GCB_STS(&v.bb23[e], make_ulonglong2(s.b.t2, s.b.w));
     GCB_STS(&v.cnt[e], make_ulonglong2(s.cnt_lo, s.cnt_hi));
@@ -497,16 +525,27 @@ GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
 template <int MODE, bool SELFPLAY = false, bool FAST = false, class G>
 GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch,
                           const SlotRef& sr, const G& geo) {
-    const bool v_bot = SELFPLAY ? false : v.opponent == 1, v_agent_black = SELFPLAY ? false : v.agent_black != 0;
+    // opponent: 0 none, 1 random (the bot draws on the device), 2 external (the step stops where the bot would move and
+    // the caller supplies the bot's ply through MODE_BOTPLY: callable opponents, chess_v2.py:171-179)
+    const bool v_bot = SELFPLAY ? false : v.opponent != 0, v_ext = SELFPLAY ? false : v.opponent == 2;
+    const bool v_agent_black = SELFPLAY ? false : v.agent_black != 0;
     const u32 genv = v.env_offset + (u32)e;
     int action = ACT_RESIGN, bot_action = -1, R = 0, phase;
     u32 fl = 0;
-    bool d_out = false, agent_ply = false;
+    bool d_out = false, agent_ply = false, owe_bot = false;
     const int n0 = s.n_legal;
     const bool was_done = s.done, capped = s.move_count > v.moves_max;
     const u32 step_idx = (u32)s.step;
     if (MODE == MODE_RESET) {
         phase = PH_FINAL;
+    } else if (MODE == MODE_BOTPLY) {
+        // the bot's ply of an "external" opponent, applied like the reference applies opponent_policy(env): no
+        // membership test (chess_v2.py:277-283, 208-213)
+        if (!s.pending) return;  // nothing owed: the env is left alone, no outputs
+        s.pending = 0;
+        action = bot_action = reinterpret_cast<const int32_t*>(io.in)[e];
+        agent_ply = true;
+        phase = (s.step == 0 && v_agent_black) ? PH_RESETBOT : PH_BOT;
     } else {
         bool valid = false;
         if (MODE == MODE_ACTION) {
@@ -520,6 +559,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 valid = true;
             }
         }
+        if (!SELFPLAY && s.pending) valid = false;  // a bot ply is owed first: the agent's action is refused
         st.f += SF_STEPS + (stm_checked(s) ? SF_INCHECK : 0u), st.legal += n0;
         s.step++;
         if (!valid) {  // chess_v2.py:240-242, before the done test (Q16)
@@ -549,9 +589,10 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 terminal = true;
             } else {
                 if (agent_ply) d_out = s.done;
-                terminal = d_out || s.n_legal == 0;
-                if (!d_out && s.n_legal == 0) fl |= EF_WEDGED;
-                if (n0 == 0 || was_done || (fl & EF_INVALID)) {
+                terminal = !owe_bot && (d_out || s.n_legal == 0);
+                if (owe_bot) fl |= EF_BOT_PENDING;
+                else if (!d_out && s.n_legal == 0) fl |= EF_WEDGED;
+                if (n0 == 0 || was_done || owe_bot || (fl & EF_INVALID)) {
                 } else if (capped) st.f += SF_CAPS;
                 else if (d_out) {
                     if (fl & EF_MATE) st.f += SF_MATES;
@@ -560,6 +601,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 if (terminal) st.f += SF_EPISODES;
                 st.reward += R;
                 if (v.auto_reset && terminal) fl |= EF_RESET;
+                GCB_CHK((unsigned)e < (unsigned)v.N, CHK_IO_INDEX);
                 if (io.reward) io.reward[e] = R;
                 if (io.done) io.done[e] = d_out ? 1 : 0;
                 if (io.flags) io.flags[e] = (uint8_t)fl;
@@ -585,7 +627,9 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                     for (int r = 0; r < np && r < sr.slots; r++) dst.st(r, ts[r]);
                 }
                 ep += (u32)io.ep_inc;
-                if (v_agent_black) {
+                if (v_agent_black && v_ext) {
+                    s.pending = 1;  // the caller's opponent opens for White (chess_v2.py:208-216): gcb_env_bot_ply
+                } else if (v_agent_black) {
                     // the bot opens for White (chess_v2.py:208-216)
                     if (s.n_legal > 0) {
                         u32 u = philox_draw(v.seed, genv, ep, 0u, 2u);
@@ -611,7 +655,9 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             s.done = rep;
             if (rep) fl |= EF_REPETITION;
             if (mate) s.done = 1, R += 100, fl |= EF_MATE;  // chess_v2.py:270-272
-            if (!s.done && v_bot) {
+            if (!s.done && v_ext) {
+                s.pending = 1, owe_bot = true;  // the step ends here; the reward so far is reported, the bot's ply follows
+            } else if (!s.done && v_bot) {
                 if (s.n_legal > 0) {  // chess_v2.py:277-288
                     u32 u = philox_draw(v.seed, genv, ep, step_idx, 1u);
                     bot_action = action_at(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
@@ -636,7 +682,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             phase = PH_END;
         }
     }
-    if (MODE != MODE_RESET && io.bot_out) io.bot_out[e] = bot_action;
+    if (MODE != MODE_RESET && MODE != MODE_BOTPLY && io.bot_out) io.bot_out[e] = bot_action;
 }
 
 template <int MODE>
@@ -659,7 +705,7 @@ GCB_HD void env_import_one(const EnvView& v, int e, const int8_t* board, int pla
     s.b = board_from_mailbox(board);
     s.zk = zobrist_full(s.b);
     s.rights = mask_rights(s.b, rights);
-    s.done = 0, s.move_count = move_count, s.step = 0, s.hist_len = 0;
+    s.done = 0, s.move_count = move_count, s.step = 0, s.hist_len = 0, s.pending = 0;
     s.gen++;  // a new episode: the repetition table starts empty
     s.stm_black = player < 0 ? 0 : 1;  // ply_and_movegen(apply = false) flips the side, then generates for it
     bool rep;
@@ -676,7 +722,7 @@ GCB_HD void make_template_one(int i, const int8_t* boards, ulonglong2* bb01, ulo
     s.zk = zobrist_full(b);
     s.rights = mask_rights(b, 15u);  // all four True, then engine.update_state masks them (chess_v2.py:195-204)
     s.chk = check_flags(b);
-    s.stm_black = 0, s.done = 0, s.move_count = 0, s.step = 0, s.hist_len = 0;
+    s.stm_black = 0, s.done = 0, s.move_count = 0, s.step = 0, s.hist_len = 0, s.pending = 0, s.gen = 0;
     GenCtx g;
     gen_prepare(b, 1, g);
     CountBytes scratch;
@@ -752,6 +798,6 @@ GCB_HD void env_export_one(const EnvView& v, int e, int8_t* board, int32_t* info
         info[0] = s.stm_black ? -1 : 1, info[1] = s.rights & RT_WK ? 1 : 0, info[2] = s.rights & RT_WQ ? 1 : 0;
         info[3] = s.rights & RT_BK ? 1 : 0, info[4] = s.rights & RT_BQ ? 1 : 0, info[5] = s.chk & 1, info[6] = (s.chk >> 1) & 1;
         info[7] = s.done, info[8] = s.move_count, info[9] = s.n_legal, info[10] = (int)v.episode[e], info[11] = s.step;
-        info[12] = s.hist_len, info[13] = (int)s.castle, info[14] = 0, info[15] = 0;
+        info[12] = s.hist_len, info[13] = (int)s.castle, info[14] = s.pending, info[15] = 0;
     }
 }

@@ -10,7 +10,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "../../include/gymchess_b200.h"
 #include "env_core.cuh"
@@ -43,6 +45,22 @@ extern "C" int gcb_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
+
+// the caller's current device is restored when an entry point returns (a process may drive several GPUs)
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev == dev) return cudaSuccess;
+        switched = true;
+        return cudaSetDevice(dev);
+    }
+    ~DeviceScope() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
 
 #ifndef GCB_BLOCK
 #define GCB_BLOCK 128
@@ -288,8 +306,18 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_
             for (int r = 0; r < np && r < GCB_SLOTS; r++) __stcs(v.tgt + (size_t)r * v.N + e, s_slots[r * GCB_BLOCK + threadIdx.x]);
         }
     }
-    // one coalesced read-modify-write of the warp's own row -- no atomics and no block barrier
-    if (MODE != MODE_RESET && lane < ST_USED) v.stat_rows[(size_t)(e >> 5) * ST_COUNT + lane] += (u64)acc;
+    // one coalesced read-modify-write of the warp's own row -- no atomics and no block barrier.  A warp that lies wholly
+    // past the env range (the idle warps of the last block) owns no row: stat_rows has ceil(N / 32) of them.
+    if (MODE != MODE_RESET && lane < ST_USED) {
+#if !defined(GCB_SELFTEST_OOB)  // (the self-test build of the checked library leaves the predicate out on purpose)
+        if ((e & ~31) < io.e_end)
+#endif
+        {
+            const size_t row = (size_t)(e >> 5);
+            GCB_CHK(row < (size_t)v.stat_nrows, CHK_STAT_ROW);
+            v.stat_rows[row * ST_COUNT + lane] += (u64)acc;
+        }
+    }
 }
 
 // totals = column sums of the per-warp rows (one block; deterministic order)
@@ -629,7 +657,37 @@ struct gcb_env {
     uint8_t *d_done = nullptr, *d_flags = nullptr;
     cudaStream_t streams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t events[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // every device array of the env: `user` is what the kernels see; with guard regions (GCB_GUARD_BYTES=<n> in the
+    // environment at create time -- a test-only mode) it sits between two regions filled with 0xA5 that
+    // gcb_env_check_guards() verifies
+    struct Alloc {
+        const char* name;
+        char* base;
+        char* user;
+        size_t bytes;
+    };
+    std::vector<Alloc> allocs;
+    size_t guard = 0;
 };
+#define GCB_GUARD_BYTE 0xA5
+
+static cudaError_t env_alloc(gcb_env* env, const char* name, void** out, size_t bytes) {
+    const size_t G = env->guard;  // a multiple of 256: `user` keeps cudaMalloc's alignment
+    char* base = nullptr;
+    cudaError_t e = cudaMalloc((void**)&base, bytes + 2 * G + (G ? 256 : 0));
+    if (e != cudaSuccess) return e;
+    if (G) {
+        e = cudaMemset(base, GCB_GUARD_BYTE, G);
+        if (e == cudaSuccess) e = cudaMemset(base + G + bytes, GCB_GUARD_BYTE, G + 256);  // starts at the first byte past the array
+        if (e != cudaSuccess) {
+            cudaFree(base);
+            return e;
+        }
+    }
+    env->allocs.push_back({name, base, base + G, bytes});
+    *out = base + G;
+    return cudaSuccess;
+}
 
 static const int8_t kDefaultBoard[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6, -6, -6, -6, -6, -6, -6, 0, 0, 0, 0, 0, 0,
                                          0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0, 0, 0, 0, 0, 0,
@@ -659,11 +717,9 @@ static int launch_step(gcb_env* env, const void* in, int32_t* reward, uint8_t* d
 
 extern "C" int gcb_env_destroy(gcb_env* env) {
     if (!env) return GCB_OK;
-    cudaSetDevice(env->cfg.device);
-    cudaFree(env->v.bb01), cudaFree(env->v.bb23), cudaFree(env->v.meta), cudaFree(env->v.zkey), cudaFree(env->v.gen), cudaFree(env->v.cnt), cudaFree(env->t_cnt);
-    cudaFree(env->v.episode), cudaFree(env->v.tgt), cudaFree(env->v.rep), cudaFree(env->v.stats), cudaFree(env->v.stat_rows);
-    cudaFree(env->t_bb01), cudaFree(env->t_bb23), cudaFree(env->t_meta), cudaFree(env->t_zkey), cudaFree(env->t_tgt), cudaFree(env->zob);
-    cudaFree(env->d_in), cudaFree(env->d_reward), cudaFree(env->d_done), cudaFree(env->d_flags);
+    DeviceScope dev;
+    dev.enter(env->cfg.device);
+    for (const gcb_env::Alloc& a : env->allocs) cudaFree(a.base);
     for (int c = 0; c < 8; c++)
         if (env->streams[c]) cudaStreamDestroy(env->streams[c]);
     for (int c = 0; c < 9; c++)
@@ -699,14 +755,19 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     if (cfg.moves_max < 0) cfg.moves_max = 149;
     if (cfg.history_cap < 8 || cfg.history_cap > 1024 || (cfg.history_cap & (cfg.history_cap - 1)))
         return fail(GCB_E_ARG, "gcb_env_create", "history_cap must be a power of two in [8, 1024]");
-    if (cfg.opponent != 0 && cfg.opponent != 1) return fail(GCB_E_ARG, "gcb_env_create", "opponent must be 0 or 1");
-    if (cfg.agent_black && cfg.opponent != 1)  // chess_v2.py:208-209 calls opponent_policy(None) -> TypeError (Q23)
-        return fail(GCB_E_ARG, "gcb_env_create", "player_color BLACK needs opponent 'random' (the reference raises TypeError)");
+    if (cfg.opponent < 0 || cfg.opponent > 2) return fail(GCB_E_ARG, "gcb_env_create", "opponent must be 0 (none), 1 (random) or 2 (external)");
+    if (cfg.agent_black && cfg.opponent == 0)  // chess_v2.py:208-209 calls opponent_policy(None) -> TypeError (Q23)
+        return fail(GCB_E_ARG, "gcb_env_create", "player_color BLACK needs an opponent (the reference raises TypeError)");
     if (cfg.n_templates < 0 || (cfg.n_templates > 0 && !cfg.template_boards))
         return fail(GCB_E_ARG, "gcb_env_create", "template_boards missing");
-    CU(cudaSetDevice(cfg.device));
+    DeviceScope dev;
+    CU(dev.enter(cfg.device));
     gcb_env* env = new (std::nothrow) gcb_env();
     if (!env) return fail(GCB_E_NOMEM, "new", "gcb_env");
+    if (const char* gv = getenv("GCB_GUARD_BYTES")) {  // test-only: guard regions around every env array
+        const long g = atol(gv);
+        env->guard = g > 0 ? (((size_t)g + 255) & ~(size_t)255) : 0;
+    }
     const int N = cfg.num_envs, T = cfg.n_templates > 0 ? cfg.n_templates : 1, S = cfg.piece_slots, H = cfg.history_cap;
     env->cfg = cfg;
     env->cfg.template_boards = nullptr;
@@ -715,7 +776,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     int8_t* d_tb = nullptr;
     cudaError_t e = cudaSuccess;
 #define ALLOC(ptr, bytes) \
-    if (e == cudaSuccess) e = cudaMalloc((void**)&(ptr), (bytes))
+    if (e == cudaSuccess) e = env_alloc(env, #ptr, (void**)&(ptr), (bytes))
     ALLOC(v.bb01, (size_t)N * 16);
     ALLOC(v.bb23, (size_t)N * 16);
     ALLOC(v.meta, (size_t)N * 8);
@@ -738,8 +799,8 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     ALLOC(env->d_reward, (size_t)N * 4);
     ALLOC(env->d_done, (size_t)N);
     ALLOC(env->d_flags, (size_t)N);
-    ALLOC(d_tb, (size_t)T * 64);
 #undef ALLOC
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_tb, (size_t)T * 64);
     if (e != cudaSuccess) {
         cudaFree(d_tb);
         gcb_env_destroy(env);
@@ -748,6 +809,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     v.t_bb01 = env->t_bb01, v.t_bb23 = env->t_bb23, v.t_meta = env->t_meta, v.t_zkey = env->t_zkey, v.t_tgt = env->t_tgt;
     v.zob = env->zob, v.t_cnt = env->t_cnt;
     v.seed = cfg.seed, v.N = N, v.slots = S, v.hist_mask = 2 * H - 1, v.n_templates = T, v.env_offset = cfg.env_id_offset;
+    v.stat_nrows = (N + 31) / 32;
     v.moves_max = cfg.moves_max, v.opponent = cfg.opponent, v.agent_black = cfg.agent_black, v.auto_reset = cfg.auto_reset;
     v.pps = 1 + (cfg.opponent == 1 ? 1 : 0);  // ring slots per step: agent ply, bot ply (a reset-bot ply reuses the bot slot)
     int rc = GCB_OK;
@@ -787,7 +849,8 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
 
 #define ENV_CHECK(env)                                               \
     if (!(env)) return fail(GCB_E_ARG, __func__, "null env");        \
-    CU(cudaSetDevice((env)->cfg.device))
+    DeviceScope dev_scope_;                                          \
+    CU(dev_scope_.enter((env)->cfg.device))
 
 extern "C" int gcb_env_reset(gcb_env* env, const uint8_t* d_mask, void* stream) {
     ENV_CHECK(env);
@@ -799,6 +862,14 @@ extern "C" int gcb_env_step(gcb_env* env, const int32_t* d_actions, int32_t* d_r
     ENV_CHECK(env);
     if (!d_actions) return fail(GCB_E_ARG, "gcb_env_step", "null actions");
     return launch_step<MODE_ACTION>(env, d_actions, d_reward, d_done, d_flags, nullptr, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gcb_env_bot_ply(gcb_env* env, const int32_t* d_bot_actions, int32_t* d_reward, uint8_t* d_done, uint8_t* d_flags,
+                               void* stream) {
+    ENV_CHECK(env);
+    if (!d_bot_actions) return fail(GCB_E_ARG, "gcb_env_bot_ply", "null actions");
+    if (env->v.opponent != 2) return fail(GCB_E_ARG, "gcb_env_bot_ply", "the env was not created with opponent 2 (external)");
+    return launch_step<MODE_BOTPLY>(env, d_bot_actions, d_reward, d_done, d_flags, nullptr, nullptr, 1, (cudaStream_t)stream);
 }
 
 extern "C" int gcb_env_step_index(gcb_env* env, const uint32_t* d_u32, int32_t* d_reward, uint8_t* d_done, uint8_t* d_flags,
@@ -827,12 +898,11 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
     // stream): every launch ends with a partly filled last wave of blocks (524,288 envs = 5.5 waves of 740 resident
     // blocks), and with independent ranges the next launch of one range fills the tail of the other.  Envs never read
     // each other, so ranges need no ordering among themselves.
-    static int want = -1;
-    if (want < 0) {
+    static const int want = [] {  // (function-local static: initialised once, thread-safe)
         const char* ev = getenv("GCB_SAMPLED_RANGES");
-        want = ev ? atoi(ev) : 2;
-        if (want < 1 || want > GCB_HOST_CHUNKS) want = 2;
-    }
+        const int w = ev ? atoi(ev) : 2;
+        return (w < 1 || w > GCB_HOST_CHUNKS) ? 2 : w;
+    }();
     const int nlaunch = (nsteps + GCB_MAX_STEPS_PER_LAUNCH - 1) / GCB_MAX_STEPS_PER_LAUNCH;
     const int R = (nlaunch >= 2 && N >= (size_t)want * 65536) ? want : 1;
     const int per = (int)((((N + R - 1) / R) + GCB_BLOCK - 1) / GCB_BLOCK * GCB_BLOCK);  // whole blocks (and whole stat rows)
@@ -842,7 +912,8 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
         CU(cudaEventRecord(env->events[GCB_HOST_CHUNKS], cs));
         for (int r = 0; r < R; r++) CU(cudaStreamWaitEvent(env->streams[r], env->events[GCB_HOST_CHUNKS], 0));
     }
-    for (int t = 0; t < nsteps;) {
+    int rc = GCB_OK;
+    for (int t = 0; t < nsteps && rc == GCB_OK;) {
         const int k = nsteps - t < GCB_MAX_STEPS_PER_LAUNCH ? nsteps - t : GCB_MAX_STEPS_PER_LAUNCH;
         StepIO io;
         io.in = nullptr, io.reward = d_reward, io.done = d_done, io.flags = d_flags;
@@ -858,18 +929,24 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
                 k_env_step<MODE_SAMPLED, true><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
             else
                 k_env_step<MODE_SAMPLED, false><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
-            LAUNCHED();
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            const cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) {
+                rc = fail(GCB_E_CUDA, "kernel launch", cudaGetErrorString(le));
+                break;
+            }
         }
         env->tick += (u64)k;
         t += k;
     }
-    if (R > 1) {
+    if (R > 1) {  // the forked streams are joined on EVERY path, also after a failed launch
         for (int r = 0; r < R; r++) {
-            CU(cudaEventRecord(env->events[r], env->streams[r]));
-            CU(cudaStreamWaitEvent(cs, env->events[r], 0));
+            const cudaError_t e1 = cudaEventRecord(env->events[r], env->streams[r]);
+            const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(cs, env->events[r], 0) : e1;
+            if (e2 != cudaSuccess && rc == GCB_OK) rc = fail(GCB_E_CUDA, "join of the range streams", cudaGetErrorString(e2));
         }
     }
-    return GCB_OK;
+    return rc;
 }
 
 // Host-buffer step: the batch is cut into chunks that travel on their own streams, so the H2D copy of chunk k+1, the
@@ -887,16 +964,15 @@ static void* mapped_ptr(const void* host) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-static int step_host_common(gcb_env* env, int mode, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags) {
+static int step_host_common(gcb_env* env, int mode, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, cudaStream_t cs) {
     const int N = env->v.N;
     // Zero-copy path: when every buffer is page-locked, the step kernel reads the actions and writes reward / done /
     // flags straight through PCIe (coalesced 128-byte rows per warp) -- one launch, no staging copies, the transfers
     // overlap the move generation of the other warps.
-    static int zero_copy = -1;
-    if (zero_copy < 0) {
+    static const int zero_copy = [] {
         const char* ev = getenv("GCB_HOST_ZEROCOPY");
-        zero_copy = ev ? atoi(ev) : 1;
-    }
+        return ev ? atoi(ev) : 1;
+    }();
     if (zero_copy) {
         void* m_in = mapped_ptr(in);
         void* m_r = mapped_ptr(reward);
@@ -904,23 +980,24 @@ static int step_host_common(gcb_env* env, int mode, const void* in, int32_t* rew
         void* m_f = mapped_ptr(flags);
         if (m_in && (m_r || !reward) && (m_d || !done) && (m_f || !flags)) {
             int rc = mode == MODE_ACTION
-                         ? launch_step<MODE_ACTION>(env, m_in, (int32_t*)m_r, (uint8_t*)m_d, (uint8_t*)m_f, nullptr, nullptr, 1, 0)
-                         : launch_step<MODE_INDEX>(env, m_in, (int32_t*)m_r, (uint8_t*)m_d, (uint8_t*)m_f, nullptr, nullptr, 1, 0);
+                         ? launch_step<MODE_ACTION>(env, m_in, (int32_t*)m_r, (uint8_t*)m_d, (uint8_t*)m_f, nullptr, nullptr, 1, cs)
+                         : launch_step<MODE_INDEX>(env, m_in, (int32_t*)m_r, (uint8_t*)m_d, (uint8_t*)m_f, nullptr, nullptr, 1, cs);
             if (rc) return rc;
-            CU(cudaStreamSynchronize(0));
+            CU(cudaStreamSynchronize(cs));
             return GCB_OK;
         }
     }
-    static int want = 0;  // GCB_HOST_CHUNKS=<1..8> overrides the default pipelining depth
-    if (!want) {
+    static const int want = [] {  // GCB_HOST_CHUNKS=<1..8> overrides the default pipelining depth
         const char* ev = getenv("GCB_HOST_CHUNKS");
-        want = ev ? atoi(ev) : 4;
-        if (want < 1 || want > GCB_HOST_CHUNKS) want = 4;
-    }
+        const int w = ev ? atoi(ev) : 4;
+        return (w < 1 || w > GCB_HOST_CHUNKS) ? 4 : w;
+    }();
     int chunks = N >= want * 16384 ? want : (N >= 32768 ? 2 : 1);
     int per = (((N + chunks - 1) / chunks) + GCB_BLOCK - 1) / GCB_BLOCK * GCB_BLOCK;  // whole blocks (and whole stat rows)
     if (int rc = ensure_streams(env)) return rc;
-    CU(cudaStreamSynchronize(0));  // earlier work of this env on the default stream
+    // the chunk streams start after everything enqueued on the caller's stream so far
+    CU(cudaEventRecord(env->events[GCB_HOST_CHUNKS], cs));
+    for (int c = 0; c < chunks; c++) CU(cudaStreamWaitEvent(env->streams[c], env->events[GCB_HOST_CHUNKS], 0));
     const char* src = reinterpret_cast<const char*>(in);
     for (int c = 0; c < chunks; c++) {
         const int b = c * per, e = (b + per < N) ? b + per : N;
@@ -937,20 +1014,25 @@ static int step_host_common(gcb_env* env, int mode, const void* in, int32_t* rew
         if (flags) CU(cudaMemcpyAsync(flags + b, env->d_flags + b, (size_t)(e - b), cudaMemcpyDeviceToHost, s));
     }
     env->tick++;
-    for (int c = 0; c < chunks; c++) CU(cudaStreamSynchronize(env->streams[c]));
+    cudaError_t first = cudaSuccess;  // every chunk stream is drained, also after an error on one of them
+    for (int c = 0; c < chunks; c++) {
+        const cudaError_t ce = cudaStreamSynchronize(env->streams[c]);
+        if (first == cudaSuccess) first = ce;
+    }
+    if (first != cudaSuccess) return fail(GCB_E_CUDA, "host-buffer step", cudaGetErrorString(first));
     return GCB_OK;
 }
 
-extern "C" int gcb_env_step_host(gcb_env* env, const int32_t* actions, int32_t* reward, uint8_t* done, uint8_t* flags) {
+extern "C" int gcb_env_step_host(gcb_env* env, const int32_t* actions, int32_t* reward, uint8_t* done, uint8_t* flags, void* stream) {
     ENV_CHECK(env);
     if (!actions) return fail(GCB_E_ARG, "gcb_env_step_host", "null actions");
-    return step_host_common(env, MODE_ACTION, actions, reward, done, flags);
+    return step_host_common(env, MODE_ACTION, actions, reward, done, flags, (cudaStream_t)stream);
 }
 
-extern "C" int gcb_env_step_index_host(gcb_env* env, const uint32_t* u32, int32_t* reward, uint8_t* done, uint8_t* flags) {
+extern "C" int gcb_env_step_index_host(gcb_env* env, const uint32_t* u32, int32_t* reward, uint8_t* done, uint8_t* flags, void* stream) {
     ENV_CHECK(env);
     if (!u32) return fail(GCB_E_ARG, "gcb_env_step_index_host", "null random words");
-    return step_host_common(env, MODE_INDEX, u32, reward, done, flags);
+    return step_host_common(env, MODE_INDEX, u32, reward, done, flags, (cudaStream_t)stream);
 }
 
 // Asynchronous host-buffer steps: page-locked buffers only (their device aliases are read / written in place by the step
@@ -1138,6 +1220,52 @@ extern "C" int gcb_env_positions(gcb_env* env, gcb_positions* out) {
     return GCB_OK;
 }
 
+// ---- memory-safety net (test support): guard regions around every env array, index checks of the CHECKED build
+extern "C" int gcb_env_check_guards(gcb_env* env, uint64_t* n_bad_bytes) {
+    ENV_CHECK(env);
+    if (!n_bad_bytes) return fail(GCB_E_ARG, "gcb_env_check_guards", "null pointer");
+    *n_bad_bytes = 0;
+    if (!env->guard) return fail(GCB_E_ARG, "gcb_env_check_guards", "the env was created without GCB_GUARD_BYTES");
+    CU(cudaDeviceSynchronize());
+    const size_t G = env->guard;
+    std::vector<unsigned char> h(G + 256);
+    char first[160] = "";
+    for (const gcb_env::Alloc& a : env->allocs) {
+        for (int side = 0; side < 2; side++) {
+            const size_t n = side ? G + 256 : G;
+            CU(cudaMemcpy(h.data(), side ? a.user + a.bytes : a.base, n, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; i++)
+                if (h[i] != GCB_GUARD_BYTE) {
+                    if (!*n_bad_bytes) snprintf(first, sizeof(first), "%s: byte %zu %s the array", a.name, side ? i : G - i, side ? "past the end of" : "before");
+                    ++*n_bad_bytes;
+                }
+        }
+    }
+    if (*n_bad_bytes) snprintf(g_err, sizeof(g_err), "guard regions overwritten, first: %s", first);
+    return GCB_OK;
+}
+
+extern "C" int gcb_debug_violations(uint64_t* out, int reset) {
+    if (!out) return fail(GCB_E_ARG, "gcb_debug_violations", "null pointer");
+    if (int rc = need_gpu()) return rc;
+    unsigned long long v = 0;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(&v, g_violations, sizeof(v)));
+    if (reset) {
+        const unsigned long long z = 0;
+        CU(cudaMemcpyToSymbol(g_violations, &z, sizeof(z)));
+    }
+    *out = v;
+    return GCB_OK;
+}
+extern "C" int gcb_build_is_checked(void) {
+#if defined(GCB_CHECKED)
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 static int stats_reduce(gcb_env* env, cudaStream_t s) {
     k_stats_reduce<<<1, 512, 0, s>>>(env->v.stat_rows, (env->v.N + 31) / 32, env->v.stats);
     LAUNCHED();
@@ -1162,7 +1290,8 @@ extern "C" int gcb_env_stats_reset(gcb_env* env, void* stream) {
 
 extern "C" int gcb_env_stats_ptr(gcb_env* env, uint64_t** d_stats, void* stream) {
     if (!env || !d_stats) return fail(GCB_E_ARG, "gcb_env_stats_ptr", "null pointer");
-    CU(cudaSetDevice(env->cfg.device));
+    DeviceScope dev;
+    CU(dev.enter(env->cfg.device));
     if (int rc = stats_reduce(env, (cudaStream_t)stream)) return rc;  // totals are current once `stream` reaches here
     *d_stats = reinterpret_cast<uint64_t*>(env->v.stats);
     return GCB_OK;

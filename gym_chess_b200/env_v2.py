@@ -3,8 +3,14 @@
 `possible_actions`, `info`, flags, codec helpers, `get_possible_moves(state, player, attack)`, `get_castle_moves`.
 
 It is a thin host-side view of a `BatchedChessEnv` with one env: `step()` is one launch of the fused CUDA step
-kernel, `get_possible_moves(state=...)` one launch of the batched movegen kernel.  gym itself is not needed (and
-not installed in this image); `observation_space` / `action_space` are minimal stand-ins with `contains`/`sample`.
+kernel (two when an opponent replies), `get_possible_moves(state=...)` one launch of the batched movegen kernel.
+Opponents run on the HOST exactly like the reference's (`opponent(env) -> move`, chess_v2.py:116-127, 171-179): the
+device env is created with opponent "external", its step stops where the bot would move, the policy is called with
+this object (state after the agent's ply, `possible_moves` = the bot's) and its move is applied without a membership
+test (gcb_env_bot_ply) -- for "random" that policy is the reference's `np.random.choice` over `possible_moves` (the
+GLOBAL numpy generator, Q18), so a seeded `np.random` replays the same games as the reference.  WHITE and BLACK agents.
+gym itself is not needed (and not installed in this image); `observation_space` / `action_space` are minimal stand-ins
+with `contains` / `sample`; `highlight` restates gym.utils.colorize (gym/utils/colorize.py of the pinned gym<1).
 """
 import sys
 from io import StringIO
@@ -12,7 +18,7 @@ from io import StringIO
 import numpy as np
 
 from . import codec
-from .batched_env import F_CAP, F_INVALID, BatchedChessEnv
+from .batched_env import F_BOT_PENDING, F_CAP, F_INVALID, F_REPETITION, BatchedChessEnv
 from .codec import (CASTLE_KING_SIDE_BLACK, CASTLE_KING_SIDE_WHITE, CASTLE_MOVES, CASTLE_QUEEN_SIDE_BLACK,
                     CASTLE_QUEEN_SIDE_WHITE, RESIGN)
 from .engine import ChessEngine
@@ -53,10 +59,31 @@ class _Box:
         return x.shape == tuple(self.shape) and bool((x >= self.low).all() and (x <= self.high).all())
 
 
+_COLOR2NUM = dict(gray=30, red=31, green=32, yellow=33, blue=34, magenta=35, cyan=36, white=37, crimson=38)
+
+
+def _colorize(string, color, bold=False, highlight=False):
+    # gym.utils.colorize: SGR code = colour number (+10 as a background), ";1" when bold
+    attrs = ";".join([str(_COLOR2NUM[color] + (10 if highlight else 0))] + (["1"] if bold else []))
+    return "\x1b[%sm%s\x1b[0m" % (attrs, string)
+
+
 def highlight(string, background="white", color="gray"):
-    # gym.utils.colorize stand-in (chess_v2.py:110-111): ANSI colours
-    colors = dict(gray=30, red=31, green=32, yellow=33, blue=34, magenta=35, cyan=36, white=37)
-    return "\x1b[%d;%dm%s\x1b[0m" % (colors[color], colors[background] + 10, string)
+    # chess_v2.py:110-111: colorize(colorize(string, color), background, highlight=True)
+    return _colorize(_colorize(string, color), background, highlight=True)
+
+
+def make_random_policy(np_random, bot_player):
+    """chess_v2.py:116-127: a uniform index into env.possible_moves drawn from the GLOBAL numpy generator (the
+    `np_random` argument is ignored there too, Q18); "resign" when there is no move (-> TypeError downstream, Q9)"""
+
+    def random_policy(env):
+        moves = env.possible_moves
+        if len(moves) == 0:
+            return "resign"
+        return moves[np.random.choice(np.arange(len(moves)))]
+
+    return random_policy
 
 
 class ChessEnvV2:
@@ -72,20 +99,18 @@ class ChessEnvV2:
         self.opponent = opponent
         self._seed, self._device = seed, device
         if isinstance(opponent, str):
-            if opponent not in ("random", "none"):
+            if opponent == "random":
+                self.opponent_policy = make_random_policy(None, self.player_2)
+            elif opponent == "none":
+                self.opponent_policy = None
+            else:
                 raise ValueError(f"Unrecognized opponent policy {opponent}")  # gym.error.Error in the reference
-            mode = opponent
         else:
-            # a callable opponent(env) -> move (chess_v2.py:178-179): the env runs in self-play mode on the device and
-            # the callable's ply is a second kernel step issued from the host
-            if player_color == BLACK:
-                raise NotImplementedError("callable opponents are supported for player_color='WHITE' only")
-            mode = "none"
-        if player_color == BLACK and mode == "none":
+            self.opponent_policy = opponent
+        if player_color == BLACK and self.opponent_policy is None:
             raise TypeError("'NoneType' object is not callable")  # what the reference does (Q23, chess_v2.py:208-209)
-        self._env = BatchedChessEnv(1, opponent=mode, player_color=player_color, seed=seed, device=device, auto_reset=False,
-                                    initial_boards=np.asarray(initial_board, np.int8))
-        self.opponent_policy = opponent if callable(opponent) else (None if opponent == "none" else "random")
+        self._env = BatchedChessEnv(1, opponent="none" if self.opponent_policy is None else "external", player_color=player_color,
+                                    seed=seed, device=device, auto_reset=False, initial_boards=np.asarray(initial_board, np.int8))
         self._first = True
         self.reset()
 
@@ -106,6 +131,28 @@ class ChessEnvV2:
         self._possible_moves = [codec.ACTION_TO_MOVE[a] for a in legal[0, : r[9]]]
         self._possible_actions = [int(a) for a in legal[0, : r[9]]]
 
+    def _log_ply(self, move):
+        # player_move's log (chess_v2.py:409-411): the mover and the move on the PRE-move board
+        print(" " * 10, ">" * 10, self.current_player)
+        self.render_moves([move], mode="human")
+
+    def _bot_ply(self):
+        """the opponent's ply: policy(env) -> move -> player_move without a membership test (chess_v2.py:277-283, 208-213).
+        -> (reward to add, done)"""
+        move = self.opponent_policy(self)
+        action = self.move_to_action(move)
+        if action is None or not isinstance(action, (int, np.integer)):
+            # "resign" (make_random_policy without moves, Q9) or anything else move_to_action does not know
+            raise TypeError("'>=' not supported between instances of 'NoneType' and 'int'")
+        if action < 4096 and self.board[(action >> 6) >> 3][(action >> 6) & 7] == 0:
+            raise RuntimeError("Bad move - piece is empty !")  # the reference's engine panics (lib.rs:693-695)
+        r, d, f = self._env.bot_ply(np.array([action], np.int32))
+        r, d, f = int(r[0]), bool(d[0]), int(f[0])
+        if self.log and not (f & F_REPETITION):
+            self._log_ply(self.action_to_move(action))
+        self._pull()
+        return r, d
+
     def reset(self):
         """chess_v2.py:183-217"""
         if not self._first:
@@ -114,10 +161,8 @@ class ChessEnvV2:
         self._pull()
         self.white_king_on_the_board = self.piece_is_on_board(self.board, KING_ID)    # set here only (Q8)
         self.black_king_on_the_board = self.piece_is_on_board(self.board, -KING_ID)
-        if self.player == BLACK:  # the board the kings were looked up on is the initial one (chess_v2.py:201-202)
-            ib = np.asarray(self.initial_board).tolist()
-            self.white_king_on_the_board = self.piece_is_on_board(ib, KING_ID)
-            self.black_king_on_the_board = self.piece_is_on_board(ib, -KING_ID)
+        if self.player == BLACK:  # the opponent opens for White (chess_v2.py:208-216)
+            self._bot_ply()
         return self.state
 
     def step(self, action):
@@ -126,26 +171,15 @@ class ChessEnvV2:
         was_done, capped = self.done, self.move_count > self.moves_max
         r, d, f = self._env.step_host(np.array([action], np.int32))
         reward, done, flags = int(r[0]), bool(d[0]), int(f[0])
-        if not (flags & F_INVALID) and (was_done or (flags & F_CAP) or capped):
+        played = not (flags & F_INVALID) and not was_done and not capped
+        if not (flags & F_INVALID) and (was_done or capped):
             reward = 0.0  # the two float literals of chess_v2.py:248,255
-        if self.log and not (flags & F_INVALID) and not was_done and not capped:
-            move = self.action_to_move(action)
-            print(" " * 10, ">" * 10, self.current_player)
-            self.render_moves([move], mode="human")
+        if played and self.log and not (flags & F_REPETITION):
+            self._log_ply(self.action_to_move(action))
         self._pull()
-        if callable(self.opponent_policy) and not (flags & F_INVALID) and not was_done and not capped and not done:
-            # bot ply from the host callable (chess_v2.py:277-288)
-            opp_move = self.opponent_policy(self)
-            opp_action = self.move_to_action(opp_move)
-            if opp_action is None or opp_action >= 4100:
-                raise TypeError("'>=' not supported between instances of 'NoneType' and 'int'")  # Q9
-            r2, d2, f2 = self._env.step_host(np.array([opp_action], np.int32))
-            self._pull()
-            # second kernel step returned -10 + capture (+100 if it mated the agent): fold into the agent's reward
-            mated = bool(int(f2[0]) & 2)
-            opp_reward = int(r2[0]) + 10 - (100 if mated else 0)
-            reward = reward - opp_reward + (-100 if mated else 0)
-            done = bool(d2[0])
+        if flags & F_BOT_PENDING:  # chess_v2.py:277-288
+            r2, done = self._bot_ply()
+            reward += r2
         return self.state, reward, done, self.info
 
     # ------------------------------------------------------------------ properties (chess_v2.py:301-391)

@@ -53,6 +53,7 @@ extern "C" {
                                 terminates here (stalemate is not a terminal state; with the random bot it raises
                                 TypeError).  Reported so that callers / auto-reset can act on it. */
 #define GCB_F_RESET 32u      /* the env was auto-reset after this step */
+#define GCB_F_BOT_PENDING 64u /* opponent 2 (external): the agent's ply is done, the bot's ply is owed (gcb_env_bot_ply) */
 
 const char *gcb_last_error(void);
 int gcb_version(void);
@@ -118,7 +119,10 @@ typedef struct {
     int32_t num_envs;       /* N on this device */
     uint32_t env_id_offset; /* global id of local env 0 (multi-GPU shards; enters the Philox counter) */
     uint64_t seed;          /* Philox key */
-    int32_t opponent;       /* 0 = "none" (self-play, one ply per step), 1 = "random" (bot replies inside step) */
+    int32_t opponent;       /* 0 = "none" (self-play, one ply per step), 1 = "random" (bot replies inside step, drawn on
+                               the device), 2 = "external": a callable opponent (chess_v2.py:171-179) -- the step stops
+                               where the bot would move, reports GCB_F_BOT_PENDING and the reward so far, and the caller
+                               supplies the bot's ply with gcb_env_bot_ply */
     int32_t agent_black;    /* player_color == "BLACK": the bot opens at reset (chess_v2.py:208-216) */
     int32_t auto_reset;     /* reset an env in the same step in which it terminates (done | cap | wedged) */
     int32_t piece_slots;    /* slots of the per-env legal set (one 64-bit target set per own piece of the side to
@@ -152,6 +156,13 @@ int gcb_env_import(gcb_env *env, const int8_t *d_boards, const int8_t *d_players
  * d_reward int32[N] (the two float 0.0 literals are 0), d_done uint8[N], d_flags uint8[N] (GCB_F_*). */
 int gcb_env_step(gcb_env *env, const int32_t *d_actions, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
                  void *stream);
+/* The bot's ply of an env created with opponent 2 (external), for every env that owes one (after a step that reported
+ * GCB_F_BOT_PENDING, or after a reset with agent_black): d_bot_actions int32[N] is applied the way the reference applies
+ * opponent_policy(env) -- player_move without a membership test (chess_v2.py:277-288, 208-216).  Outputs like gcb_env_step,
+ * written only for envs that owed a ply: d_reward = -(the bot's capture value) - 100 if the agent is mated (to be ADDED to
+ * the reward of the agent's half), d_done, d_flags.  Envs that owe nothing are left alone. */
+int gcb_env_bot_ply(gcb_env *env, const int32_t *d_bot_actions, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
+                    void *stream);
 /* same, but env i plays possible_actions[i][(u32[i] * n_legal[i]) >> 32] (RESIGN when it has no legal move): the uniform
  * draw of make_random_policy (chess_v2.py:116-127) with caller-provided random words */
 int gcb_env_step_index(gcb_env *env, const uint32_t *d_u32, int32_t *d_reward, uint8_t *d_done, uint8_t *d_flags,
@@ -166,10 +177,11 @@ int gcb_env_step_sampled(gcb_env *env, int nsteps, int32_t *d_reward, uint8_t *d
 
 /* HOST-buffer forms (synchronous; what a binding of the reference env calls).  Page-locked buffers (cudaHostAlloc /
  * cudaHostRegister / torch pin_memory) are read and written IN PLACE by the step kernel through their device aliases --
- * one launch, no staging copy; pageable buffers are staged in up to 4 pipelined chunks.  Both order themselves after
- * earlier work on the default stream only. */
-int gcb_env_step_host(gcb_env *env, const int32_t *actions, int32_t *reward, uint8_t *done, uint8_t *flags);
-int gcb_env_step_index_host(gcb_env *env, const uint32_t *u32, int32_t *reward, uint8_t *done, uint8_t *flags);
+ * one launch, no staging copy; pageable buffers are staged in up to 4 pipelined chunks.  The step is ordered after the work
+ * already enqueued on `stream` (NULL = the default stream) and has finished when the call returns. */
+int gcb_env_step_host(gcb_env *env, const int32_t *actions, int32_t *reward, uint8_t *done, uint8_t *flags, void *stream);
+int gcb_env_step_index_host(gcb_env *env, const uint32_t *u32, int32_t *reward, uint8_t *done, uint8_t *flags,
+                            void *stream);
 
 /* Asynchronous HOST-buffer forms: page-locked buffers ONLY (GCB_E_ARG otherwise -- nothing is staged); the step is
  * enqueued on `stream` and the call returns; the outputs are valid once gcb_env_wait(env, stream) (or any other
@@ -232,6 +244,19 @@ int gcb_env_stats_reset(gcb_env *env, void *stream);
 /* device pointer to the 16 counters (for an NCCL reduce by the caller); the totals are brought up to date by a small
  * reduction kernel enqueued on `stream` */
 int gcb_env_stats_ptr(gcb_env *env, uint64_t **d_stats, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Memory-safety net (test support; compute-sanitizer is not available on the GPU pool this was built on).
+ * (1) Guard regions: with GCB_GUARD_BYTES=<n> in the environment when gcb_env_create runs, every device array of the
+ *     env sits between two regions of n (rounded up to 256) bytes filled with 0xA5; gcb_env_check_guards counts the guard
+ *     bytes that no longer hold the pattern (0 = no kernel wrote outside an array).  GCB_E_ARG for an env without guards.
+ * (2) The CHECKED build of the library (libgymchess_b200_checked.so, -DGCB_CHECKED) verifies the index of every indexed
+ *     global access of the env kernels against the extent of its array; gcb_debug_violations returns the bit set of
+ *     violated checks (always 0 in the product build, gcb_build_is_checked() == 0) and optionally clears it.
+ * ------------------------------------------------------------------------------------------ */
+int gcb_env_check_guards(gcb_env *env, uint64_t *n_bad_bytes);
+int gcb_debug_violations(uint64_t *out, int reset);
+int gcb_build_is_checked(void);
 
 #ifdef __cplusplus
 }

@@ -587,6 +587,32 @@ void gco_selfplay(gco_env *e, uint64_t nsteps, gco_stats *st) {
     }
 }
 
+/* Positions for the fixed movegen test set (tests/positions_1m.py): env `id` plays `nsteps` sampled self-play steps (same
+ * draws and auto-reset as gco_selfplay) and the position BEFORE step t is recorded whenever t % every == id % every, so
+ * every ply index of a game is equally likely.  Returns the number of positions written (<= cap). */
+int gco_harvest(uint64_t seed, uint32_t env_lo, uint32_t env_hi, uint64_t nsteps, int every, int8_t *boards,
+                int8_t *players, uint8_t *rights, int cap) {
+    int n = 0;
+    gco_stats st;
+    memset(&st, 0, sizeof(st));
+    for (uint32_t id = env_lo; id < env_hi && n < cap; id++) {
+        gco_env e;
+        gco_env_init(&e, NULL, 0, GCO_OPP_NONE, seed, id);
+        for (uint64_t t = 0; t < nsteps && n < cap; t++) {
+            if ((int)(t % (uint64_t)every) == (int)(id % (uint32_t)every)) {
+                memcpy(boards + (size_t)n * 64, e.st.board, 64);
+                players[n] = e.st.current_player;
+                rights[(size_t)n * 4 + 0] = e.st.wk, rights[(size_t)n * 4 + 1] = e.st.wq;
+                rights[(size_t)n * 4 + 2] = e.st.bk, rights[(size_t)n * 4 + 3] = e.st.bq;
+                n++;
+            }
+            gco_selfplay(&e, 1, &st);
+        }
+        gco_env_free(&e);
+    }
+    return n;
+}
+
 typedef struct {
     uint64_t seed, nsteps;
     uint32_t lo, hi;

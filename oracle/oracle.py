@@ -98,6 +98,7 @@ def lib():
         L.gco_movegen_batch_mt.argtypes = L.gco_movegen_batch.argtypes + [C.c_int]
         L.gco_next_state_batch.argtypes = [C.c_int] + [C.c_void_p] * 9
         L.gco_update_state_batch.argtypes = [C.c_int] + [C.c_void_p] * 4
+        L.gco_harvest.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int] + [C.c_void_p] * 3 + [C.c_int]
         L.gco_default_board.restype = C.POINTER(C.c_int8 * 64)
         _lib = L
     return _lib
@@ -282,6 +283,27 @@ class SelfplayPool:
         if getattr(self, "_h", None):
             lib().gco_pool_free(self._h)
             self._h = None
+
+
+def harvest(seed, env_lo, env_hi, nsteps, every, threads=1):
+    """positions of sampled self-play games of envs [env_lo, env_hi), uniform over the ply index
+    -> (boards int8[n,64], players int8[n], rights uint8[n,4]); deterministic (independent of `threads`)"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    L = lib()
+    per = -(-int(nsteps) // int(every)) + 1
+
+    def run(lo, hi):
+        cap = (hi - lo) * per
+        b, p, r = np.zeros((cap, 64), np.int8), np.zeros(cap, np.int8), np.zeros((cap, 4), np.uint8)
+        n = L.gco_harvest(seed, lo, hi, nsteps, every, b.ctypes.data, p.ctypes.data, r.ctypes.data, cap)
+        return b[:n], p[:n], r[:n]
+
+    threads = max(1, min(int(threads), env_hi - env_lo))
+    cuts = [env_lo + (env_hi - env_lo) * t // threads for t in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL during the call
+        parts = list(ex.map(lambda k: run(cuts[k], cuts[k + 1]), range(threads)))
+    return tuple(np.concatenate([q[i] for q in parts]) for i in range(3))
 
 
 def draw_u32(seed, env_id, episode, step, purpose):

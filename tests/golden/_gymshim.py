@@ -46,7 +46,16 @@ def install():
     error = types.ModuleType("gym.error")
     error.Error = Error
     utils = types.ModuleType("gym.utils")
-    utils.colorize = lambda string, color=None, bold=False, highlight=False: string
+    # gym.utils.colorize as published by OpenAI gym (gym/utils/colorize.py; the reference pins gym>=0,<1, setup.py:39,
+    # which is not under /root/reference): ANSI SGR code = colour number (+10 as a background), ";1" when bold
+    color2num = dict(gray=30, red=31, green=32, yellow=33, blue=34, magenta=35, cyan=36, white=37, crimson=38)
+
+    def colorize(string, color, bold=False, highlight=False):
+        num = color2num[color] + (10 if highlight else 0)
+        attrs = ";".join([str(num)] + (["1"] if bold else []))
+        return "\x1b[%sm%s\x1b[0m" % (attrs, string)
+
+    utils.colorize = colorize
     seeding = types.ModuleType("gym.utils.seeding")
 
     def np_random(seed=None):

@@ -96,7 +96,7 @@ class EmulEnv:
         slots = 16
         if tb is not None:
             slots = max(16, int(max((tb > 0).sum(1).max(), (tb < 0).sum(1).max())))
-        self._h = lib().emul_env_create(num_envs, env_id_offset, seed, {"none": 0, "random": 1}[opponent],
+        self._h = lib().emul_env_create(num_envs, env_id_offset, seed, {"none": 0, "random": 1, "external": 2}[opponent],
                                         int(player_color == "BLACK"), int(auto_reset), slots, history_cap, moves_max,
                                         nt, _p(tb))
 
@@ -120,6 +120,9 @@ class EmulEnv:
 
     def step_sampled(self):
         return self._step(2, None)
+
+    def bot_ply(self, bot_actions):
+        return self._step(4, np.ascontiguousarray(np.asarray(bot_actions, np.int32)))
 
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(np.asarray(mask, np.uint8))

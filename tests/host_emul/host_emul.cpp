@@ -142,7 +142,7 @@ EmulEnv* emul_env_create(int N, uint32_t env_offset, uint64_t seed, int opponent
     return E;
 }
 
-// mode: 0 actions, 1 index words, 2 sampled, 3 reset (in = uint8 mask or NULL)
+// mode: 0 actions, 1 index words, 2 sampled, 3 reset (in = uint8 mask or NULL), 4 the bot ply of an external opponent
 void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, int32_t* act_out,
                    int32_t* bot_out) {
     StepIO io;
@@ -156,6 +156,7 @@ void emul_env_step(EmulEnv* E, int mode, const void* in, int32_t* reward, uint8_
         case 0: env_step_one<MODE_ACTION>(E->v, io, e, st, &scratch); break;
         case 1: env_step_one<MODE_INDEX>(E->v, io, e, st, &scratch); break;
         case 2: env_step_one<MODE_SAMPLED>(E->v, io, e, st, &scratch); break;
+        case 4: env_step_one<MODE_BOTPLY>(E->v, io, e, st, &scratch); break;
         default:
             if (!in || ((const uint8_t*)in)[e]) env_step_one<MODE_RESET>(E->v, io, e, st, &scratch);
         }

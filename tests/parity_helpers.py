@@ -25,7 +25,7 @@ def load_golden():
     with open(os.path.join(GOLD, "reference_v2_tests.json")) as f:
         ref = json.load(f)
     return dict(reference_tests=ref, trajectories=gz("trajectories.json.gz"), positions=gz("positions.json.gz"),
-                v1_move_sets=gz("v1_move_sets.json.gz"))
+                v1_move_sets=gz("v1_move_sets.json.gz"), render_info=gz("render_info.json.gz"))
 
 
 # ------------------------------------------------------------------ engine level
@@ -293,6 +293,46 @@ def check_trajectory_replay(make_env, traj):
         assert (int(r[0]), bool(d[0])) == (int(s["reward"]), bool(s["done"])), (traj["name"], traj["seed"], i, r, d, s["reward"], s["done"])
         cmp(s, (traj["name"], traj["seed"], i))
     return len(traj["steps"])
+
+
+def check_external_bot_replay(make_env, traj):
+    """Replay a recorded game of the REAL chess_v2.py against its (callable) bot through a 1-env device env created with
+    opponent="external": every step stops where the bot would move (F_BOT_PENDING) and the recorded bot move is supplied
+    with bot_ply() -- WHITE and BLACK agents (the BLACK agent's reset owes White's opening ply, chess_v2.py:208-216)."""
+    assert traj["opponent"] == "random"
+    env = make_env(np.array(traj["initial_board"], np.int8), traj["player_color"])
+
+    def cmp(s, where):
+        b, info, legal = env.export()
+        assert [int(x) for x in b[0]] == s["board"], where
+        assert [int(x) for x in info[0, 1:7]] == s["flags"], where
+        assert int(info[0, 8]) == s["move_count"], where
+        assert int(info[0, 0]) == (1 if s["current_player"] == "WHITE" else -1), where
+        assert [int(x) for x in legal[0, : info[0, 9]]] == s["legal"], where
+        assert int(info[0, 14]) == 0, where  # nothing owed between steps
+
+    if traj["player_color"] == "BLACK":
+        assert int(env.export()[1][0, 14]) == 1  # the opening ply is owed
+        env.bot_ply(np.array([traj["reset"]["bot_action"]], np.int32))
+    cmp(traj["reset"], (traj["name"], "reset"))
+    n = 0
+    for i, s in enumerate(traj["steps"]):
+        if s["raised"]:  # the bot had no move: the reference raises TypeError (Q9); here the ply stays owed
+            r, d, f = env.step(np.array([s["action"]], np.int32))[:3]
+            assert int(f[0]) & 64 and s["bot_action"] < 0
+            break
+        r, d, f = env.step(np.array([s["action"]], np.int32))[:3]
+        reward, done = int(r[0]), bool(d[0])
+        if int(f[0]) & 64:
+            assert s["bot_action"] >= 0, (traj["name"], i)
+            r2, d2, f2 = env.bot_ply(np.array([s["bot_action"]], np.int32))[:3]
+            reward, done = reward + int(r2[0]), bool(d2[0])
+        else:
+            assert s["bot_action"] < 0, (traj["name"], i)
+        assert (reward, done) == (int(s["reward"]), bool(s["done"])), (traj["name"], traj["seed"], i, reward, done, s["reward"], s["done"])
+        cmp(s, (traj["name"], traj["seed"], i))
+        n += 1
+    return n
 
 
 def queen_heavy_boards():

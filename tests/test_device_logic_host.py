@@ -23,6 +23,9 @@ class EmulAdapter:
     def step_sampled(self):
         return self.e.step_sampled()
 
+    def bot_ply(self, a):
+        return self.e.bot_ply(a)
+
     def export(self):
         return self.e.export()
 
@@ -131,6 +134,18 @@ def test_env_replays_real_chess_v2_selfplay_games(golden):
             continue
         n += ph.check_trajectory_replay(lambda ib: EmulAdapter(1, opponent="none", auto_reset=False, initial_boards=ib), t)
     assert n > 5000
+
+
+def test_external_opponent_replays_real_chess_v2_bot_games(golden):
+    """opponent="external" (callable opponents, chess_v2.py:171-179): the recorded WHITE- and BLACK-agent games of the real
+    chess_v2.py against its callable bot, the bot's plies supplied from outside"""
+    n = 0
+    for t in golden["trajectories"]:
+        if t["opponent"] != "random":
+            continue
+        n += ph.check_external_bot_replay(
+            lambda ib, color: EmulAdapter(1, opponent="external", player_color=color, auto_reset=False, initial_boards=ib), t)
+    assert n > 4000
 
 
 def test_many_piece_templates_use_more_slots():

@@ -279,43 +279,87 @@ def test_more_than_255_legal_moves():
     assert a.stats() == b.stats()
 
 
+def _compat_snapshot(env, info, printed):
+    moves = env.possible_moves
+    d = dict(info)
+    d["possible_moves"] = [int(env.move_to_action(m)) for m in d["possible_moves"]]
+    d = {k: (v if isinstance(v, (list, str)) else int(v)) for k, v in d.items()}
+    return dict(render=env.render(mode="string"), render_moves=env.render_moves(moves, mode="string"),
+                move_strings=[env.move_to_string(m) for m in moves], info=d, stdout=printed)
+
+
 def test_compat_env_v2_replays_recorded_games(golden):
-    """the single-env gym-style class (reference surface) against games recorded from the REAL chess_v2.py: self-play,
-    and WHITE vs a callable opponent that replays the recorded bot moves (chess_v2.py:171-179 accepts callables)"""
+    """the single-env gym-style class (reference surface) against games recorded from the REAL chess_v2.py: self-play and
+    WHITE / BLACK agents against a callable opponent that replays the recorded bot moves (chess_v2.py:171-179 accepts
+    callables); besides (state, reward, done), everything the text / info side returns is compared with what the real
+    chess_v2.py returned along the same game (tests/golden/make_golden_render.py): render(mode="string"),
+    render_moves(possible_moves, "string"), move_to_string of every legal move, the whole info dict (incl. the stale
+    *_king_on_the_board of Q8) and what log=True printed (chess_v2.py:337-353, 409-411, 422-490, 542-556)"""
+    import contextlib
+    import io
+
     from gym_chess_b200 import ChessEnvV2, codec
 
-    done_games = 0
-    for t in golden["trajectories"]:
-        if t["player_color"] != "WHITE" or done_games >= 14:
-            continue
-        if any(s["raised"] for s in t["steps"]):
-            continue
-        bot_moves = [s["bot_action"] for s in t["steps"]]
-        it = iter(bot_moves)
-        if t["opponent"] == "none":
-            env = ChessEnvV2(opponent="none", log=False, initial_board=np.array(t["initial_board"], np.int8).reshape(8, 8))
-        else:
-            cursor = {"i": 0}
+    games = steps = 0
+    modes = set()
+    for idx, rec in golden["render_info"].items():
+        t = golden["trajectories"][int(idx)]
+        bots = [t["reset"]["bot_action"]] + [s["bot_action"] for s in t["steps"]]
+        cur = {"i": 0}
 
-            def bot(e, cursor=cursor, moves=bot_moves):
-                return codec.action_to_move(moves[cursor["i"]])
+        def bot(e, cur=cur, bots=bots):
+            a = bots[cur["i"]]
+            return "resign" if a < 0 else codec.action_to_move(a)
 
-            env = ChessEnvV2(opponent=bot, log=False, initial_board=np.array(t["initial_board"], np.int8).reshape(8, 8))
-        assert [v for row in env.state["board"] for v in row] == t["reset"]["board"]
-        assert env.possible_actions == t["reset"]["legal"]
-        for i, s in enumerate(t["steps"][:120]):
-            if t["opponent"] != "none":
-                cursor["i"] = i
-            state, reward, done, info = env.step(s["action"])
-            assert (reward, done) == (s["reward"], s["done"]), (t["name"], i, reward, done, s["reward"], s["done"])
+        out = io.StringIO()
+        with contextlib.redirect_stdout(out):
+            env = ChessEnvV2(player_color=t["player_color"], opponent=(bot if t["opponent"] == "random" else "none"), log=True,
+                             initial_board=np.array(t["initial_board"], np.int8).reshape(8, 8))
+        assert _compat_snapshot(env, env.info, out.getvalue()) == rec["reset"], (t["name"], "reset")
+        assert [v for row in env.state["board"] for v in row] == t["reset"]["board"] and env.possible_actions == t["reset"]["legal"]
+        for i, want in enumerate(rec["steps"]):
+            s = t["steps"][i]
+            cur["i"] = i + 1
+            out = io.StringIO()
+            with contextlib.redirect_stdout(out):
+                state, reward, done, info = env.step(s["action"])
+            assert (reward, done) == (s["reward"], s["done"]) and type(reward) is type(s["reward"]), (t["name"], i, reward, s["reward"])
             assert [v for row in state["board"] for v in row] == s["board"], (t["name"], i)
-            assert env.possible_actions == s["legal"] and info["move_count"] == s["move_count"], (t["name"], i)
-            assert state["current_player"] == s["current_player"]
-            if done:
-                break
+            assert env.possible_actions == s["legal"] and state["current_player"] == s["current_player"], (t["name"], i)
+            got = _compat_snapshot(env, info, out.getvalue())
+            assert got == want, (t["name"], t["player_color"], i, {k: (got[k], want[k]) for k in got if got[k] != want[k]})
+            steps += 1
         env.close()
-        done_games += 1
-    assert done_games >= 10
+        games += 1
+        modes.add((t["player_color"], t["opponent"]))
+    assert games >= 50 and steps > 3000 and len(modes) == 3
+
+
+def test_compat_env_v2_random_opponent_uses_the_global_numpy_generator():
+    """opponent="random" draws like the reference's make_random_policy (np.random.choice over possible_moves, the GLOBAL
+    generator, chess_v2.py:116-127): replaying the same np.random stream through a callable gives the same game"""
+    from gym_chess_b200 import ChessEnvV2
+
+    for color in ("WHITE", "BLACK"):
+        np.random.seed(123)
+        a = ChessEnvV2(player_color=color, opponent="random", log=False)
+        rng = np.random.RandomState(5)
+        acts = []
+        for _ in range(60):
+            if a.done or not a.possible_actions:
+                break
+            acts.append(a.possible_actions[rng.randint(len(a.possible_actions))])
+            a.step(acts[-1])
+        np.random.seed(123)
+
+        def policy(env):
+            return env.possible_moves[np.random.choice(np.arange(len(env.possible_moves)))]
+
+        b = ChessEnvV2(player_color=color, opponent=policy, log=False)
+        for x in acts:
+            b.step(x)
+        assert a.state == b.state and a.info == b.info and len(acts) > 20
+        a.close(), b.close()
 
 
 def test_host_step_paths_agree():
@@ -648,3 +692,49 @@ def test_compat_env_v2_state_setter():
     eng = ChessEngine()
     assert [codec_s for codec_s in eng.get_possible_moves(s, env.current_player)] == [env.move_to_str_code(m) for m in other.possible_moves]
     env.close(), other.close()
+
+
+def test_config2_fixed_positions_full_byte_compare():
+    """BASELINE.json configs[1] / SURVEY.md 8(d) "Config 2" as specified: the FIXED 1,048,576-position set (tests/golden/
+    make_positions_1m.py: ~92 % seeded self-play uniform over the ply index, ~8 % crafted -- every board of the reference's
+    own v2 tests, castle-through-attack, OR-rights Q4, kings on rays Q6, kingless Q7, multi-king Q15, pawns on rows 0/7 Q1,
+    pawn jumps Q13, double checks, both sides to move).  Every ordered list, count and in-check flag of ALL positions is
+    byte-compared with the oracle, legal lists and attack lists; the set's SHA-256 is the committed one, and its self-play
+    share is regenerated here by the CUDA env (same Philox counters as the oracle's harvest)."""
+    import os
+    import torch
+    from gym_chess_b200 import _lib
+    from gym_chess_b200._lib import Positions, check
+    from tests.golden import make_positions_1m as mp
+
+    boards, players, rights = mp.build(lambda *a: mp.harvest_gpu(*a))
+    assert mp.digest(boards, players, rights) == mp.committed_digest()
+    n = len(boards)
+    assert n == 1 << 20
+    dev = torch.device("cuda", 0)
+    L = _lib.lib()
+    d_b, d_p, d_r = torch.from_numpy(boards).to(dev), torch.from_numpy(players).to(dev), torch.from_numpy(rights).to(dev)
+    bb01 = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    bb23 = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    pl, rt = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    pos = Positions(bb01.data_ptr(), bb23.data_ptr(), pl.data_ptr(), rt.data_ptr())
+    check(L.gcb_pack(n, d_b.data_ptr(), d_p.data_ptr(), d_r.data_ptr(), pos, None))
+    threads = os.cpu_count() or 1
+    orr, oc = orc.update_state_batch(boards, rights)
+    exp_chk = np.where(players > 0, oc[:, 0], oc[:, 1])
+    stride = 256
+    for attack in (0, 1):
+        out = torch.zeros((n, stride), dtype=torch.int16, device=dev)
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        chk = torch.zeros(n, dtype=torch.uint8, device=dev)
+        check(L.gcb_get_possible_moves(n, pos, attack, 0, out.data_ptr(), stride, cnt.data_ptr(), chk.data_ptr(), None))
+        torch.cuda.synchronize()
+        exp, ecnt = orc.movegen_batch(boards, players, rights, bool(attack), stride=stride, threads=threads)
+        got, gcnt = out.cpu().numpy().view(np.uint16), cnt.cpu().numpy()
+        assert ecnt.max() <= stride and (gcnt == ecnt).all(), np.nonzero(gcnt != ecnt)[0][:10]
+        m = np.arange(stride)[None, :] < ecnt[:, None]
+        bad = ((got != exp) & m).any(1)
+        assert not bad.any(), (attack, np.nonzero(bad)[0][:10])
+        if not attack:
+            assert (chk.cpu().numpy() == exp_chk).all()
+            assert int(ecnt.sum()) > 24_000_000 and (ecnt == 0).sum() > 1000 and exp_chk.mean() > 0.05

@@ -15,9 +15,9 @@ wp = [C.c_void_p(words[i].data_ptr()) for i in range(8)]; rp, dp, fp = C.c_void_
 K = 300
 for name, args in (("reward+done+flags", (rp, dp, fp)), ("reward only", (rp, None, None)), ("no outputs", (None, None, None)),
                    ("reward+done+flags", (rp, dp, fp))):
-    for i in range(5): fn(h, wp[i % 8], *args)
+    for i in range(5): fn(h, wp[i % 8], *args, None)
     torch.cuda.synchronize(); t0 = time.time()
-    for i in range(K): fn(h, wp[i % 8], *args)
+    for i in range(K): fn(h, wp[i % 8], *args, None)
     torch.cuda.synchronize(); dt = time.time() - t0
     print("host step, %-18s: %.1f us/step, %.3e env steps/s" % (name, dt / K * 1e6, N * K / dt))
 dw = words.cuda()

@@ -11,9 +11,9 @@ words = torch.empty((8, N), dtype=torch.int32).pin_memory(); words.random_(-2**3
 h_r = torch.empty(N, dtype=torch.int32).pin_memory(); h_d = torch.empty(N, dtype=torch.uint8).pin_memory(); h_f = torch.empty(N, dtype=torch.uint8).pin_memory()
 L = _lib.lib(); fn = L.gcb_env_step_index_host; h = env._h
 wp = [C.c_void_p(words[i].data_ptr()) for i in range(8)]; rp, dp, fp = C.c_void_p(h_r.data_ptr()), C.c_void_p(h_d.data_ptr()), C.c_void_p(h_f.data_ptr())
-for i in range(5): fn(h, wp[i % 8], rp, dp, fp)
+for i in range(5): fn(h, wp[i % 8], rp, dp, fp, None)
 torch.cuda.synchronize(); t0 = time.time(); K = 300
-for i in range(K): fn(h, wp[i % 8], rp, dp, fp)
+for i in range(K): fn(h, wp[i % 8], rp, dp, fp, None)
 torch.cuda.synchronize(); dt = time.time() - t0
 print("raw ctypes: %.1f us/step, %.3e env steps/s e2e" % (dt / K * 1e6, N * K / dt))
 # kernel-only single step for comparison (device words)
