@@ -105,6 +105,7 @@ SIGNATURES = {
     "gcb_env_export": (i32, [vp, vp, vp, vp]),
     "gcb_env_legal_mask": (i32, [vp, vp, vp]),
     "gcb_env_legal_bitmask": (i32, [vp, vp, i32, vp]),
+    "gcb_env_step_mask_output": (i32, [vp, vp, i32]),
     "gcb_env_legal_actions": (i32, [vp, vp, i32, vp, vp]),
     "gcb_env_piece_slots": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_int32)]),
     "gcb_env_positions": (i32, [vp, C.POINTER(Positions)]),

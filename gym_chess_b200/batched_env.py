@@ -163,6 +163,16 @@ class BatchedChessEnv:
             return self.reward, self.done, self.flags, acts, bots
         return self.reward, self.done, self.flags
 
+    def dephase(self, groups=43, period=301):
+        """Spread the episode phases of a batch that was reset together.  Three random self-play episodes in four end at the
+        150-move cap after exactly `period` = 301 steps (chess_v2.py:252-258), so such a batch moves through the game in
+        lockstep for good -- every later window sees one narrow band of plies.  Group g (global env id % groups) is reset
+        again after (g + 1) * (period // groups) sampled steps, which leaves the groups period // groups steps apart."""
+        ids = torch.arange(self.num_envs, device=self.device) + self.env_id_offset
+        for g in range(groups):
+            self.step_sampled(max(1, period // groups))
+            self.reset(ids % groups == g)
+
     # ------------------------------------------------------------------ stepping (host buffers, copies inside)
     def step_host(self, actions, reward=None, done=None, flags=None):
         """numpy in / numpy out through gcb_env_step_host (H2D + kernel + D2H inside the call)."""
@@ -261,6 +271,16 @@ class BatchedChessEnv:
             check(_lib.lib().gcb_env_legal_bitmask(self._h, C.c_void_p(m.data_ptr()), int(m.stride(0)), _stream_ptr()))
         return m
 
+    def set_mask_output(self, bits=None):
+        """Register (or, with None, remove) a cuda int64 [N, W >= 65] buffer that EVERY later step call fills with the bit mask
+        of possible_actions of the state the step leaves behind (layout of legal_bitmask) -- written by the step kernel
+        itself while the legal set sits in shared memory.  An even W (66) lets the rows be written as 16-byte stores."""
+        if bits is not None:
+            assert bits.is_cuda and bits.dtype == torch.int64 and bits.dim() == 2 and bits.shape[0] == self.num_envs and bits.stride(1) == 1
+        self._mask_out = bits  # keeps the buffer alive
+        check(_lib.lib().gcb_env_step_mask_output(self._h, None if bits is None else C.c_void_p(bits.data_ptr()),
+                                                  0 if bits is None else int(bits.stride(0))))
+
     @staticmethod
     def unpack_bitmask(bits):
         """int64 [N, 65] bit mask -> bool [N, 4101] (torch ops; for tests and small batches)"""
@@ -328,3 +348,12 @@ class BatchedChessEnv:
         p = Positions()
         check(_lib.lib().gcb_env_positions(self._h, C.byref(p)))
         return p
+
+    def planes(self):
+        """zero-copy views of the resident board: (int64 [N, 2] bit-planes t0 | t1, int64 [N, 2] bit-plane t2 | colour plane
+        white) -- piece code (t2 t1 t0) = the reference id: K=001 Q=010 R=011 B=100 N=101 P=110; square = row * 8 + col, row 0 =
+        rank 8.  This is the observation a learner can read without any export kernel (32 B per env)."""
+        p = self.positions()
+        with torch.cuda.device(self.device):
+            return (torch.as_tensor(_DevArray(p.bb01, (self.num_envs, 2), "<i8"), device=self.device),
+                    torch.as_tensor(_DevArray(p.bb23, (self.num_envs, 2), "<i8"), device=self.device))

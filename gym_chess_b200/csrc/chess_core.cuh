@@ -572,11 +572,15 @@ GCB_HD void emit_piece_moves(Emit& em, int code, int white, int sq, u64 T) {
 
 // the idx-th (0-based) target of one piece in the reference's order; idx < popc(T).  Same instructions for every
 // piece type: find the direction that holds the idx-th target, then walk idx squares along it (nearest first).
+// ROLLED: a loop with early exit (8x less code: what the multi-step kernel wants, whose hot loop has to fit the instruction
+// cache) or all 8 table loads issued at once (what the single-step kernels want: their caches are cold at every launch and
+// the rolled loop's dependent load -> popcount -> branch chain is paid at L2 latency)
+template <bool ROLLED = (GCB_ROLL_NTH != 0)>
 GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
     const int cls = order_class(code, white);
     u64 mf = 0;
     bool desc = false;
-#if GCB_ROLL_NTH
+  if (ROLLED) {
     // a rolled loop with early exit: 8x less code on the step kernel's hot path (its instruction footprint is what the
     // instruction cache holds)
 #if defined(__CUDA_ARCH__)
@@ -591,7 +595,7 @@ GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
         }
         idx -= c;
     }
-#else
+  } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -602,7 +606,7 @@ GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
         if (hit) mf = m, desc = (GCB_RAY_DESC_MASK >> k) & 1;
         if (!mf) idx -= c;
     }
-#endif
+  }
     if (!mf) return sq;
     if (desc) mf = gcb_brev64(mf);  // nearest first = lowest bit first in both cases
     const int t = gcb_select64(mf, idx);

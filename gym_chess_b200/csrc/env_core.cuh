@@ -268,7 +268,8 @@ struct StepStats {
     // slot_overflow (the kernel looks at them only when some lane of the warp has one)
     u32 f;
     int reward, legal, scan, window;
-    GCB_HD void clear() { f = 0, reward = 0, legal = 0, scan = 0, window = 0; }
+    bool wrote_slots;  // (not a statistic) the step rewrote the env's piece slots: a ply was generated or a reset copied its template
+    GCB_HD void clear() { f = 0, reward = 0, legal = 0, scan = 0, window = 0, wrote_slots = false; }
     GCB_HD int get(int k) const {
         switch (k) {
         case ST_STEPS: return (int)(f & 127u);
@@ -312,6 +313,22 @@ struct StepStats {
 // The table has 2 * history_cap slots, so while the window fits history_cap the load factor stays <= 1/2 and a probe
 // sequence of 128 slots cannot be exhausted in practice (expected length 1.5 - 2.5).
 #define GCB_REP_MAX_PROBES 128
+#ifndef GCB_REP_PREFETCH
+#define GCB_REP_PREFETCH 1
+#endif
+// The entry a ply will probe first is known as soon as the pre-move key is: ask L2 for its line at the START of the step, so
+// that the DRAM latency of this one randomly addressed access runs under the action pick instead of stalling the ply.
+GCB_HD void rep_prefetch(const EnvView& v, int e, const EnvRegs& s) {
+#if defined(__CUDA_ARCH__) && GCB_REP_PREFETCH
+    if (s.hist_len != 0) {
+        const unsigned mask = (unsigned)v.hist_mask;
+        const ulonglong2* p = v.rep + (size_t)e * ((size_t)mask + 1) + ((unsigned)(hist_key(s.zk) >> 24) & mask);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+#else
+    (void)v, (void)e, (void)s;
+#endif
+}
 GCB_HD int rep_lookup_insert(const EnvView& v, int e, const EnvRegs& s, u64 key, bool insert, StepStats& st) {
     const unsigned mask = (unsigned)v.hist_mask;
     unsigned i = (unsigned)(key >> 24) & mask;
@@ -359,6 +376,7 @@ GCB_HD u64 swar_le_u8(u64 x, u64 y) {
 
 // The action `possible_moves[idx]` of the reference-ordered list, decoded from the slots (chess_v2.py:116-127:
 // the uniform draw indexes the ORDERED list).  idx < n_legal.
+template <bool ROLLED = true>
 GCB_HD int action_at(const SlotRef& sr, const EnvRegs& s, int idx) {
     // which piece: prefix scan over the 16 count bytes (registers only); pieces beyond 16 (only on crafted initial
     // boards) by reading their slots
@@ -401,7 +419,7 @@ GCB_HD int action_at(const SlotRef& sr, const EnvRegs& s, int idx) {
     if (hit_r >= 0) {
         const u64 T = slots.get(hit_r);  // the one slot this draw needs
         const int sq = gcb_select64(own, hit_r);
-        return sq * 64 + nth_target(piece_code(s.b, sq), !s.stm_black, sq, T, hit_idx);
+        return sq * 64 + nth_target<ROLLED>(piece_code(s.b, sq), !s.stm_black, sq, T, hit_idx);
     }
     // castles come last, queen side first (lib.rs:1473-1479, 992, 1011)
     const int king_side = (s.castle & 1u) ? (idx - acc != 0) : 1;
@@ -458,6 +476,7 @@ GCB_HD int ply_and_movegen(const EnvView& v, int e, EnvRegs& s, int action, bool
     gen_prepare(s.b, !s.stm_black, g, geo);
     typename SinkOf<FAST>::type sink(sr, scratch);
     gen_targets(s.b, g, g.own, sink, geo);
+    st.wrote_slots = true;
     const int n = sink.total();
     if (sink.dropped) st.f += SF_SLOTOVF;
     s.cnt_lo = sink.count_lo(), s.cnt_hi = sink.count_hi();
@@ -491,7 +510,21 @@ struct StepIO {
     // per env: bits 0-7 reward (int8; a reward is always within [-120, 100]), bits 8-13 flags, bit 15 done
     uint16_t* packed = nullptr;
     int in16 = 0;
+    // learner-facing output of the step itself: possible_actions of the state the step leaves behind as the 65-word bit
+    // mask (uint64[N][bits_stride]); NULL = off
+    u64* bits_out = nullptr;
+    int bits_stride = 0;
 };
+// the step's input of env e (MODE_ACTION: the action; MODE_INDEX: the caller's random word as a 32-bit word; MODE_BOTPLY: the
+// bot's action): loaded FIRST, together with the state, so that its latency (it may sit in page-locked host memory, read
+// through PCIe) is not paid where it is used
+template <int MODE>
+GCB_HD u32 step_input(const StepIO& io, int e) {
+    if (MODE == MODE_ACTION) return io.in16 ? (u32)reinterpret_cast<const uint16_t*>(io.in)[e] : (u32)reinterpret_cast<const int32_t*>(io.in)[e];
+    if (MODE == MODE_INDEX) return io.in16 ? (u32)reinterpret_cast<const uint16_t*>(io.in)[e] << 16 : reinterpret_cast<const u32*>(io.in)[e];
+    if (MODE == MODE_BOTPLY) return (u32)reinterpret_cast<const int32_t*>(io.in)[e];
+    return 0u;
+}
 GCB_HD uint16_t pack_result(int reward, bool done, u32 flags) {
     return (uint16_t)((u32)(reward & 0xFF) | ((flags & 63u) << 8) | (done ? 0x8000u : 0u));
 }
@@ -522,9 +555,14 @@ GCB_HD void env_store(const EnvView& v, int e, const EnvRegs& s, u32 ep) {
 // chess_v2.py:219-294 for env `e` (plus auto-reset and the episode statistics of this step), state in registers
 // SELFPLAY = true: the caller guarantees opponent "none" (one ply per step, no bot, WHITE agent) -- the bot's branches
 // are compiled out of the self-play kernel.
-template <int MODE, bool SELFPLAY = false, bool FAST = false, class G>
+// MULTI = true: the step runs inside a multi-step launch (warm caches, a hot loop that has to fit the instruction cache):
+// rolled direction scan in the ordered pick, L2 prefetch of the ply's repetition entry at the start of the step.  Single-step
+// launches start with cold caches every time and run back to back over an L2-resident state that a prefetch would push out.
+template <int MODE, bool SELFPLAY = false, bool FAST = false, bool MULTI = false, class G>
 GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s, u32& ep, StepStats& st, CountBytes* scratch,
-                          const SlotRef& sr, const G& geo) {
+                          const SlotRef& sr, const SlotRef& pick_sr, const G& geo, const u32 input) {
+    // sr: where the generation writes the piece slots (and later picks of the same step read them); pick_sr: where the
+    // legal set of the state the step STARTS from lives (the same place, except in single-step tile kernels)
     // opponent: 0 none, 1 random (the bot draws on the device), 2 external (the step stops where the bot would move and
     // the caller supplies the bot's ply through MODE_BOTPLY: callable opponents, chess_v2.py:171-179)
     const bool v_bot = SELFPLAY ? false : v.opponent != 0, v_ext = SELFPLAY ? false : v.opponent == 2;
@@ -543,19 +581,19 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
         // membership test (chess_v2.py:277-283, 208-213)
         if (!s.pending) return;  // nothing owed: the env is left alone, no outputs
         s.pending = 0;
-        action = bot_action = reinterpret_cast<const int32_t*>(io.in)[e];
+        action = bot_action = (int)input;
         agent_ply = true;
         phase = (s.step == 0 && v_agent_black) ? PH_RESETBOT : PH_BOT;
     } else {
         bool valid = false;
+        if (MULTI) rep_prefetch(v, e, s);
         if (MODE == MODE_ACTION) {
-            action = io.in16 ? (int)reinterpret_cast<const uint16_t*>(io.in)[e] : reinterpret_cast<const int32_t*>(io.in)[e];
-            valid = action_is_legal(sr, s, action);  // action in possible_actions
+            action = (int)input;
+            valid = action_is_legal(pick_sr, s, action);  // action in possible_actions
         } else {
-            u32 u = (MODE == MODE_INDEX) ? (io.in16 ? (u32)reinterpret_cast<const uint16_t*>(io.in)[e] << 16 : reinterpret_cast<const u32*>(io.in)[e])
-                                         : philox_draw(v.seed, genv, ep, step_idx, 0u);
+            const u32 u = (MODE == MODE_INDEX) ? input : philox_draw(v.seed, genv, ep, step_idx, 0u);
             if (n0 > 0) {
-                action = action_at(sr, s, (int)gcb_umulhi(u, (u32)n0));
+                action = action_at<MULTI>(pick_sr, s, (int)gcb_umulhi(u, (u32)n0));
                 valid = true;
             }
         }
@@ -625,6 +663,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 {
                     TgtSink dst(sr, nullptr);
                     for (int r = 0; r < np && r < sr.slots; r++) dst.st(r, ts[r]);
+                    st.wrote_slots = true;
                 }
                 ep += (u32)io.ep_inc;
                 if (v_agent_black && v_ext) {
@@ -633,7 +672,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                     // the bot opens for White (chess_v2.py:208-216)
                     if (s.n_legal > 0) {
                         u32 u = philox_draw(v.seed, genv, ep, 0u, 2u);
-                        cur = action_at(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
+                        cur = action_at<MULTI>(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
                         do_apply = true;
                     } else {
                         do_apply = false;
@@ -660,7 +699,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             } else if (!s.done && v_bot) {
                 if (s.n_legal > 0) {  // chess_v2.py:277-288
                     u32 u = philox_draw(v.seed, genv, ep, step_idx, 1u);
-                    bot_action = action_at(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
+                    bot_action = action_at<MULTI>(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
                     cur = bot_action, phase = PH_BOT;
                     continue;
                 }
@@ -690,7 +729,9 @@ GCB_HD void env_step_one(const EnvView& v, const StepIO& io, int e, StepStats& s
     EnvRegs s;
     u32 ep;
     env_load(v, e, s, ep);
-    env_step_regs<MODE, false, false>(v, io, e, s, ep, st, scratch, resident_slots(v, e), GeomGlobal());
+    const SlotRef sr = resident_slots(v, e);
+    const u32 input = step_input<MODE>(io, e);
+    env_step_regs<MODE, false, false, false>(v, io, e, s, ep, st, scratch, sr, sr, GeomGlobal(), input);
     env_store(v, e, s, ep);
 }
 

@@ -74,6 +74,17 @@ struct DeviceScope {
 #ifndef GCB_SAMPLED_MIN_BLOCKS
 #define GCB_SAMPLED_MIN_BLOCKS 5
 #endif
+#ifndef GCB_SINGLE_TILE  // single-step launches generate on the shared-memory tile (TILE 2) when the env has 16 piece slots
+#define GCB_SINGLE_TILE 1
+#endif
+#ifndef GCB_BITS_STREAM  // bit-mask rows of the step kernels: streaming (evict-first) stores (1) or default write-back stores (0)
+#define GCB_BITS_STREAM 1
+#endif
+#if GCB_BITS_STREAM
+#define GCB_BITS_ST(p, v) __stcs((p), (v))
+#else
+#define GCB_BITS_ST(p, v) (*(p) = (v))
+#endif
 static inline int grid_for(int n) { return (n + GCB_BLOCK - 1) / GCB_BLOCK; }
 
 // ------------------------------------------------------------------------------------------------ pack / unpack
@@ -212,63 +223,115 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions
     if (checks) checks[i] = (uint8_t)check_flags(b);
 }
 
-// TILE (multi-step sampled launches with the default 16 piece slots): the slots live in a shared-memory tile for the whole
-// launch; a compile-time property so that slot accesses are plain LDS / STS with constant strides.
-// SELFPLAY: opponent "none" is a launch-time fact, so the self-play kernel carries no bot code (a smaller hot loop: the
+// possible_actions of the 32 envs of a warp as BIT masks, rows of `stride_words` 64-bit words (include/gymchess_b200.h,
+// gcb_env_legal_bitmask): word `from` of an env is exactly the legal-target set of the piece on that square, word 64 holds
+// the castles -- at most 17 of the 65 words are non-zero.  The rows of a warp's envs are contiguous, so the warp first
+// ZERO-FILLS the whole span with coalesced 16-byte stores, and after a warp barrier (which orders the two stores to the same
+// address) every thread SCATTERS its own env's non-zero words: one 8-byte store per own piece, slot index = a running count
+// along the ascending square scan.  ~10x fewer instructions than assembling the rows word by word with shuffles, which
+// matters because the step kernel that calls this is bound by the integer pipe.  `slots`: the calling thread's piece slots.
+__device__ __forceinline__ void write_bits_rows(u64* __restrict__ out, int stride_words, int e0, int e_end, bool active, int e,
+                                                u64 own, u32 cword, const SlotRef& slots, int lane) {
+    const int nrows = e_end - e0 < 32 ? e_end - e0 : 32;
+    if (nrows <= 0) return;
+    u64* const span = out + (size_t)e0 * (size_t)stride_words;
+    const int words = nrows * stride_words;
+    if (((stride_words & 1) == 0) && ((reinterpret_cast<uintptr_t>(span) & 15) == 0)) {
+        ulonglong2* q = reinterpret_cast<ulonglong2*>(span);
+        for (int i = lane; i < words / 2; i += 32) GCB_BITS_ST(q + i, make_ulonglong2(0ULL, 0ULL));
+    } else {
+        for (int i = lane; i < words; i += 32) GCB_BITS_ST(span + i, 0ULL);
+    }
+    __syncwarp();
+    if (active) {
+        u64* const row = out + (size_t)e * (size_t)stride_words;
+        TgtSink src(slots, nullptr);
+        int r = 0;
+        for (u64 t = own; t; t &= t - 1, r++) {
+            const u64 T = src.get(r);
+            if (T) GCB_BITS_ST(row + gcb_lsb(t), T);
+        }
+        if (cword) GCB_BITS_ST(row + 64, (u64)cword);
+    }
+}
+__device__ __forceinline__ u32 castle_word(const EnvRegs& s) {  // castle bits of meta -> bit (action - 4096)
+    u32 c = 0;
+    if (s.castle & 1u) c |= 1u << (castle_action(!s.stm_black, 0) - 4096);
+    if (s.castle & 2u) c |= 1u << (castle_action(!s.stm_black, 1) - 4096);
+    return c;
+}
+
+// One UNIT of step work of one block: the envs [e, ...) of the block's tile run `nsteps` consecutive steps.
+// TILE selects where the piece slots live while the unit runs:
+//   0  in their resident place (any number of slots; the generic path),
+//   1  multi-step units: staged into a shared-memory tile at the start, copied back at the end; slot accesses are plain
+//      LDS / STS with constant strides, the small geometry tables sit next to them in shared memory,
+//   2  single-step units: nothing is staged in -- the step's pick / validity test reads its ONE slot from the resident
+//      array -- but the generation still writes the new legal set into the tile (the cheap code path of 1) and the tile is
+//      copied out row by row at the end, only for envs whose legal set was rewritten.
+// SELFPLAY: opponent "none" is a launch-time fact, so the self-play kernels carry no bot code (a smaller hot loop: the
 // kernel's instruction footprint is what it waits for most).
-template <int MODE, bool TILE = false, bool SELFPLAY = false>
-// measured on B200: the multi-step sampled kernel is fastest with 4 resident blocks per SM (128 registers; more warps
-// thrash the instruction cache), the single-step kernels with 5 (96 registers)
-__global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_MIN_BLOCKS : GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
-    __shared__ CountBytes s_counts[GCB_BLOCK];
-    const int e = io.e_begin + blockIdx.x * blockDim.x + threadIdx.x;
+template <int MODE, int TILE, bool SELFPLAY>
+__device__ __forceinline__ void run_unit(const EnvView& v, StepIO io, const int e, const int nsteps, u64* s_slots, u64* s_geom,
+                                         CountBytes* s_counts) {
     const int lane = threadIdx.x & 31;
     bool active = e < io.e_end;
     if (MODE == MODE_RESET && active && io.in && !reinterpret_cast<const uint8_t*>(io.in)[e]) active = false;  // masked reset
-    // Sampled self-play runs `nsteps` consecutive steps in one launch: every env only depends on its own previous step,
-    // so a block simply keeps stepping its envs -- no launch gap, no wave tail between steps.
-    const int nsteps = MODE == MODE_SAMPLED ? io.nsteps : 1;
     long long acc = 0;  // lane k accumulates statistics counter k of this warp
     EnvRegs s;          // the env's state stays in registers from step to step
     u32 ep = 0;
-    if (active) env_load(v, e, s, ep);
-    // ... and its piece slots in a shared-memory tile (multi-step launches with the default 16 slots): the generation
-    // writes them and the next step's draw reads one of them without a round trip through L2
-    __shared__ u64 s_slots[TILE ? GCB_SLOTS * GCB_BLOCK : 1];
-    const bool tile = TILE;
-    const SlotRef gsr = resident_slots(v, e < io.e_end ? e : io.e_begin);
-    const SlotRef tsr = {s_slots + threadIdx.x, (unsigned)GCB_BLOCK, GCB_SLOTS, true};
+    // the block's copy of the small geometry tables: its loads are issued first and stored after the state loads have been
+    // issued too, so that the two latencies overlap (a single-step launch pays this start-up once per step)
+    u64 gw[(GCB_SGEOM_WORDS + GCB_BLOCK - 1) / GCB_BLOCK];
     if (TILE) {
-        if (active) {
-            const int np = gcb_popc(stm_pieces(s));
-            for (int r = 0; r < np && r < GCB_SLOTS; r++) s_slots[r * GCB_BLOCK + threadIdx.x] = __ldcs(gsr.base + (unsigned)r * gsr.stride);
+#pragma unroll
+        for (int k = 0; k < (GCB_SGEOM_WORDS + GCB_BLOCK - 1) / GCB_BLOCK; k++) {
+            const int i = threadIdx.x + k * GCB_BLOCK;
+            gw[k] = i < GCB_SGEOM_WORDS ? GeomShared::source_word(i) : 0ULL;
         }
     }
-    const SlotRef sr = TILE ? tsr : gsr;
-    // ... and the small geometry tables (5 KB) next to it
-    __shared__ u64 s_geom[TILE ? GCB_SGEOM_WORDS : 1];
+    u32 input = 0;
+    if (active) {
+        input = step_input<MODE>(io, e);  // (MODE_RESET's mask byte was read above; sampled runs have no input)
+        env_load(v, e, s, ep);
+    }
     if (TILE) {
-        for (int i = threadIdx.x; i < GCB_SGEOM_WORDS; i += GCB_BLOCK) s_geom[i] = GeomShared::source_word(i);
+#pragma unroll
+        for (int k = 0; k < (GCB_SGEOM_WORDS + GCB_BLOCK - 1) / GCB_BLOCK; k++) {
+            const int i = threadIdx.x + k * GCB_BLOCK;
+            if (i < GCB_SGEOM_WORDS) s_geom[i] = gw[k];
+        }
         __syncthreads();
     }
+    const SlotRef gsr = resident_slots(v, e < io.e_end ? e : io.e_begin);
+    const SlotRef tsr = {s_slots + threadIdx.x, (unsigned)GCB_BLOCK, GCB_SLOTS, true};
+    if (TILE == 1 && active) {
+        const int np = gcb_popc(stm_pieces(s));
+        for (int r = 0; r < np && r < GCB_SLOTS; r++) s_slots[r * GCB_BLOCK + threadIdx.x] = __ldcs(gsr.base + (unsigned)r * gsr.stride);
+    }
+    const SlotRef sr = TILE ? tsr : gsr;
     const GeomShared sgeo = {s_geom};
     // at most 16 pieces of either colour (always, from the standard start position: pieces only leave the board): the
-    // generation then stores its slots without bounds tests for the whole launch
+    // generation then stores its slots without bounds tests for the whole unit
     const bool small = TILE && active && gcb_popc(s.b.w) <= GCB_SLOTS && gcb_popc(bb_occ(s.b) & ~s.b.w) <= GCB_SLOTS;
     (void)small;
+    bool wrote = TILE == 1;  // TILE 2: does the tile hold this env's legal set (was it rewritten by this unit)?
 #pragma unroll 1
     for (int t = 0; t < nsteps; t++) {
         StepStats st;
         st.clear();
         if (active) {
+            // the first pick of a single-step unit reads the resident slot; everything later goes through the tile
+            const SlotRef& pick = (TILE == 2 && !wrote) ? gsr : sr;
             if (TILE) {
 #if GCB_FAST_SINK
-                if (small) env_step_regs<MODE, SELFPLAY, true>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, sgeo);
+                if (small) env_step_regs<MODE, SELFPLAY, true, TILE == 1>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, pick, sgeo, input);
                 else
 #endif
-                    env_step_regs<MODE, SELFPLAY, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, sgeo);
+                    env_step_regs<MODE, SELFPLAY, false, TILE == 1>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, pick, sgeo, input);
             } else
-                env_step_regs<MODE, SELFPLAY, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, GeomGlobal());
+                env_step_regs<MODE, SELFPLAY, false, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, pick, GeomGlobal(), input);
+            wrote = wrote || st.wrote_slots;
         }
         if (MODE != MODE_RESET) {
             // episode statistics: warp reduce (REDUX), lane k keeps counter k.  The three counters every step touches are
@@ -301,12 +364,21 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_
     }
     if (active) {
         env_store(v, e, s, ep);
-        if (tile) {  // slots of the side to move back to their resident place
+        if (TILE && wrote) {  // slots of the side to move back to their resident place
             const int np = gcb_popc(stm_pieces(s));
             for (int r = 0; r < np && r < GCB_SLOTS; r++) __stcs(v.tgt + (size_t)r * v.N + e, s_slots[r * GCB_BLOCK + threadIdx.x]);
         }
     }
-    // one coalesced read-modify-write of the warp's own row -- no atomics and no block barrier.  A warp that lies wholly
+    // learner-facing output of the step itself: possible_actions of the state the step leaves behind as
+    // the 65-word bit mask, written while the legal set still sits in the shared-memory tile (no second kernel, no re-read;
+    // envs whose legal set the step did not touch read it from its resident place)
+    if (io.bits_out) {
+        u64 own = 0;
+        u32 cword = 0;
+        if (active) own = stm_pieces(s), cword = castle_word(s);
+        write_bits_rows(io.bits_out, io.bits_stride, e - lane, io.e_end, active, e, own, cword, (TILE && wrote) ? sr : gsr, lane);
+    }
+    // one coalesced fire-and-forget add to the warp's own row -- no contention and no block barrier.  A warp that lies wholly
     // past the env range (the idle warps of the last block) owns no row: stat_rows has ceil(N / 32) of them.
     if (MODE != MODE_RESET && lane < ST_USED) {
 #if !defined(GCB_SELFTEST_OOB)  // (the self-test build of the checked library leaves the predicate out on purpose)
@@ -315,9 +387,20 @@ __global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_
         {
             const size_t row = (size_t)(e >> 5);
             GCB_CHK(row < (size_t)v.stat_nrows, CHK_STAT_ROW);
-            v.stat_rows[row * ST_COUNT + lane] += (u64)acc;
+            // (a reduction without a return value: the warp does not wait for the row; the row is this warp's own)
+            atomicAdd(reinterpret_cast<unsigned long long*>(v.stat_rows + row * ST_COUNT + lane), (unsigned long long)acc);
         }
     }
+}
+
+// one unit per block: the envs [io.e_begin, io.e_end), io.nsteps steps each (one for everything but the sampled mode)
+template <int MODE, int TILE = 0, bool SELFPLAY = false>
+__global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_MIN_BLOCKS : GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
+    __shared__ CountBytes s_counts[GCB_BLOCK];
+    __shared__ u64 s_slots[TILE ? GCB_SLOTS * GCB_BLOCK : 1];
+    __shared__ u64 s_geom[TILE ? GCB_SGEOM_WORDS : 1];
+    run_unit<MODE, TILE, SELFPLAY>(v, io, io.e_begin + blockIdx.x * GCB_BLOCK + threadIdx.x, MODE == MODE_SAMPLED ? io.nsteps : 1,
+                                   s_slots, s_geom, s_counts);
 }
 
 // totals = column sums of the per-warp rows (one block; deterministic order)
@@ -414,27 +497,28 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_mask(EnvView v, uint8_t
 // (0..63) is exactly the resident legal-target set of the piece on that square, word 64 holds the four castle actions
 // (bit a - 4096).  A streaming kernel (HBM-bound): the thread that owns an env stages its piece slots in shared memory,
 // then the warp writes the 32 rows one after the other, lane = from-square, as coalesced 256-byte stores.
-__global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_bits(EnvView v, u64* __restrict__ out, int stride_words) {
+// (The stand-alone mask kernel is a pure stream bound by HBM: here every row word is written exactly ONCE, assembled by the
+// warp -- the thread that owns an env stages its piece slots in shared memory, then the warp writes the 32 rows one after
+// the other, lane = from-square, as coalesced 256-byte stores.  The zero-fill + scatter writer of the step kernels costs
+// ~10x fewer instructions but touches the non-zero sectors twice: 111-124 us against 78 us for this kernel alone.)
+__global__ void __launch_bounds__(GCB_BLOCK) k_env_legal_bits(EnvView v, u64* __restrict__ out, int stride_words, int e_begin, int e_end) {
     __shared__ u64 s_slots[GCB_SLOTS * GCB_BLOCK];
-    const int e = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    const int e = e_begin + blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
     u64 own = 0;
     u32 cword = 0;
-    if (e < v.N) {
+    if (e < e_end) {
         EnvRegs s;
         ulonglong2 a = __ldcs(&v.bb01[e]), c = __ldcs(&v.bb23[e]);
         s.b.t0 = a.x, s.b.t1 = a.y, s.b.t2 = c.x, s.b.w = c.y;
         unpack_meta(__ldcs(&v.meta[e]), s);
-        own = stm_pieces(s);
+        own = stm_pieces(s), cword = castle_word(s);
         const int np = gcb_popc(own);
         for (int r = 0; r < np && r < GCB_SLOTS; r++) s_slots[r * GCB_BLOCK + threadIdx.x] = __ldcs(v.tgt + (size_t)r * v.N + e);
-        // castle bits of meta (bit0 queen side, bit1 king side, of the side to move) -> bit (action - 4096)
-        if (s.castle & 1u) cword |= 1u << (castle_action(!s.stm_black, 0) - 4096);
-        if (s.castle & 2u) cword |= 1u << (castle_action(!s.stm_black, 1) - 4096);
     }
     __syncwarp();
     const int e0 = e - lane;
 #pragma unroll 1
-    for (int p = 0; p < 32 && e0 + p < v.N; p++) {
+    for (int p = 0; p < 32 && e0 + p < e_end; p++) {
         const u64 own_p = __shfl_sync(0xffffffffu, own, p);
         const u32 c_p = __shfl_sync(0xffffffffu, cword, p);
         u64* row = out + (size_t)(e0 + p) * (size_t)stride_words;
@@ -668,6 +752,9 @@ struct gcb_env {
     };
     std::vector<Alloc> allocs;
     size_t guard = 0;
+    // optional learner-facing output of every step call (gcb_env_step_mask_output)
+    u64* bits_out = nullptr;
+    int bits_stride = 0;
 };
 #define GCB_GUARD_BYTE 0xA5
 
@@ -693,18 +780,34 @@ static const int8_t kDefaultBoard[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6,
                                          0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0, 0, 0, 0, 0, 0,
                                          0,  0,  0,  0,  6,  6,  6,  6,  6,  6,  6,  6,  3,  5,  4,  2,  1, 4, 5, 3};
 
+// single-step launches: with the default 16 piece slots the generation runs on the shared-memory tile (TILE 2)
+template <int MODE>
+static int launch_io(gcb_env* env, StepIO& io, cudaStream_t s) {
+    const int grid = grid_for(io.e_end - io.e_begin);
+    // (measured: without the mask output the generic kernel is faster at one step per launch -- 95 vs 105 us per step of 524,288
+    // envs; with it the tile wins, 166 vs 191 us, because the mask is scattered from shared memory)
+    const bool tile = GCB_SINGLE_TILE && env->bits_out != nullptr && env->v.slots == GCB_SLOTS && MODE != MODE_RESET && MODE != MODE_BOTPLY;
+    const bool selfplay = MODE != MODE_RESET && MODE != MODE_BOTPLY && env->v.opponent == 0 && !env->v.agent_black;
+    io.bits_out = (MODE != MODE_RESET) ? env->bits_out : nullptr, io.bits_stride = env->bits_stride;
+    if constexpr (MODE == MODE_RESET || MODE == MODE_BOTPLY) {
+        k_env_step<MODE, 0, false><<<grid, GCB_BLOCK, 0, s>>>(env->v, io);
+    } else {
+        if (tile && selfplay) k_env_step<MODE, 2, true><<<grid, GCB_BLOCK, 0, s>>>(env->v, io);
+        else if (tile) k_env_step<MODE, 2, false><<<grid, GCB_BLOCK, 0, s>>>(env->v, io);
+        else if (selfplay) k_env_step<MODE, 0, true><<<grid, GCB_BLOCK, 0, s>>>(env->v, io);
+        else k_env_step<MODE, 0, false><<<grid, GCB_BLOCK, 0, s>>>(env->v, io);
+    }
+    LAUNCHED();
+    return GCB_OK;
+}
+
 template <int MODE>
 static int launch_range(gcb_env* env, const void* in, int32_t* reward, uint8_t* done, uint8_t* flags, int32_t* act_out,
                         int32_t* bot_out, int ep_inc, int e_begin, int e_end, cudaStream_t s) {
     StepIO io;
     io.in = in, io.reward = reward, io.done = done, io.flags = flags, io.act_out = act_out, io.bot_out = bot_out;
     io.tick = env->tick, io.ep_inc = ep_inc, io.e_begin = e_begin, io.e_end = e_end, io.nsteps = 1;
-    if (MODE != MODE_RESET && env->v.opponent == 0 && !env->v.agent_black)
-        k_env_step<MODE, false, (MODE != MODE_RESET)><<<grid_for(e_end - e_begin), GCB_BLOCK, 0, s>>>(env->v, io);
-    else
-        k_env_step<MODE><<<grid_for(e_end - e_begin), GCB_BLOCK, 0, s>>>(env->v, io);
-    LAUNCHED();
-    return GCB_OK;
+    return launch_io<MODE>(env, io, s);
 }
 
 template <int MODE>
@@ -832,7 +935,7 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
         StepIO io;
         memset(&io, 0, sizeof(io));
         io.tick = env->tick, io.e_begin = 0, io.e_end = N, io.nsteps = 1;
-        k_env_step<MODE_RESET><<<grid_for(N), GCB_BLOCK>>>(v, io);
+        k_env_step<MODE_RESET, 0, false><<<grid_for(N), GCB_BLOCK>>>(v, io);
         env->tick++;
         g_launches.fetch_add(1);
         cudaError_t e2 = cudaDeviceSynchronize();
@@ -893,6 +996,7 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
                                     int32_t* d_actions_out, int32_t* d_bot_out, void* stream) {
     ENV_CHECK(env);
     if (nsteps < 0) return fail(GCB_E_ARG, "gcb_env_step_sampled", "nsteps < 0");
+    if (env->v.opponent == 2) return fail(GCB_E_ARG, "gcb_env_step_sampled", "an env with an external opponent is stepped with gcb_env_step + gcb_env_bot_ply");
     const size_t N = (size_t)env->v.N;
     // A run of several launches is issued as a few env RANGES on their own streams (forked from / joined to the caller's
     // stream): every launch ends with a partly filled last wave of blocks (524,288 envs = 5.5 waves of 740 resident
@@ -912,6 +1016,7 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
         CU(cudaEventRecord(env->events[GCB_HOST_CHUNKS], cs));
         for (int r = 0; r < R; r++) CU(cudaStreamWaitEvent(env->streams[r], env->events[GCB_HOST_CHUNKS], 0));
     }
+    const bool selfplay = env->v.opponent == 0 && !env->v.agent_black, tiled = env->v.slots == GCB_SLOTS;
     int rc = GCB_OK;
     for (int t = 0; t < nsteps && rc == GCB_OK;) {
         const int k = nsteps - t < GCB_MAX_STEPS_PER_LAUNCH ? nsteps - t : GCB_MAX_STEPS_PER_LAUNCH;
@@ -919,16 +1024,19 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
         io.in = nullptr, io.reward = d_reward, io.done = d_done, io.flags = d_flags;
         io.act_out = d_actions_out ? d_actions_out + t * N : nullptr, io.bot_out = d_bot_out ? d_bot_out + t * N : nullptr;
         io.tick = env->tick, io.ep_inc = 1, io.nsteps = k;
+        // the mask output belongs to the state the RUN leaves behind: only the last launch writes it
+        io.bits_out = (t + k == nsteps) ? env->bits_out : nullptr, io.bits_stride = env->bits_stride;
         for (int r = 0; r < R; r++) {
             io.e_begin = r * per, io.e_end = (r + 1) * per < (int)N ? (r + 1) * per : (int)N;
             if (io.e_begin >= io.e_end) break;
             cudaStream_t ls = R > 1 ? env->streams[r] : cs;
-            if (k >= 4 && env->v.slots == GCB_SLOTS && env->v.opponent == 0 && !env->v.agent_black)
-                k_env_step<MODE_SAMPLED, true, true><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
-            else if (k >= 4 && env->v.slots == GCB_SLOTS)
-                k_env_step<MODE_SAMPLED, true><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
-            else
-                k_env_step<MODE_SAMPLED, false><<<grid_for(io.e_end - io.e_begin), GCB_BLOCK, 0, ls>>>(env->v, io);
+            const int grid = grid_for(io.e_end - io.e_begin);
+            // several steps: the slots are staged into the tile once (TILE 1); a few: nothing is staged in (TILE 2)
+            if (tiled && k >= 4 && selfplay) k_env_step<MODE_SAMPLED, 1, true><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
+            else if (tiled && k >= 4) k_env_step<MODE_SAMPLED, 1, false><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
+            else if (tiled && selfplay) k_env_step<MODE_SAMPLED, 2, true><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
+            else if (tiled) k_env_step<MODE_SAMPLED, 2, false><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
+            else k_env_step<MODE_SAMPLED, 0, false><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             const cudaError_t le = cudaGetLastError();
             if (le != cudaSuccess) {
@@ -1086,13 +1194,9 @@ static int step_packed(gcb_env* env, const uint16_t* in16, uint16_t* result16, v
     io.in = d_in, io.in16 = 1, io.packed = (uint16_t*)d_out;
     io.reward = nullptr, io.done = nullptr, io.flags = nullptr, io.act_out = nullptr, io.bot_out = nullptr;
     io.tick = env->tick, io.ep_inc = 1, io.e_begin = 0, io.e_end = env->v.N, io.nsteps = 1;
-    if (env->v.opponent == 0 && !env->v.agent_black)
-        k_env_step<MODE, false, true><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
-    else
-        k_env_step<MODE><<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, io);
-    LAUNCHED();
+    const int rc = launch_io<MODE>(env, io, (cudaStream_t)stream);
     env->tick++;
-    return GCB_OK;
+    return rc;
 }
 extern "C" int gcb_env_step_packed(gcb_env* env, const uint16_t* actions16, uint16_t* result16, void* stream) {
     ENV_CHECK(env);
@@ -1192,8 +1296,15 @@ extern "C" int gcb_env_legal_mask(gcb_env* env, uint8_t* d_mask, void* stream) {
 extern "C" int gcb_env_legal_bitmask(gcb_env* env, uint64_t* d_bits, int stride_words, void* stream) {
     ENV_CHECK(env);
     if (!d_bits || stride_words < 65) return fail(GCB_E_ARG, "gcb_env_legal_bitmask", "null pointer or stride_words < 65");
-    k_env_legal_bits<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, reinterpret_cast<u64*>(d_bits), stride_words);
+    k_env_legal_bits<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, reinterpret_cast<u64*>(d_bits), stride_words, 0, env->v.N);
     LAUNCHED();
+    return GCB_OK;
+}
+
+extern "C" int gcb_env_step_mask_output(gcb_env* env, uint64_t* d_bits, int stride_words) {
+    if (!env) return fail(GCB_E_ARG, "gcb_env_step_mask_output", "null env");
+    if (d_bits && stride_words < 65) return fail(GCB_E_ARG, "gcb_env_step_mask_output", "stride_words < 65");
+    env->bits_out = reinterpret_cast<u64*>(d_bits), env->bits_stride = d_bits ? stride_words : 0;
     return GCB_OK;
 }
 

@@ -22,7 +22,12 @@ from .batched_env import BatchedChessEnv
 
 
 class PipelinedChessEnv:
-    def __init__(self, num_envs, shards=2, device=0, env_id_offset=0, **env_kwargs):
+    def __init__(self, num_envs, shards=2, device=0, env_id_offset=0, observe=False, mask=False, **env_kwargs):
+        """observe=True: every step also brings the observation back -- the four 64-bit bit-planes of the board (32 B per env,
+        the resident form of `state["board"]`; piece code = reference id in planes t0..t2, colour plane `white`) are copied to
+        page-locked host memory behind the step, on the shard's stream: `observations[k]` = (int64 [H, 2] t0|t1, int64 [H, 2]
+        t2|white).  mask=True: likewise the bit mask of possible_actions (int64 [H, 66], written by the step kernel itself,
+        gcb_env_step_mask_output): `masks[k]`.  Both are valid after recv(k), like the result records."""
         if shards < 1 or num_envs % shards:
             raise ValueError("num_envs must be a multiple of shards")
         self.num_envs, self.shards, self.shard_envs = int(num_envs), int(shards), int(num_envs) // int(shards)
@@ -38,19 +43,42 @@ class PipelinedChessEnv:
         # ... and reads the result records here after recv()
         self.results = [t.numpy().view(np.uint16) for t in self._out]
         self._in_flight = [False] * shards
+        self.observe, self.mask = bool(observe), bool(mask)
+        self.observations, self.masks, self._planes, self._dmask = [], [], [], []
+        for e in self.envs:
+            if self.observe:
+                self._planes.append(e.planes())
+                self.observations.append(tuple(torch.zeros((H, 2), dtype=torch.int64).pin_memory() for _ in range(2)))
+            if self.mask:
+                with torch.cuda.device(self.device):
+                    m = torch.zeros((H, 66), dtype=torch.int64, device=self.device)
+                e.set_mask_output(m)
+                self._dmask.append(m)
+                self.masks.append(torch.zeros((H, 66), dtype=torch.int64).pin_memory())
+
+    def _after_step(self, k):
+        # device -> host copies of the step's other outputs, enqueued behind the step kernel on the shard's stream
+        if self.observe or self.mask:
+            with torch.cuda.stream(self.streams[k]):
+                if self.observe:
+                    for dst, src in zip(self.observations[k], self._planes[k]):
+                        dst.copy_(src, non_blocking=True)
+                if self.mask:
+                    self.masks[k].copy_(self._dmask[k], non_blocking=True)
+        self._in_flight[k] = True
 
     def send_actions(self, k, src=None):
         """enqueue ChessEnvV2.step(action) of every env of shard k with the actions in inputs[k] (action codes < 4101), or in
         `src`: any other page-locked int16/uint16 buffer of shard_envs entries (e.g. where a policy's output already lies),
         read in place -- it must stay untouched until recv(k)"""
         self.envs[k].step_packed(self._in[k] if src is None else src, self._out[k], stream=self.streams[k])
-        self._in_flight[k] = True
+        self._after_step(k)
 
     def send_words(self, k, src=None):
         """enqueue a step in which env i plays possible_actions[(word[i] * n_legal) >> 16] (a uniform random legal action for
         uniform 16-bit words; RESIGN when it has no legal move); words from inputs[k] or from a page-locked `src`"""
         self.envs[k].step_index_packed(self._in[k] if src is None else src, self._out[k], stream=self.streams[k])
-        self._in_flight[k] = True
+        self._after_step(k)
 
     def recv(self, k):
         """block until shard k's step has finished; returns results[k] (uint16 records, see unpack)"""
@@ -61,10 +89,13 @@ class PipelinedChessEnv:
 
     unpack = staticmethod(BatchedChessEnv.unpack_result)
 
-    def burn_in(self, steps):
-        """`steps` sampled self-play steps of every shard (on-device draws), e.g. to mix game phases before measuring"""
+    def burn_in(self, steps, dephase=False):
+        """`steps` sampled self-play steps of every shard (on-device draws), e.g. to mix game phases before measuring;
+        dephase=True first spreads the episode phases (BatchedChessEnv.dephase)"""
         for k, e in enumerate(self.envs):
             with torch.cuda.stream(self.streams[k]):
+                if dephase:
+                    e.dephase()
                 e.step_sampled(steps)
         for k in range(self.shards):
             self.streams[k].synchronize()

@@ -217,6 +217,14 @@ int gcb_env_legal_mask(gcb_env *env, uint8_t *d_mask, void *stream);
  * word 64 holds the castle actions 4096..4099 in bits 0..3.  520 B per env instead of 4101: the form a learner should
  * read every step (one streaming kernel, HBM-bound). */
 int gcb_env_legal_bitmask(gcb_env *env, uint64_t *d_bits, int stride_words, void *stream);
+/* The bit mask as an OUTPUT OF EVERY STEP CALL (what a learner reads next to the reward: possible_actions of the state the
+ * step leaves behind, chess_v2.py:333-335): once a buffer is registered here, gcb_env_step / _step_index / _step_sampled /
+ * the host-buffer and packed forms fill d_bits (uint64[N][stride_words], device memory, layout of gcb_env_legal_bitmask)
+ * on the stream of the step: the step kernel writes the mask itself, right where it leaves the env's legal set (no second
+ * kernel, no second pass over the state) -- the rows of a warp's envs are zero-filled with coalesced stores and each
+ * thread scatters the at most 17 non-zero words of its env.
+ * d_bits = NULL switches the output off.  An even stride_words (e.g. 66) lets the rows be written as 16-byte stores. */
+int gcb_env_step_mask_output(gcb_env *env, uint64_t *d_bits, int stride_words);
 /* ChessEnvV2.possible_actions (chess_v2.py:333-335) of every env: d_actions uint16[N][stride] receives the list in
  * the reference's order (normal moves in generation order, then castles), d_counts int32[N] (may be NULL) the true
  * count.  Like the reference's property, the list is DERIVED on access: the resident form of possible_moves is one

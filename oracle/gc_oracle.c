@@ -664,13 +664,15 @@ typedef struct {
     gco_pool *pool;
     uint32_t lo, hi;
     uint64_t nsteps;
+    uint32_t stagger; /* > 0: env i runs (i % stagger) steps more (spreads the episode phases of a pool) */
     gco_stats st;
 } pool_arg;
 
 static void *pool_worker(void *p) {
     pool_arg *a = (pool_arg *)p;
     memset(&a->st, 0, sizeof(a->st));
-    for (uint32_t i = a->lo; i < a->hi; i++) gco_selfplay(&a->pool->envs[i], a->nsteps, &a->st);
+    for (uint32_t i = a->lo; i < a->hi; i++)
+        gco_selfplay(&a->pool->envs[i], a->nsteps + (a->stagger ? (uint64_t)(i % a->stagger) : 0), &a->st);
     return NULL;
 }
 
@@ -682,13 +684,22 @@ gco_pool *gco_pool_new(uint64_t seed, uint32_t env_lo, uint32_t env_hi) {
     return p;
 }
 
+static void pool_run(gco_pool *p, uint64_t nsteps_per_env, uint32_t stagger, int threads, gco_stats *st);
 void gco_pool_run(gco_pool *p, uint64_t nsteps_per_env, int threads, gco_stats *st) {
+    pool_run(p, nsteps_per_env, 0, threads, st);
+}
+/* env i runs nsteps_per_env + (i % stagger) steps: 3 random self-play episodes in 4 end at the 150-move cap after exactly 301
+ * steps, so a pool started together stays in lockstep unless its phases are spread once */
+void gco_pool_run_staggered(gco_pool *p, uint64_t nsteps_per_env, uint32_t stagger, int threads, gco_stats *st) {
+    pool_run(p, nsteps_per_env, stagger, threads, st);
+}
+static void pool_run(gco_pool *p, uint64_t nsteps_per_env, uint32_t stagger, int threads, gco_stats *st) {
     if (threads < 1) threads = 1;
     if ((uint32_t)threads > p->n) threads = (int)(p->n ? p->n : 1);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
     pool_arg *args = (pool_arg *)malloc(sizeof(pool_arg) * (size_t)threads);
     for (int t = 0; t < threads; t++) {
-        args[t].pool = p, args[t].nsteps = nsteps_per_env;
+        args[t].pool = p, args[t].nsteps = nsteps_per_env, args[t].stagger = stagger;
         args[t].lo = (uint32_t)((uint64_t)p->n * (uint64_t)t / (uint64_t)threads);
         args[t].hi = (uint32_t)((uint64_t)p->n * (uint64_t)(t + 1) / (uint64_t)threads);
         pthread_create(&th[t], NULL, pool_worker, &args[t]);

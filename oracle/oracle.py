@@ -272,11 +272,13 @@ class SelfplayPool:
         L.gco_pool_new.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
         L.gco_pool_run.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Stats)]
         L.gco_pool_free.argtypes = [C.c_void_p]
+        L.gco_pool_run_staggered.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(Stats)]
         self._h = L.gco_pool_new(seed, env_lo, env_hi)
 
-    def run(self, nsteps_per_env, threads):
+    def run(self, nsteps_per_env, threads, stagger=0):
+        """every env plays nsteps_per_env more steps (+ env index % stagger with stagger > 0: spreads the episode phases)"""
         st = Stats()
-        lib().gco_pool_run(self._h, nsteps_per_env, threads, C.byref(st))
+        lib().gco_pool_run_staggered(self._h, nsteps_per_env, stagger, threads, C.byref(st))
         return st.as_dict()
 
     def __del__(self):

@@ -738,3 +738,69 @@ def test_config2_fixed_positions_full_byte_compare():
         if not attack:
             assert (chk.cpu().numpy() == exp_chk).all()
             assert int(ecnt.sum()) > 24_000_000 and (ecnt == 0).sum() > 1000 and exp_chk.mean() > 0.05
+
+
+@pytest.mark.parametrize("opponent,color,auto_reset", [("none", "WHITE", True), ("random", "WHITE", True), ("random", "BLACK", True),
+                                                         ("none", "WHITE", False)])
+def test_step_writes_the_legal_bit_mask_itself(opponent, color, auto_reset):
+    """gcb_env_step_mask_output: the bit mask of possible_actions as an output of every step call (written by the step kernel
+    while the legal set sits in shared memory) == gcb_env_legal_bitmask of the state the step left behind; every step
+    entry point, valid and invalid actions (envs whose legal set the step does not touch), ragged env count"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv
+
+    N = 20011
+    env = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=19, auto_reset=auto_reset)
+    ref = BatchedChessEnv(N, opponent=opponent, player_color=color, seed=19, auto_reset=auto_reset)
+    rng = np.random.RandomState(2)
+    for width in (66, 65):
+        bits = torch.full((N, width), -1, dtype=torch.int64, device="cuda")
+        env.set_mask_output(bits)
+        h_in, h_out = torch.empty(N, dtype=torch.int16).pin_memory(), torch.empty(N, dtype=torch.int16).pin_memory()
+        for t in range(24):
+            kind = t % 6
+            if kind == 0:
+                env.step_sampled(1), ref.step_sampled(1)
+            elif kind == 1:
+                env.step_sampled(21), ref.step_sampled(21)       # the persistent run kernel: mask of the LAST step
+            elif kind == 2:
+                env.step_sampled(3), ref.step_sampled(3)
+            elif kind == 3:
+                w = torch.from_numpy(rng.randint(0, 2 ** 31, size=N).astype(np.int32)).cuda()
+                env.step_index(w), ref.step_index(w)
+            elif kind == 4:
+                legal, cnt = ref.legal_actions()
+                legal, cnt = legal.cpu().numpy().view(np.uint16), cnt.cpu().numpy()
+                acts = legal[np.arange(N), rng.randint(0, 1 << 30, size=N) % np.maximum(cnt, 1)].astype(np.int32)
+                acts[rng.rand(N) < 0.3] = rng.randint(0, 4101)   # invalid ones: the legal set stays as it is
+                a = torch.from_numpy(acts).cuda()
+                env.step(a), ref.step(a)
+            else:
+                w = rng.randint(0, 1 << 16, size=N).astype(np.uint16)
+                h_in.numpy().view(np.uint16)[:] = w
+                env.step_index_packed(h_in, h_out)
+                env.wait()
+                ref.step_index(torch.from_numpy((w.astype(np.uint32) << 16).view(np.int32)).cuda())
+            assert torch.equal(bits[:, :65], ref.legal_bitmask()), (width, t, kind)
+        env.set_mask_output(None)
+    assert env.stats() == ref.stats()
+    # more piece slots than the tile holds: the mask kernel runs behind the generic step kernel
+    boards = np.zeros((2, 64), np.int8)
+    boards[0, :20], boards[0, 40], boards[0, 63] = 2, 1, -1
+    boards[1, 8:30], boards[1, 50], boards[1, 0] = 3, 1, -1
+    a, b = (BatchedChessEnv(300, opponent="none", seed=4, initial_boards=boards) for _ in range(2))
+    bits = torch.zeros((300, 66), dtype=torch.int64, device="cuda")
+    a.set_mask_output(bits)
+    for n in (1, 5, 2):
+        a.step_sampled(n), b.step_sampled(n)
+        assert torch.equal(bits[:, :65], b.legal_bitmask())
+
+
+def test_no_index_violation_flag_in_this_process():
+    """runs last in this file: the violation word of the library stayed clear through every test above"""
+    import ctypes as C
+    from gym_chess_b200 import _lib
+
+    v = C.c_uint64()
+    _lib.check(_lib.lib().gcb_debug_violations(C.byref(v), 0))
+    assert v.value == 0

@@ -29,8 +29,9 @@ def mangled(pat):
     if not m:
         return pat
     name, args = m.group(1), m.group(2).split(",")
-    if name == "k_env_step":
-        return name + "ILi%sE" % args[0] + "".join("Lb%dE" % int(a not in ("0", "false")) for a in (args[1:] + ["0", "0"])[:2])
+    if name == "k_env_step":  # <int MODE, int TILE, bool SELFPLAY>
+        args = (args + ["0", "0"])[:3]
+        return name + "ILi%sELi%sELb%dE" % (args[0], args[1], int(args[2] not in ("0", "false")))
     return name + "I" + "".join("Lb%dE" % int(a not in ("0", "false")) for a in args)
 mang = mangled(pat)
 locs = []
