@@ -773,6 +773,60 @@ GCB_HD int gen_legal_list(const Board& b, int white_to_move, u32 rights, Slots& 
     return n;
 }
 
+// ---- attack=True lists through the same two stages as the legal lists: per own piece its attack / defence set (rays up
+// to and including the first piece of either colour, lib.rs:1089-1104; knight / king neighbourhoods, lib.rs:1147-1174;
+// pawn diagonals minus squares holding the mover's own king, lib.rs:928-933, Q14), type-major, then the ordered decode.
+// No legality filter, no castles.  (gen_attack_moves above is the direct square-major form; the host-compiled tests use both.)
+template <class Sink, class G>
+GCB_HD void gen_attack_targets(const Board& b, int white, u64 subset, Sink& sink, const G& geo) {
+    const u64 occ = bb_occ(b), own = white ? b.w : (occ & ~b.w), mine = own & subset, ownk = bb_kings(b) & own;
+#define GCB_APUT(bit_, T_) sink.put(gcb_popc(mine & ((bit_) - 1)), (T_))
+    for (u64 s = bb_rooks(b) & mine; s;) {
+        const int sq = gcb_take(s);
+        GCB_APUT(1ULL << sq, rook_att(geo, sq, occ));
+    }
+    for (u64 s = bb_bishops(b) & mine; s;) {
+        const int sq = gcb_take(s);
+        GCB_APUT(1ULL << sq, bishop_att(geo, sq, occ));
+    }
+    for (u64 s = bb_queens(b) & mine; s;) {
+        const int sq = gcb_take(s);
+        GCB_APUT(1ULL << sq, rook_att(geo, sq, occ) | bishop_att(geo, sq, occ));
+    }
+    for (u64 s = bb_knights(b) & mine; s;) {
+        const int sq = gcb_take(s);
+        GCB_APUT(1ULL << sq, geo.knight(sq));
+    }
+    for (u64 s = bb_kings(b) & mine; s;) {
+        const int sq = gcb_take(s);
+        GCB_APUT(1ULL << sq, geo.king(sq));
+    }
+    for (u64 s = bb_pawns(b) & mine; s;) {
+        const int sq = gcb_take(s);
+        GCB_APUT(1ULL << sq, geo.pawn(!white, sq, 1) & ~ownk);
+    }
+#undef GCB_APUT
+}
+
+template <class Slots, class Offs, class Out>
+GCB_HD int gen_attack_list(const Board& b, int white_to_move, Slots& slots, Offs& offs, Out& out) {
+    const u64 occ = bb_occ(b);
+    int n = 0;
+    u64 rem = white_to_move ? b.w : (occ & ~b.w);
+    while (rem) {
+        u64 chunk = rem;
+        if (gcb_popc(rem) > GCB_SLOTS) {
+            u64 t = rem;
+            for (int i = 0; i < GCB_SLOTS; i++) t &= t - 1;
+            chunk = rem ^ t;
+        }
+        rem ^= chunk;
+        gen_attack_targets(b, white_to_move, chunk, slots, GeomGlobal());
+        n = emit_chunk_typemajor(b, white_to_move, chunk, slots, offs, out, n);
+    }
+    return n;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Zobrist key of the board only (the reference's repetition key is the 64-char board string,
 // chess_v2.py:404-407, 599-602: no side to move, no rights).  Keys are splitmix64 of

@@ -152,12 +152,18 @@ struct SmemOffs {
     __device__ __forceinline__ int get(int r) const { return base[r * GCB_BLOCK]; }
 };
 
+// ATTACK: get_possible_moves(attack=True) -- the attack / defence pseudo-move list (lib.rs:928-933, 1089-1104, 1147-1174).
+// Both kinds go through the same two stages: one 64-bit target set per own piece into the thread's shared-memory slots
+// (type-major loops), then the type-major ordered decode.
+#ifndef GCB_MOVEGEN_MIN_BLOCKS
+#define GCB_MOVEGEN_MIN_BLOCKS 6  // measured: 6 resident blocks per SM (80 registers) beat 7-8 (spills) and the compiler default
+#endif
 template <bool ATTACK>
-__global__ void __launch_bounds__(GCB_BLOCK) k_movegen(int n, gcb_positions pos, int castles_only,
+__global__ void __launch_bounds__(GCB_BLOCK, GCB_MOVEGEN_MIN_BLOCKS) k_movegen(int n, gcb_positions pos, int castles_only,
                                                        uint16_t* __restrict__ actions, int stride,
                                                        int32_t* __restrict__ counts, uint8_t* __restrict__ incheck) {
-    __shared__ u64 s_slots[ATTACK ? 1 : GCB_SLOTS * GCB_BLOCK];
-    __shared__ uint16_t s_offs[ATTACK ? 1 : GCB_SLOTS * GCB_BLOCK];
+    __shared__ u64 s_slots[GCB_SLOTS * GCB_BLOCK];
+    __shared__ uint16_t s_offs[GCB_SLOTS * GCB_BLOCK];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     ulonglong2 a = reinterpret_cast<const ulonglong2*>(pos.bb01)[i], c = reinterpret_cast<const ulonglong2*>(pos.bb23)[i];
@@ -166,17 +172,11 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_movegen(int n, gcb_positions pos,
     const u32 rights = mask_rights(b, pos.rights[i]);  // convert_py_state -> State::new, lib.rs:1267-1274
     bool chk = false;
     int cnt;
-    if (ATTACK) {
-        ListWriter lw(actions + (size_t)i * stride, stride);
-        gen_attack_moves(b, white, lw);
-        lw.flush();
-        cnt = lw.n;
-    } else {
-        SmemSlots slots = {s_slots + threadIdx.x};
-        SmemOffs offs = {s_offs + threadIdx.x};
-        ListOut out = {actions + (size_t)i * stride, stride};
-        cnt = gen_legal_list(b, white, rights, slots, offs, out, &chk);
-    }
+    SmemSlots slots = {s_slots + threadIdx.x};
+    SmemOffs offs = {s_offs + threadIdx.x};
+    ListOut out = {actions + (size_t)i * stride, stride};
+    if (ATTACK) cnt = gen_attack_list(b, white, slots, offs, out);
+    else cnt = gen_legal_list(b, white, rights, slots, offs, out, &chk);
     if (castles_only) {  // get_castle_moves, lib.rs:1482-1500: the castle tail of the same list
         uint16_t* l = actions + (size_t)i * stride;
         int m = 0, lim = cnt < stride ? cnt : stride;

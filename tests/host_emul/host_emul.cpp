@@ -30,11 +30,19 @@ void emul_movegen(int n, const int8_t* boards, const int8_t* players, const uint
         rights = mask_rights(b, rights);
         bool chk = false;
         int cnt;
-        if (attack) {
-            ListWriter lw(out + (size_t)i * stride, stride);
+        if (attack) {  // the kernel's form (slots + type-major decode) ...
+            LocalSlots slots;
+            LocalOffs offs;
+            ListOut lo = {out + (size_t)i * stride, stride};
+            cnt = gen_attack_list(b, players[i] > 0, slots, offs, lo);
+            // ... which must equal the direct square-major generator
+            uint16_t tmp[512];
+            ListWriter lw(tmp, 512);
             gen_attack_moves(b, players[i] > 0, lw);
             lw.flush();
-            cnt = lw.n;
+            bool same = lw.n == cnt;
+            for (int k = 0; same && k < cnt && k < stride && k < 512; k++) same = tmp[k] == out[(size_t)i * stride + k];
+            if (!same) cnt = -1;
         } else {
             LocalSlots slots;
             LocalOffs offs;
