@@ -208,9 +208,12 @@ __global__ void __launch_bounds__(GCB_BLOCK) k_next_state(int n, gcb_positions p
     reinterpret_cast<ulonglong2*>(out.bb23)[i] = make_ulonglong2(nb.t2, nb.w);
     if (out.player) out.player[i] = st ? black : !black;  // lib.rs:779-780
     if (out.rights) out.rights[i] = (uint8_t)rights;
-    if (checks) checks[i] = (uint8_t)check_flags(nb);  // update_state, lib.rs:1440
+    const u32 chk = check_flags(nb);  // update_state, lib.rs:1440
+    if (checks) checks[i] = (uint8_t)chk;
     if (reward) reward[i] = r;
-    if (status) status[i] = (int8_t)st;
+    // status 1: the move was applied and BOTH kings are in check afterwards -- the reference prints, sets a Python exception
+    // and still returns the state (lib.rs:1442-1446, Q19); reported so that a binding can raise like CPython does
+    if (status) status[i] = (int8_t)(st ? st : (chk == 3u ? 1 : 0));
 }
 
 __global__ void __launch_bounds__(GCB_BLOCK) k_update_state(int n, gcb_positions pos, uint8_t* __restrict__ rights_out,

@@ -41,7 +41,8 @@ class BatchedChessEngine:
         return out, cnt, chk
 
     def next_state(self, boards, players, rights, actions):
-        """-> (boards int8[n,64], rights uint8[n,4], checks uint8[n,2], reward int32[n], status int8[n])"""
+        """-> (boards int8[n,64], rights uint8[n,4], checks uint8[n,2], reward int32[n], status int8[n]: 0 ok, 1 ok with both
+        kings in check afterwards (Q19), -1 empty from-square, -2 bad action code)"""
         n, boards, players, rights = self._prep(boards, players, rights)
         actions = np.ascontiguousarray(np.asarray(actions, np.int32).reshape(n))
         ob, orr, oc = np.zeros((n, 64), np.int8), np.zeros((n, 4), np.uint8), np.zeros((n, 2), np.uint8)
@@ -84,8 +85,13 @@ class ChessEngine:
         ob, orr, oc, rew, st = self._b.next_state(board, p, rights, [STR_TO_ACTION[move]])
         if st[0] == -1:
             raise RuntimeError("Bad move - piece is empty !")  # the reference panics (lib.rs:693-695)
-        if st[0]:
+        if st[0] < 0:
             raise ValueError("bad move %r" % (move,))
+        if st[0] == 1:
+            # both kings in check after the move: the reference prints, sets an exception with PyErr::restore and still
+            # returns Ok(...) (lib.rs:1442-1446, Q19) -- which CPython turns into this SystemError at the call site
+            raise SystemError("<method 'next_state' of 'ChessEngine' objects> returned a result with an exception set "
+                              "(Both Kings are in check: this position is impossible)")
         return self._dict(ob[0], orr[0], oc[0], BLACK if p > 0 else WHITE), int(rew[0])
 
     def get_possible_moves(self, state, player, attack=False):

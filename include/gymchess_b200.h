@@ -90,8 +90,9 @@ int gcb_get_possible_moves(int n, gcb_positions pos, int attack, int castles_onl
                            int32_t *d_counts, uint8_t *d_incheck, void *stream);
 
 /* ChessEngine.next_state(state, player, move), lib.rs:1422-1452: mask rights by king presence on the input
- * board, apply, recompute both check flags.  `pos.player` is the mover.  d_status int8[n]: 0 ok, -1 the from
- * square is empty (the reference panics, lib.rs:693-695), -2 bad action code; on error the position is copied. */
+ * board, apply, recompute both check flags.  `pos.player` is the mover.  d_status int8[n]: 0 ok, 1 ok but BOTH kings
+ * are in check afterwards (the reference sets a Python exception and still returns the state, lib.rs:1442-1446), -1 the from
+ * square is empty (the reference panics, lib.rs:693-695), -2 bad action code; on an error (< 0) the position is copied. */
 int gcb_next_state(int n, gcb_positions pos, const int32_t *d_actions, gcb_positions out, uint8_t *d_checks,
                    int32_t *d_reward, int8_t *d_status, void *stream);
 

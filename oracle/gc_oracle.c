@@ -748,7 +748,7 @@ void gco_next_state_batch(int n, const int8_t *boards, const int8_t *players, co
         int rew = 0, both = 0;
         gco_state_new(&s, boards + (size_t)i * 64, players[i], r[0], r[1], r[2], r[3]);
         int rc = gco_next_state(&s, players[i], actions[i], &o, &rew, &both);
-        out_status[i] = (int8_t)rc;
+        out_status[i] = (int8_t)(rc ? rc : (both ? 1 : 0)); /* 1: both kings in check afterwards (lib.rs:1442-1446) */
         if (rc) { o = s; gco_update_state(&o); rew = 0; } /* reference panics; defined here as: position unchanged */
         memcpy(out_boards + (size_t)i * 64, o.board, 64);
         out_rights[(size_t)i * 4 + 0] = o.wk, out_rights[(size_t)i * 4 + 1] = o.wq;

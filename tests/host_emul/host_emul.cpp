@@ -78,7 +78,7 @@ void emul_next_state(int n, const int8_t* boards, const int8_t* players, const u
         out_rights4[4 * i + 2] = rights & RT_BK ? 1 : 0, out_rights4[4 * i + 3] = rights & RT_BQ ? 1 : 0;
         u32 c = check_flags(nb);
         out_checks[2 * i] = c & 1, out_checks[2 * i + 1] = (c >> 1) & 1;
-        out_reward[i] = r, out_status[i] = (int8_t)st;
+        out_reward[i] = r, out_status[i] = (int8_t)(st ? st : (c == 3u ? 1 : 0));
     }
 }
 

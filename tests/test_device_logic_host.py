@@ -200,3 +200,15 @@ def test_external_actions_incl_invalid_vs_oracle(opponent, color, auto_reset):
     env = EmulAdapter(10, opponent=opponent, player_color=color, seed=77, auto_reset=auto_reset)
     st = ph.check_external_actions_vs_oracle(env, opponent, color, 77, 420, np.random.RandomState(8), auto_reset)
     assert st[7] > 0  # invalid actions occurred
+
+
+def test_next_state_reports_both_kings_in_check():
+    """Q19 (lib.rs:1442-1446): a move after which BOTH kings are in check is applied, and flagged with status 1"""
+    b = np.zeros(64, np.int8)
+    b[60], b[56], b[28], b[7] = 1, 3, -3, -1          # Ke1, Ra1; black Re5 (checks e1), Kh8
+    a = 56 * 64 + 0                                    # Ra1-a8+: the white king stays in check, the black king is checked
+    for fn in (orc.next_state_batch, emul.next_state):
+        ob, orr, oc, rew, st = fn(b[None], 1, np.ones((1, 4), np.uint8), [a])
+        assert st[0] == 1 and list(oc[0]) == [1, 1] and ob[0, 0] == 3 and ob[0, 56] == 0
+    ob, orr, oc, rew, st = emul.next_state(b[None], 1, np.ones((1, 4), np.uint8), [56 * 64 + 57])   # Ra1-b1: only White in check
+    assert st[0] == 0 and list(oc[0]) == [1, 0]

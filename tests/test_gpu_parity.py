@@ -796,6 +796,24 @@ def test_step_writes_the_legal_bit_mask_itself(opponent, color, auto_reset):
         assert torch.equal(bits[:, :65], b.legal_bitmask())
 
 
+def test_engine_shim_raises_like_cpython_when_both_kings_are_in_check(eng):
+    """Q19: the reference sets an exception and still returns the state (lib.rs:1442-1446) -> SystemError at the call site;
+    the batched call reports status 1 and the position"""
+    from gym_chess_b200 import ChessEngine
+
+    b = np.zeros(64, np.int8)
+    b[60], b[56], b[28], b[7] = 1, 3, -3, -1
+    ob, orr, oc, rew, st = eng.next_state(b[None], 1, np.ones((1, 4), np.uint8), [56 * 64 + 0])
+    exp = orc.next_state_batch(b[None], 1, np.ones((1, 4), np.uint8), [56 * 64 + 0])
+    assert st[0] == 1 == exp[4][0] and (ob == exp[0]).all() and list(oc[0]) == [1, 1]
+    state = dict(board=b.reshape(8, 8).tolist(), current_player="WHITE", white_king_castle_is_possible=False,
+                 white_queen_castle_is_possible=False, black_king_castle_is_possible=False, black_queen_castle_is_possible=False)
+    with pytest.raises(SystemError):
+        ChessEngine().next_state(state, "WHITE", "a1a8")
+    ns, r = ChessEngine().next_state(state, "WHITE", "a1b1")
+    assert ns["white_king_is_checked"] and not ns["black_king_is_checked"] and r == 0
+
+
 def test_no_index_violation_flag_in_this_process():
     """runs last in this file: the violation word of the library stayed clear through every test above"""
     import ctypes as C

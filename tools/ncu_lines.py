@@ -71,6 +71,21 @@ for title, dct in (("by innermost line", by_line), ("by env_core-level frame", b
     print("==", title)
     for k, (s, wi, ti) in sorted(dct.items(), key=lambda x: -x[1][0])[:top]:
         print("  %-24s %5d  samples %6d (%4.1f%%)  warp-inst %9d (%4.1f%%)  lanes %.1f" % (k[0], k[1], s, 100.0 * s / tot[0], wi, 100.0 * wi / tot[1], ti / max(1, wi)))
+csv_out = os.environ.get("NCU_LINES_CSV")  # NCU_LINES_CSV=<path>: the per-line table (top `top` lines by warp instructions) as CSV
+if csv_out:
+    src_cache = {}
+    def src_line(f, ln):
+        for cand in ("gym_chess_b200/csrc/" + f, f):
+            if os.path.exists(cand):
+                if cand not in src_cache:
+                    src_cache[cand] = open(cand).read().split("\n")
+                return src_cache[cand][ln - 1].strip()[:100] if 0 < ln <= len(src_cache[cand]) else ""
+        return ""
+    with open(csv_out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["file", "line", "stall_samples", "samples_pct", "warp_instructions", "warp_instructions_pct", "active_lanes", "source"])
+        for k, (sm, wi, ti) in sorted(by_line.items(), key=lambda x: -x[1][1])[:top]:
+            w.writerow([k[0], k[1], sm, "%.2f" % (100.0 * sm / tot[0]), wi, "%.2f" % (100.0 * wi / tot[1]), "%.1f" % (ti / max(1, wi)), src_line(k[0], k[1])])
 if len(sys.argv) > 5:  # annotated listing: file:lo-hi
     f, rng = sys.argv[5].split(":")
     lo, hi = map(int, rng.split("-"))
