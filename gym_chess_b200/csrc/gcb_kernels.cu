@@ -65,14 +65,17 @@ struct DeviceScope {
 #ifndef GCB_BLOCK
 #define GCB_BLOCK 128
 #endif
-#ifndef GCB_STEP_MIN_BLOCKS
-#define GCB_STEP_MIN_BLOCKS 5
+#ifndef GCB_STEP_MIN_BLOCKS  // single-step kernels: 6 resident blocks per SM (80 registers, no spills) measure 3 % faster than 5
+#define GCB_STEP_MIN_BLOCKS 6
 #endif
 #ifndef GCB_FAST_SINK
 #define GCB_FAST_SINK 1
 #endif
 #ifndef GCB_SAMPLED_MIN_BLOCKS
 #define GCB_SAMPLED_MIN_BLOCKS 5
+#endif
+#ifndef GCB_FAST_GENERIC  // unchecked slot stores also in the generic (resident-slot) kernels when the env has 16 slots
+#define GCB_FAST_GENERIC 1
 #endif
 #ifndef GCB_SINGLE_TILE  // single-step launches generate on the shared-memory tile (TILE 2) when the env has 16 piece slots
 #define GCB_SINGLE_TILE 1
@@ -316,7 +319,7 @@ __device__ __forceinline__ void run_unit(const EnvView& v, StepIO io, const int 
     const GeomShared sgeo = {s_geom};
     // at most 16 pieces of either colour (always, from the standard start position: pieces only leave the board): the
     // generation then stores its slots without bounds tests for the whole unit
-    const bool small = TILE && active && gcb_popc(s.b.w) <= GCB_SLOTS && gcb_popc(bb_occ(s.b) & ~s.b.w) <= GCB_SLOTS;
+    const bool small = (TILE || v.slots == GCB_SLOTS) && active && gcb_popc(s.b.w) <= GCB_SLOTS && gcb_popc(bb_occ(s.b) & ~s.b.w) <= GCB_SLOTS;
     (void)small;
     bool wrote = TILE == 1;  // TILE 2: does the tile hold this env's legal set (was it rewritten by this unit)?
 #pragma unroll 1
@@ -332,8 +335,13 @@ __device__ __forceinline__ void run_unit(const EnvView& v, StepIO io, const int 
                 else
 #endif
                     env_step_regs<MODE, SELFPLAY, false, TILE == 1>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, pick, sgeo, input);
-            } else
-                env_step_regs<MODE, SELFPLAY, false, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, pick, GeomGlobal(), input);
+            } else {
+#if GCB_FAST_SINK && GCB_FAST_GENERIC
+                if (small) env_step_regs<MODE, SELFPLAY, true, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, pick, GeomGlobal(), input);
+                else
+#endif
+                    env_step_regs<MODE, SELFPLAY, false, false>(v, io, e, s, ep, st, &s_counts[threadIdx.x], sr, pick, GeomGlobal(), input);
+            }
             wrote = wrote || st.wrote_slots;
         }
         if (MODE != MODE_RESET) {
@@ -787,8 +795,8 @@ static const int8_t kDefaultBoard[64] = {-3, -5, -4, -2, -1, -4, -5, -3, -6, -6,
 template <int MODE>
 static int launch_io(gcb_env* env, StepIO& io, cudaStream_t s) {
     const int grid = grid_for(io.e_end - io.e_begin);
-    // (measured: without the mask output the generic kernel is faster at one step per launch -- 95 vs 105 us per step of 524,288
-    // envs; with it the tile wins, 166 vs 191 us, because the mask is scattered from shared memory)
+    // (measured: without the mask output the generic kernel -- with unchecked slot stores -- is faster at one step per launch:
+    // 90 vs 105 us per step of 524,288 envs; with it the tile wins, 166 vs 191 us, because the mask is scattered from shared memory)
     const bool tile = GCB_SINGLE_TILE && env->bits_out != nullptr && env->v.slots == GCB_SLOTS && MODE != MODE_RESET && MODE != MODE_BOTPLY;
     const bool selfplay = MODE != MODE_RESET && MODE != MODE_BOTPLY && env->v.opponent == 0 && !env->v.agent_black;
     io.bits_out = (MODE != MODE_RESET) ? env->bits_out : nullptr, io.bits_stride = env->bits_stride;
@@ -1037,11 +1045,13 @@ extern "C" int gcb_env_step_sampled(gcb_env* env, int nsteps, int32_t* d_reward,
             if (io.e_begin >= io.e_end) break;
             cudaStream_t ls = R > 1 ? env->streams[r] : cs;
             const int grid = grid_for(io.e_end - io.e_begin);
-            // several steps: the slots are staged into the tile once (TILE 1); a few: nothing is staged in (TILE 2)
+            // several steps: the slots are staged into the tile once (TILE 1); a few steps that also write the bit mask:
+            // generation on the tile without stage-in (TILE 2); a few plain steps: the generic kernel (measured fastest)
             if (tiled && k >= 4 && selfplay) k_env_step<MODE_SAMPLED, 1, true><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
             else if (tiled && k >= 4) k_env_step<MODE_SAMPLED, 1, false><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
-            else if (tiled && selfplay) k_env_step<MODE_SAMPLED, 2, true><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
-            else if (tiled) k_env_step<MODE_SAMPLED, 2, false><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
+            else if (tiled && io.bits_out && selfplay) k_env_step<MODE_SAMPLED, 2, true><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
+            else if (tiled && io.bits_out) k_env_step<MODE_SAMPLED, 2, false><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
+            else if (selfplay) k_env_step<MODE_SAMPLED, 0, true><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
             else k_env_step<MODE_SAMPLED, 0, false><<<grid, GCB_BLOCK, 0, ls>>>(env->v, io);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             const cudaError_t le = cudaGetLastError();
