@@ -966,9 +966,14 @@ extern "C" int gcb_env_create(const gcb_env_config* cfg_in, gcb_env** out) {
     DeviceScope dev_scope_;                                          \
     CU(dev_scope_.enter((env)->cfg.device))
 
+// a registered mask output (gcb_env_step_mask_output) is kept current by everything that changes the legal set: the step
+// kernels write it themselves, reset and import run the mask kernel behind them
+static int refresh_mask_output(gcb_env* env, cudaStream_t s);
+
 extern "C" int gcb_env_reset(gcb_env* env, const uint8_t* d_mask, void* stream) {
     ENV_CHECK(env);
-    return launch_step<MODE_RESET>(env, d_mask, nullptr, nullptr, nullptr, nullptr, nullptr, 1, (cudaStream_t)stream);
+    if (int rc = launch_step<MODE_RESET>(env, d_mask, nullptr, nullptr, nullptr, nullptr, nullptr, 1, (cudaStream_t)stream)) return rc;
+    return refresh_mask_output(env, (cudaStream_t)stream);
 }
 
 extern "C" int gcb_env_step(gcb_env* env, const int32_t* d_actions, int32_t* d_reward, uint8_t* d_done, uint8_t* d_flags,
@@ -1237,7 +1242,7 @@ extern "C" int gcb_env_import(gcb_env* env, const int8_t* d_boards, const int8_t
                                                                                d_mask, env->tick);
     env->tick++;
     LAUNCHED();
-    return GCB_OK;
+    return refresh_mask_output(env, (cudaStream_t)stream);
 }
 
 // ---- checkpoint / resume: the resident state is plain arrays; a snapshot is their concatenation in one device buffer
@@ -1313,6 +1318,13 @@ extern "C" int gcb_env_legal_bitmask(gcb_env* env, uint64_t* d_bits, int stride_
     ENV_CHECK(env);
     if (!d_bits || stride_words < 65) return fail(GCB_E_ARG, "gcb_env_legal_bitmask", "null pointer or stride_words < 65");
     k_env_legal_bits<<<grid_for(env->v.N), GCB_BLOCK, 0, (cudaStream_t)stream>>>(env->v, reinterpret_cast<u64*>(d_bits), stride_words, 0, env->v.N);
+    LAUNCHED();
+    return GCB_OK;
+}
+
+static int refresh_mask_output(gcb_env* env, cudaStream_t s) {
+    if (!env->bits_out) return GCB_OK;
+    k_env_legal_bits<<<grid_for(env->v.N), GCB_BLOCK, 0, s>>>(env->v, env->bits_out, env->bits_stride, 0, env->v.N);
     LAUNCHED();
     return GCB_OK;
 }

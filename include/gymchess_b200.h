@@ -224,7 +224,8 @@ int gcb_env_legal_bitmask(gcb_env *env, uint64_t *d_bits, int stride_words, void
  * on the stream of the step: the step kernel writes the mask itself, right where it leaves the env's legal set (no second
  * kernel, no second pass over the state) -- the rows of a warp's envs are zero-filled with coalesced stores and each
  * thread scatters the at most 17 non-zero words of its env.
- * d_bits = NULL switches the output off.  An even stride_words (e.g. 66) lets the rows be written as 16-byte stores. */
+ * gcb_env_reset and gcb_env_import keep a registered buffer current too (the mask kernel runs behind them; gcb_env_restore does
+ * not).  d_bits = NULL switches the output off.  An even stride_words (e.g. 66) lets the rows be written as 16-byte stores. */
 int gcb_env_step_mask_output(gcb_env *env, uint64_t *d_bits, int stride_words);
 /* ChessEnvV2.possible_actions (chess_v2.py:333-335) of every env: d_actions uint16[N][stride] receives the list in
  * the reference's order (normal moves in generation order, then castles), d_counts int32[N] (may be NULL) the true

@@ -782,6 +782,13 @@ def test_step_writes_the_legal_bit_mask_itself(opponent, color, auto_reset):
                 env.wait()
                 ref.step_index(torch.from_numpy((w.astype(np.uint32) << 16).view(np.int32)).cuda())
             assert torch.equal(bits[:, :65], ref.legal_bitmask()), (width, t, kind)
+        m = torch.arange(N, device="cuda") % 5 == 0                         # a masked reset and a state import keep it current
+        env.reset(m), ref.reset(m)
+        assert torch.equal(bits[:, :65], ref.legal_bitmask()), (width, "reset")
+        b, info = ref.observe().reshape(N, 64), ref.info_tensor()
+        for x in (env, ref):
+            x.set_state(b, info[:, 0].to(torch.int8), info[:, 1:5].to(torch.uint8), info[:, 8], ~m)
+        assert torch.equal(bits[:, :65], ref.legal_bitmask()), (width, "import")
         env.set_mask_output(None)
     assert env.stats() == ref.stats()
     # more piece slots than the tile holds: the mask kernel runs behind the generic step kernel
