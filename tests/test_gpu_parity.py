@@ -504,6 +504,54 @@ def test_pipelined_env_send_recv():
     assert pipe.stats() == whole.stats() and whole.stats()["episodes"] > 0
 
 
+def test_pipelined_env_brings_observation_and_mask_back():
+    """PipelinedChessEnv(observe=True, mask=True): after recv(k) the page-locked observation planes and bit mask of shard k are
+    those of the state the step left behind (== a reference env stepped with the same words); planes() decode to observe()"""
+    import torch
+    from gym_chess_b200 import BatchedChessEnv, PipelinedChessEnv
+
+    N, T = 20480, 40
+    ref = BatchedChessEnv(N, opponent="random", seed=31)
+    pipe = PipelinedChessEnv(N, shards=2, opponent="random", seed=31, observe=True, mask=True)
+    H = pipe.shard_envs
+    rng = np.random.RandomState(4)
+    for t_ in range(T):
+        w = rng.randint(0, 1 << 16, size=N).astype(np.uint16)
+        ref.step_index(torch.from_numpy((w.astype(np.uint32) << 16).view(np.int32)).cuda())
+        for k in range(2):
+            pipe.inputs[k][:] = w[k * H:(k + 1) * H]
+            pipe.send_words(k)
+        p01, p23 = ref.planes()
+        bits = ref.legal_bitmask()
+        for k in range(2):
+            pipe.recv(k)
+            sl = slice(k * H, (k + 1) * H)
+            assert torch.equal(pipe.observations[k][0], p01[sl].cpu()) and torch.equal(pipe.observations[k][1], p23[sl].cpu()), (t_, k)
+            assert torch.equal(pipe.masks[k][:, :65], bits[sl].cpu()), (t_, k)
+    # the planes are the observation: piece code bits t0 | t1 | t2 and the colour plane reproduce observe()
+    p01, p23 = ref.planes()
+    sq = torch.arange(64, device="cuda", dtype=torch.int64)
+    bit = lambda plane: ((plane[:, None] >> sq) & 1)
+    code = bit(p01[:, 0]) + 2 * bit(p01[:, 1]) + 4 * bit(p23[:, 0])
+    board = torch.where(bit(p23[:, 1]) == 1, code, -code).to(torch.int8)
+    assert torch.equal(board, ref.observe().reshape(N, 64))
+    pipe.close()
+
+
+def test_dephase_spreads_the_episode_phases():
+    """BatchedChessEnv.dephase: afterwards the envs are not in lockstep any more (step_in_episode takes many values) and the
+    env still agrees with the oracle's rules (statistics identity)"""
+    from gym_chess_b200 import BatchedChessEnv
+
+    env = BatchedChessEnv(8192, opponent="none", seed=3)
+    env.dephase()
+    steps = env.info_tensor()[:, 11]
+    assert steps.unique().numel() >= 40
+    env.step_sampled(400)
+    s = env.stats()
+    assert s["episodes"] == s["mates"] + s["repetitions"] + s["caps"] + s["wedged"] and s["invalid"] == 0
+
+
 def test_endgames_with_long_repetition_windows():
     """BASELINE.json configs[4]: repetition/promotion-heavy endgames with a 512-ply Zobrist history.  Parity against the
     oracle at a size it replays in seconds; at 1M envs the size-independent properties."""
