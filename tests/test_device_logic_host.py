@@ -212,3 +212,28 @@ def test_next_state_reports_both_kings_in_check():
         assert st[0] == 1 and list(oc[0]) == [1, 1] and ob[0, 0] == 3 and ob[0, 56] == 0
     ob, orr, oc, rew, st = emul.next_state(b[None], 1, np.ones((1, 4), np.uint8), [56 * 64 + 57])   # Ra1-b1: only White in check
     assert st[0] == 0 and list(oc[0]) == [1, 0]
+
+
+def test_hypothesis_random_boards_movegen_and_next_state():
+    """hypothesis-driven differential test on arbitrary boards (illegal, kingless, many pieces of a
+    kind, pawns anywhere): ordered legal / attack lists, update_state and next_state of the device rules == the oracle"""
+    from hypothesis import given, settings, strategies as hs
+
+    piece = hs.sampled_from([0, 0, 0, 0, 1, -1, 2, -2, 3, -3, 4, -4, 5, -5, 6, -6])
+
+    @settings(max_examples=300, deadline=None)
+    @given(hs.lists(piece, min_size=64, max_size=64), hs.sampled_from([1, -1]), hs.lists(hs.booleans(), min_size=4, max_size=4),
+           hs.integers(0, 4100))
+    def check(cells, player, rights, action):
+        b = np.array(cells, np.int8)[None]
+        r = np.array(rights, np.uint8)[None]
+        for attack in (False, True):
+            out, cnt, _ = emul.movegen(b, player, r, attack)
+            exp, ecnt = orc.movegen_batch(b, player, r, attack, stride=out.shape[1])
+            assert cnt[0] == ecnt[0] and (out[0, : cnt[0]] == exp[0, : cnt[0]]).all()
+        assert all((x == y).all() for x, y in zip(emul.update_state(b, r), orc.update_state_batch(b, r)))
+        out, cnt, _ = emul.movegen(b, player, r, False)
+        a = int(out[0, action % cnt[0]]) if cnt[0] and action % 3 else action
+        assert all((np.asarray(x) == np.asarray(y)).all() for x, y in zip(emul.next_state(b, player, r, [a]), orc.next_state_batch(b, player, r, [a])))
+
+    check()
