@@ -8,7 +8,8 @@ v1 never captures a king with a non-pawn piece, needs both rights for any castle
 fixture stores v1's answers verbatim; the comparison (tests/test_oracle_golden.py) drops castles and moves onto the
 enemy king square from both sides and skips positions v1 refuses.
 
-Output: tests/golden/v1_move_sets.json.gz = [{board[64], player, moves [[from, to], ...]}]
+Output: tests/golden/v1_move_sets.json.gz = [{board[64], player, moves [[from, to], ...], attack [[from, to], ...]}]
+(`attack` = v1's get_possible_moves(attack=True): the attack / defence pseudo-moves, in v1's order)
 """
 import gzip
 import json
@@ -47,6 +48,7 @@ def main():
             env = ChessEnvV1(opponent="none", log=False, initial_state=b.reshape(8, 8).astype(np.int8).copy())
             color = "WHITE" if p > 0 else "BLACK"
             moves = env.get_possible_moves(state=env.state, player=color)
+            attack = env.get_possible_moves(state=env.state, player=color, attack=True)
         except Exception:  # noqa: BLE001  (v1 raises on adjacent kings etc.)
             skipped += 1
             continue
@@ -57,9 +59,10 @@ def main():
             else:
                 (r0, c0), (r1, c1) = m
                 ms.append([int(r0) * 8 + int(c0), int(r1) * 8 + int(c1)])
-        out.append({"board": [int(x) for x in b], "player": p, "moves": ms})
-    with gzip.open(os.path.join(HERE, "v1_move_sets.json.gz"), "wt") as f:
-        json.dump(out, f)
+        att = [[int(r0) * 8 + int(c0), int(r1) * 8 + int(c1)] for (r0, c0), (r1, c1) in attack]
+        out.append({"board": [int(x) for x in b], "player": p, "moves": ms, "attack": att})
+    with gzip.GzipFile(os.path.join(HERE, "v1_move_sets.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(out, separators=(",", ":")).encode())
     print("positions", len(out), "skipped", skipped)
     # report the agreement with the oracle under the documented normalisation
     bad = 0

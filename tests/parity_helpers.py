@@ -352,10 +352,12 @@ def endgame_boards():
 
 
 def check_v1_move_sets(movegen_fn, records):
-    """Move SETS of the reference's own pure-Python env (chess_v1.py, unmodified; tests/golden/make_golden_v1.py): an
+    """Move lists of the reference's own pure-Python env (chess_v1.py, unmodified; tests/golden/make_golden_v1.py): an
     implementation that shares no code with lib.rs or with the oracle.  v1 never captures a king with a non-pawn piece
     and castles under other conditions: castles and moves onto the enemy king square are dropped from
-    both sides, everything else must agree exactly."""
+    both sides, everything else must agree exactly -- as SETS and in ORDER, for both colours.  The one documented order
+    difference is normalised: v1 lists a black pawn's captures as (col-1, col+1), v2 as (col+1, col-1) for both colours
+    (v1.py:761-764 vs lib.rs:921-924)."""
     boards = np.array([r["board"] for r in records], np.int8)
     players = np.array([r["player"] for r in records], np.int8)
     res = movegen_fn(boards, players, np.zeros((len(records), 4), np.uint8), False)
@@ -363,8 +365,36 @@ def check_v1_move_sets(movegen_fn, records):
     n = 0
     for i, r in enumerate(records):
         eking = int(np.nonzero(boards[i] == -r["player"])[0][0])
-        mine = {(int(a) >> 6, int(a) & 63) for a in out[i, : cnt[i]] if a < 4096 and (int(a) & 63) != eking}
-        theirs = {tuple(m) for m in r["moves"] if not isinstance(m, str) and m[1] != eking}
-        assert mine == theirs, (i, np.array(r["board"]).reshape(8, 8), r["player"], sorted(mine ^ theirs))
+        mine = [(int(a) >> 6, int(a) & 63) for a in out[i, : cnt[i]] if a < 4096 and (int(a) & 63) != eking]
+        theirs = [tuple(m) for m in r["moves"] if not isinstance(m, str) and m[1] != eking]
+        assert set(mine) == set(theirs), (i, np.array(r["board"]).reshape(8, 8), r["player"], sorted(set(mine) ^ set(theirs)))
+        if r["player"] < 0:
+            k = 0
+            while k + 1 < len(theirs):
+                (f0, t0), (f1, t1) = theirs[k], theirs[k + 1]
+                if f0 == f1 and boards[i][f0] == -6 and t0 == f0 + 7 and t1 == f0 + 9:
+                    theirs[k], theirs[k + 1] = theirs[k + 1], theirs[k]
+                    k += 2
+                else:
+                    k += 1
+        assert mine == theirs, ("order", i, np.array(r["board"]).reshape(8, 8), r["player"], mine, theirs)
         n += len(theirs)
+    # attack=True lists (v1's get_possible_moves(attack=True)): the whole ordered list, same black-pawn normalisation
+    if records and "attack" in records[0]:
+        res = movegen_fn(boards, players, np.zeros((len(records), 4), np.uint8), True)
+        out, cnt = res[0], res[1]
+        for i, r in enumerate(records):
+            mine = [(int(a) >> 6, int(a) & 63) for a in out[i, : cnt[i]]]
+            theirs = [tuple(m) for m in r["attack"]]
+            if r["player"] < 0:
+                k = 0
+                while k + 1 < len(theirs):
+                    (f0, t0), (f1, t1) = theirs[k], theirs[k + 1]
+                    if f0 == f1 and boards[i][f0] == -6 and t0 == f0 + 7 and t1 == f0 + 9:
+                        theirs[k], theirs[k + 1] = theirs[k + 1], theirs[k]
+                        k += 2
+                    else:
+                        k += 1
+            assert mine == theirs, ("attack", i, np.array(r["board"]).reshape(8, 8), r["player"], mine, theirs)
+            n += len(theirs)
     return n
