@@ -25,7 +25,8 @@ def load_golden():
     with open(os.path.join(GOLD, "reference_v2_tests.json")) as f:
         ref = json.load(f)
     return dict(reference_tests=ref, trajectories=gz("trajectories.json.gz"), positions=gz("positions.json.gz"),
-                v1_move_sets=gz("v1_move_sets.json.gz"), render_info=gz("render_info.json.gz"))
+                v1_move_sets=gz("v1_move_sets.json.gz"), render_info=gz("render_info.json.gz"),
+                v1_next_states=gz("v1_next_states.json.gz"))
 
 
 # ------------------------------------------------------------------ engine level
@@ -333,6 +334,26 @@ def check_external_bot_replay(make_env, traj):
         cmp(s, (traj["name"], traj["seed"], i))
         n += 1
     return n
+
+
+def check_v1_next_states(next_state_fn, records):
+    """`next_state` of the reference's own pure-Python env (chess_v1.py:366-450, unmodified; tests/golden/
+    make_golden_v1_next.py): board after the move, reward (capture value, K = 0; the dead promotion of Q1 by direct call)
+    and both check flags (v1.py:1008-1026) for plain moves, castles and pawn moves onto the wrong last rank.  Rights are
+    not compared (v1 tracks them differently)."""
+    boards = np.array([r["board"] for r in records], np.int8)
+    players = np.array([r["player"] for r in records], np.int8)
+    actions = np.array([r["action"] for r in records], np.int32)
+    ob, orr, oc, rew, st = next_state_fn(boards, players, np.ones((len(records), 4), np.uint8), actions)
+    ob, oc, rew, st = np.asarray(ob).reshape(-1, 64), np.asarray(oc).reshape(-1, 2), np.asarray(rew), np.asarray(st)
+    exp_b = np.array([r["board_after"] for r in records], np.int8)
+    assert (ob == exp_b).all(), np.nonzero((ob != exp_b).any(1))[0][:10]
+    assert (rew == np.array([r["reward"] for r in records])).all()
+    assert (st >= 0).all()
+    for i, r in enumerate(records):
+        if r["checks"] is not None:
+            assert [int(x) for x in oc[i]] == r["checks"], (i, r)
+    return len(records)
 
 
 def queen_heavy_boards():

@@ -237,3 +237,7 @@ def test_hypothesis_random_boards_movegen_and_next_state():
         assert all((np.asarray(x) == np.asarray(y)).all() for x, y in zip(emul.next_state(b, player, r, [a]), orc.next_state_batch(b, player, r, [a])))
 
     check()
+
+
+def test_next_states_of_the_reference_pure_python_env(golden):
+    assert ph.check_v1_next_states(emul.next_state, golden["v1_next_states"]) > 3500

@@ -869,6 +869,10 @@ def test_engine_shim_raises_like_cpython_when_both_kings_are_in_check(eng):
     assert ns["white_king_is_checked"] and not ns["black_king_is_checked"] and r == 0
 
 
+def test_next_states_of_the_reference_pure_python_env(eng, golden):
+    assert ph.check_v1_next_states(eng.next_state, golden["v1_next_states"]) > 3500
+
+
 def test_no_index_violation_flag_in_this_process():
     """runs last in this file: the violation word of the library stayed clear through every test above"""
     import ctypes as C

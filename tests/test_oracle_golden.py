@@ -146,3 +146,7 @@ def test_oracle_matches_move_sets_of_the_reference_pure_python_env(golden):
 
     assert len(golden["v1_move_sets"]) > 800
     assert ph.check_v1_move_sets(mg, golden["v1_move_sets"]) > 15000
+
+
+def test_next_states_of_the_reference_pure_python_env(golden):
+    assert ph.check_v1_next_states(orc.next_state_batch, golden["v1_next_states"]) > 3500
