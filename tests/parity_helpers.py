@@ -356,6 +356,21 @@ def check_v1_next_states(next_state_fn, records):
     return len(records)
 
 
+def check_v1_castle_through_attack_vector(castle_moves_fn):
+    """gym_chess/test/v1/test_castle_moves.py:54-74 (commented out in the v2 twin, same rule in lib.rs:966-1012): white pawns
+    on rank 2 except c2, Ra1, Ke1, black Rc8 -> c1 is attacked, no queen-side castle; with the c-pawn back it is offered.
+    castle_moves_fn(board int8[64], player) -> list of action codes."""
+    b = np.zeros(64, np.int8)
+    b[48:56] = 6
+    b[50] = 0
+    b[2], b[56], b[60] = -3, 3, 1
+    assert castle_moves_fn(b, 1) == []
+    b[50] = 6
+    assert castle_moves_fn(b, 1) == [4097]
+    b[63] = 3                                             # and with Rh1 both, queen side first (lib.rs:992, 1011)
+    assert castle_moves_fn(b, 1) == [4097, 4096]
+
+
 def queen_heavy_boards():
     """initial boards on which White has more than 255 legal moves (found by hill climbing; 266 and 271 moves).  Sixteen
     pieces cannot get there (best found: 243), so these have 24 and 28 white pieces -> more than 16 piece slots."""

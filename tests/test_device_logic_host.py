@@ -241,3 +241,10 @@ def test_hypothesis_random_boards_movegen_and_next_state():
 
 def test_next_states_of_the_reference_pure_python_env(golden):
     assert ph.check_v1_next_states(emul.next_state, golden["v1_next_states"]) > 3500
+
+
+def test_v1_castle_through_attack_vector():
+    def fn(b, p):
+        out, cnt, _ = emul.movegen(b[None], p, np.ones((1, 4), np.uint8), False, castles_only=True)
+        return [int(a) for a in out[0, : cnt[0]]]
+    ph.check_v1_castle_through_attack_vector(fn)

@@ -873,6 +873,13 @@ def test_next_states_of_the_reference_pure_python_env(eng, golden):
     assert ph.check_v1_next_states(eng.next_state, golden["v1_next_states"]) > 3500
 
 
+def test_v1_castle_through_attack_vector(eng):
+    def fn(b, p):
+        out, cnt, _ = eng.get_possible_moves(b[None], p, np.ones((1, 4), np.uint8), castles_only=True)
+        return [int(a) for a in out[0, : cnt[0]]]
+    ph.check_v1_castle_through_attack_vector(fn)
+
+
 def test_no_index_violation_flag_in_this_process():
     """runs last in this file: the violation word of the library stayed clear through every test above"""
     import ctypes as C

@@ -150,3 +150,10 @@ def test_oracle_matches_move_sets_of_the_reference_pure_python_env(golden):
 
 def test_next_states_of_the_reference_pure_python_env(golden):
     assert ph.check_v1_next_states(orc.next_state_batch, golden["v1_next_states"]) > 3500
+
+
+def test_v1_castle_through_attack_vector():
+    def fn(b, p):
+        out, cnt = orc.movegen_batch(b[None], p, np.ones((1, 4), np.uint8), False)
+        return [int(a) for a in out[0, : cnt[0]] if a >= 4096]
+    ph.check_v1_castle_through_attack_vector(fn)
