@@ -33,8 +33,9 @@ class _DevArray:
         self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
 
 
-def _stream_ptr(stream=None):
-    return C.c_void_p((torch.cuda.current_stream() if stream is None else stream).cuda_stream)
+def _stream_ptr(stream=None, device=None):
+    """cudaStream_t of `stream`, or of the current torch stream of `device` (default: the current device)"""
+    return C.c_void_p((torch.cuda.current_stream(device) if stream is None else stream).cuda_stream)
 
 
 def _host_ptr(buf):
@@ -219,8 +220,9 @@ class BatchedChessEnv:
         reward = np.empty(N, np.int32) if reward is None else reward
         done = np.empty(N, np.uint8) if done is None else done
         flags = np.empty(N, np.uint8) if flags is None else flags
-        with torch.cuda.device(self.device):
-            check(fn(self._h, inp.ctypes.data, reward.ctypes.data, done.ctypes.data, flags.ctypes.data, _stream_ptr()))
+        # (no torch.cuda.device(...) context here: the library selects and restores the device itself, and this is the hot
+        # synchronous path -- the context manager alone costs more than the launch)
+        check(fn(self._h, inp.ctypes.data, reward.ctypes.data, done.ctypes.data, flags.ctypes.data, _stream_ptr(None, self.device)))
         return reward, done, flags
 
     # ------------------------------------------------------------------ observation / state
