@@ -250,14 +250,21 @@ def main():
     words16.random_(-2 ** 15, 2 ** 15 - 1)
     src16 = [[words16[j, k] for k in range(2)] for j in range(8)]
 
-    def pipelined(observe, mask):
+    def pipelined(observe, mask, shards=2):
         """the rank's envs as two shards stepped alternately through PipelinedChessEnv.send_words / recv: uint16 words in,
-        uint16 records out (+ observation planes / + bit mask, copied device -> host behind each step)"""
-        pipe = PipelinedChessEnv(N, shards=2, device=local_rank, env_id_offset=off, opponent="none", seed=2, auto_reset=True,
+        uint16 records out (+ observation planes / + bit mask, copied device -> host behind each step); shards=1: one
+        synchronous send + recv per step"""
+        pipe = PipelinedChessEnv(N, shards=shards, device=local_rank, env_id_offset=off, opponent="none", seed=2, auto_reset=True,
                                  observe=observe, mask=mask)
         pipe.burn_in(args.burn_in, dephase=True)
+        src1 = [words16[j].reshape(-1) for j in range(8)]
 
         def loop(steps):
+            if shards == 1:
+                for i in range(steps):
+                    pipe.send_words(0, src=src1[i % 8])
+                    pipe.recv(0)
+                return
             pipe.send_words(0, src=src16[0][0])
             for i in range(steps):
                 pipe.send_words(1, src=src16[i % 8][1])
@@ -273,6 +280,7 @@ def main():
 
     e2e_value = pipelined(False, False)
     clk = clocks.stop() if rank == 0 else None  # sampled over the timed regions (kernel-only and end-to-end)
+    sync_packed_value = pipelined(False, False, shards=1)
     full_obs_value = pipelined(True, False)
     full_mask_value = pipelined(True, True) if not args.no_extras else None
 
@@ -338,7 +346,10 @@ def main():
                 "full_obs_mask_api": "PipelinedChessEnv(observe=True, mask=True): + the 66-word legal-action bit mask per env "
                                      "(written by the step kernel, gcb_env_step_mask_output); PCIe-bound",
                 "sync_call_value": sync_value,
-                "sync_call_api": "gcb_env_step_index_host: one synchronous call per step for all envs of the rank (4 + 6 bytes)"},
+                "sync_call_api": "gcb_env_step_index_host: one synchronous call per step for all envs of the rank (4 + 6 bytes per env "
+                                 "step across PCIe: 5.2 MB per step of 524,288 envs -- the link, not the kernel, bounds it)",
+                "sync_packed_value": sync_packed_value,
+                "sync_packed_api": "one synchronous send + recv per step with the 16-bit records (PipelinedChessEnv with one shard)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_env_step<MODE_SAMPLED, TILE 1, SELFPLAY>",
