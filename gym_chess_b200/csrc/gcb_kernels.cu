@@ -38,7 +38,7 @@ static int fail(int code, const char* what, const char* detail) {
     } while (0)
 
 extern "C" const char* gcb_last_error(void) { return g_err; }
-extern "C" int gcb_version(void) { return 100; }
+extern "C" int gcb_version(void) { return 200; }  // round 2: host calls take a stream, bot ply, mask output, guards
 extern "C" uint64_t gcb_launch_count(void) { return g_launches.load(); }
 extern "C" int gcb_device_count(void) {
     int n = 0;

@@ -54,3 +54,43 @@ def test_product_package_never_imports_the_oracle():
                 assert "oracle" not in src.replace("the oracle", "").replace("oracle/", "ORACLE_DIR/") or f.endswith((".cuh", ".cu")), f
                 assert "import oracle" not in src and "from oracle" not in src and "libgc_oracle" not in src, f
                 assert "host_emul" not in src or f.endswith(".cuh"), f
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """include/gymchess_b200.h is the whole contract: a C99 program that includes it and links libgymchess_b200.so calls
+    the library (no torch / C++ / CUDA types in the signatures); without a GPU the compute entry points refuse (GCB_E_NOGPU)."""
+    import subprocess
+
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "gymchess_b200.h"
+int main(void) {
+    gcb_env_config cfg;
+    gcb_env *env = NULL;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.num_envs = 4, cfg.moves_max = -1;
+    printf("version %d devices %d\n", gcb_version(), gcb_device_count());
+    int rc = gcb_env_create(&cfg, &env);
+    printf("create rc %d (%s)\n", rc, rc ? gcb_last_error() : "ok");
+    if (rc == GCB_OK) {
+        uint64_t st[16];
+        rc = gcb_env_step_sampled(env, 3, NULL, NULL, NULL, NULL, NULL, NULL);
+        if (rc == GCB_OK) rc = gcb_env_stats(env, st, NULL);
+        printf("steps %llu rc %d\n", (unsigned long long)st[0], rc);
+        gcb_env_destroy(env);
+    }
+    return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           _lib.SO_PATH, "-Wl,-rpath," + os.path.dirname(_lib.SO_PATH)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "version 200" in out.stdout
+    if _lib.lib().gcb_device_count() > 0:
+        assert "steps 12 rc 0" in out.stdout, out.stdout
+    else:
+        assert "create rc -3" in out.stdout and "no CPU fallback" in out.stdout, out.stdout
