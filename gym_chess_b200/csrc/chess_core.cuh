@@ -48,8 +48,24 @@ GCB_HD int gcb_lsb(u64 x) {  // index of the lowest set bit, x != 0
     return __builtin_ctzll(x);
 #endif
 }
+#ifndef GCB_BFIND  // device gcb_msb: one FLO on the non-zero half (1) or the compiler's 63 - clz64 (0)
+#define GCB_BFIND 1
+#endif
+#ifndef GCB_TAKE_BELOW  // piece loops clear the taken square with the mask they need for the slot rank anyway
+#define GCB_TAKE_BELOW 1
+#endif
+#ifndef GCB_NTH_BSEARCH  // nth_target: binary search over cumulative direction masks instead of a walk over the 8 directions
+#define GCB_NTH_BSEARCH 1
+#endif
 GCB_HD int gcb_msb(u64 x) {  // index of the highest set bit, x != 0
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && GCB_BFIND
+    // FLO returns the bit index itself: pick the half, one FLO, add 32 for the high half (63 - clz64 compiles to three more
+    // integer instructions, and this sits in every piece loop)
+    const u32 hi = (u32)(x >> 32), lo = (u32)x;
+    u32 r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(hi ? hi : lo));
+    return (int)(hi ? r + 32u : r);
+#elif defined(__CUDA_ARCH__)
     return 63 - __clzll((long long)x);
 #else
     return 63 - __builtin_clzll(x);
@@ -59,6 +75,19 @@ GCB_HD int gcb_msb(u64 x) {  // index of the highest set bit, x != 0
 GCB_HD int gcb_take(u64& s) {
     const int sq = gcb_msb(s);
     s ^= 1ULL << sq;
+    return sq;
+}
+// ... and also hand back the set of squares BELOW the taken one: the piece loops need it for the slot rank
+// (popcount of the own pieces below), and since the taken square is the highest of s it clears the square as well
+GCB_HD int gcb_take(u64& s, u64& below) {
+    const int sq = gcb_msb(s);
+#if GCB_TAKE_BELOW
+    below = ~(~0ULL << sq);
+    s &= below;
+#else
+    below = (1ULL << sq) - 1;
+    s ^= 1ULL << sq;
+#endif
     return sq;
 }
 GCB_HD int gcb_popc(u64 x) {
@@ -165,7 +194,8 @@ struct alignas(16) GeomTables {
     u64 knight[64], king[64];
     u64 pawn[2][64][2];  // [black][sq]: {push squares (one step; two from the start row), capture squares}
     u64 between[64][64]; // squares strictly between two aligned squares (0 when not aligned)
-    constexpr GeomTables() : line(), ord(), knight(), king(), pawn(), between() {
+    u64 cum[5][64][8];   // cum[c][sq][k] = ord[c][sq][0] | ... | ord[c][sq][k]: nth_target's binary search
+    constexpr GeomTables() : line(), ord(), knight(), king(), pawn(), between(), cum() {
         const int sl[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
         const int kg[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
         const int kn[8][2] = {{-2, -1}, {-2, 1}, {2, -1}, {2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}};
@@ -207,6 +237,10 @@ struct alignas(16) GeomTables {
                         if (k != 1 || r == 1) pawn[1][sq][k >= 2] |= 1ULL << (tr * 8 + tc);  // two steps from row 1 only
                     }
                 }
+            }
+            for (int c5 = 0; c5 < 5; c5++) {
+                u64 acc = 0;
+                for (int k = 0; k < 8; k++) acc |= ord[c5][sq][k], cum[c5][sq][k] = acc;
             }
         }
     }
@@ -452,45 +486,50 @@ template <class Sink, class G>
 GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink, const G& geo) {
     const u64 occ = g.occ, own = g.own, notown = ~g.own;
     const u64 mine = own & subset;
-#define GCB_PUT(sq_, bit_, T_)                                         \
+#define GCB_PUT(sq_, below_, T_)                                       \
     do {                                                               \
         const u64 t__ = (T_);                                          \
-        sink.put(gcb_popc(mine & ((bit_) - 1)), t__);                  \
+        sink.put(gcb_popc(mine & (below_)), t__);                      \
     } while (0)
     // rooks
     for (u64 s = bb_rooks(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = rook_att(geo, sq, occ);
+        u64 below;
+        const int sq = gcb_take(s, below);
+        const u64 a = rook_att(geo, sq, occ);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & g.cm);
+        GCB_PUT(sq, below, a & notown & g.cm);
     }
     // bishops
     for (u64 s = bb_bishops(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = bishop_att(geo, sq, occ);
+        u64 below;
+        const int sq = gcb_take(s, below);
+        const u64 a = bishop_att(geo, sq, occ);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & g.cm);
+        GCB_PUT(sq, below, a & notown & g.cm);
     }
     // queens
     for (u64 s = bb_queens(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = rook_att(geo, sq, occ) | bishop_att(geo, sq, occ);
+        u64 below;
+        const int sq = gcb_take(s, below);
+        const u64 a = rook_att(geo, sq, occ) | bishop_att(geo, sq, occ);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & g.cm);
+        GCB_PUT(sq, below, a & notown & g.cm);
     }
     // knights
     for (u64 s = bb_knights(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = geo.knight(sq);
+        u64 below;
+        const int sq = gcb_take(s, below);
+        const u64 a = geo.knight(sq);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & g.cm);
+        GCB_PUT(sq, below, a & notown & g.cm);
     }
     // kings: never passed through the legality filter (lib.rs:615-619); attack map with the king on it (Q6)
     for (u64 s = bb_kings(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        const u64 bit = 1ULL << sq, a = geo.king(sq);
+        u64 below;
+        const int sq = gcb_take(s, below);
+        const u64 a = geo.king(sq);
         g.satt |= a;
-        GCB_PUT(sq, bit, a & notown & ~g.eatt);
+        GCB_PUT(sq, below, a & notown & ~g.eatt);
     }
     // pawns (lib.rs:918-964): one step if empty; two steps from the start row if the TARGET is empty (the
     // jumped square is not tested, Q13); diagonals onto enemy pieces incl. the king; no en passant
@@ -499,17 +538,18 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink, const
         g.satt |= pawn_set_att(pw, g.white) & ~(bb_kings(b) & own);  // Q14
         (void)allp;
         for (u64 s = pw; s;) {
-            const int sq = gcb_take(s);
-            const u64 bit = 1ULL << sq;
+            u64 below;
+            const int sq = gcb_take(s, below);
             const u64 push = geo.pawn(!g.white, sq, 0), cap = geo.pawn(!g.white, sq, 1);
-            GCB_PUT(sq, bit, ((push & ~occ) | (cap & g.enemy)) & g.cm);
+            GCB_PUT(sq, below, ((push & ~occ) | (cap & g.enemy)) & g.cm);
         }
     }
 #undef GCB_PUT
     // pinned pieces (rare per position, but some env of a warp nearly always has one): one fix-up pass over the
     // slots instead of a pin test at every generation site
     for (u64 p = g.pinned & mine & ~bb_kings(b); p;) {
-        const int sq = gcb_take(p), r = gcb_popc(mine & ((1ULL << sq) - 1));
+        u64 below;
+        const int sq = gcb_take(p, below), r = gcb_popc(mine & below);
         const u64 t = sink.get(r), t2 = t & pin_mask(g, sq);
         sink.replace(r, t, t2);
     }
@@ -580,6 +620,28 @@ GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
     const int cls = order_class(code, white);
     u64 mf = 0;
     bool desc = false;
+#if GCB_NTH_BSEARCH
+    // the direction that holds the idx-th target = the first k with popc(T & cum[k]) > idx: three dependent table loads, the
+    // same instructions in every lane (the walk over the directions ran the warp for its slowest lane: 10 of 32 lanes
+    // active).  `below` / `above` end up as cum[k-1] / cum[k], so the direction's own targets need no fourth load.
+    {
+        (void)ROLLED;
+        int k = 0, nb = 0;
+        u64 below = 0, above = ~0ULL;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int step = 4; step; step >>= 1) {
+            const u64 m = GCB_GEOM(cum[cls][sq][k + step - 1]);
+            const int c = gcb_popc(T & m);
+            const bool right = idx >= c;
+            k = right ? k + step : k, nb = right ? c : nb;
+            below = right ? m : below, above = right ? above : m;
+        }
+        mf = T & above & ~below, idx -= nb;
+        desc = (GCB_RAY_DESC_MASK >> k) & 1;
+    }
+#else
   if (ROLLED) {
     // a rolled loop with early exit: 8x less code on the step kernel's hot path (its instruction footprint is what the
     // instruction cache holds)
@@ -607,6 +669,7 @@ GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
         if (!mf) idx -= c;
     }
   }
+#endif
     if (!mf) return sq;
     if (desc) mf = gcb_brev64(mf);  // nearest first = lowest bit first in both cases
     const int t = gcb_select64(mf, idx);
@@ -681,15 +744,16 @@ GCB_HD int emit_chunk_typemajor(const Board& b, int white, u64 mine, const Slots
         base = acc;
     }
     const u64 t0 = b.t0, t1 = b.t1, t2 = b.t2;
-#define GCB_PIECE(sq_)                                              \
-    const int sq = (sq_);                                           \
-    const int r = gcb_popc(mine & ((1ULL << sq) - 1));              \
+#define GCB_PIECE(set_)                                             \
+    u64 below;                                                      \
+    const int sq = gcb_take(set_, below);                           \
+    const int r = gcb_popc(mine & below);                           \
     const u64 T = slots.get(r);                                     \
     int pos = offs.get(r);                                          \
     const int from64 = sq * 64
     // rooks: rays 0-3
     for (u64 s = (t0 & t1 & ~t2) & mine; s;) {
-        GCB_PIECE(gcb_take(s));
+        GCB_PIECE(s);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -697,7 +761,7 @@ GCB_HD int emit_chunk_typemajor(const Board& b, int white, u64 mine, const Slots
     }
     // bishops: rays 4-7
     for (u64 s = (~t0 & ~t1 & t2) & mine; s;) {
-        GCB_PIECE(gcb_take(s));
+        GCB_PIECE(s);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -705,7 +769,7 @@ GCB_HD int emit_chunk_typemajor(const Board& b, int white, u64 mine, const Slots
     }
     // queens: all eight
     for (u64 s = (~t0 & t1 & ~t2) & mine; s;) {
-        GCB_PIECE(gcb_take(s));
+        GCB_PIECE(s);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -713,7 +777,7 @@ GCB_HD int emit_chunk_typemajor(const Board& b, int white, u64 mine, const Slots
     }
     // knights (lib.rs:891-900) and kings (lib.rs:797-806): eight single squares in the reference's order
     for (u64 s = (t0 & ~t1 & t2) & mine; s;) {
-        GCB_PIECE(gcb_take(s));
+        GCB_PIECE(s);
         const int d[8] = {-17, -15, 15, 17, -10, -6, 6, 10};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -722,7 +786,7 @@ GCB_HD int emit_chunk_typemajor(const Board& b, int white, u64 mine, const Slots
             if (T & sq_bit_safe(sq + d[k])) out.put(pos++, from64 + sq + d[k]);
     }
     for (u64 s = (t0 & ~t1 & ~t2) & mine; s;) {
-        GCB_PIECE(gcb_take(s));
+        GCB_PIECE(s);
         const int d[8] = {8, -8, 1, -1, 9, 7, -7, -9};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -734,7 +798,7 @@ GCB_HD int emit_chunk_typemajor(const Board& b, int white, u64 mine, const Slots
     {
         const int d0 = white ? -8 : 8, d1 = white ? -16 : 16, d2 = white ? -7 : 9, d3 = white ? -9 : 7;
         for (u64 s = (~t0 & t1 & t2) & mine; s;) {
-            GCB_PIECE(gcb_take(s));
+            GCB_PIECE(s);
             if (T & sq_bit_safe(sq + d0)) out.put(pos++, from64 + sq + d0);
             if (T & sq_bit_safe(sq + d1)) out.put(pos++, from64 + sq + d1);
             if (T & sq_bit_safe(sq + d2)) out.put(pos++, from64 + sq + d2);
@@ -780,30 +844,36 @@ GCB_HD int gen_legal_list(const Board& b, int white_to_move, u32 rights, Slots& 
 template <class Sink, class G>
 GCB_HD void gen_attack_targets(const Board& b, int white, u64 subset, Sink& sink, const G& geo) {
     const u64 occ = bb_occ(b), own = white ? b.w : (occ & ~b.w), mine = own & subset, ownk = bb_kings(b) & own;
-#define GCB_APUT(bit_, T_) sink.put(gcb_popc(mine & ((bit_) - 1)), (T_))
+#define GCB_APUT(below_, T_) sink.put(gcb_popc(mine & (below_)), (T_))
     for (u64 s = bb_rooks(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        GCB_APUT(1ULL << sq, rook_att(geo, sq, occ));
+        u64 below;
+        const int sq = gcb_take(s, below);
+        GCB_APUT(below, rook_att(geo, sq, occ));
     }
     for (u64 s = bb_bishops(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        GCB_APUT(1ULL << sq, bishop_att(geo, sq, occ));
+        u64 below;
+        const int sq = gcb_take(s, below);
+        GCB_APUT(below, bishop_att(geo, sq, occ));
     }
     for (u64 s = bb_queens(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        GCB_APUT(1ULL << sq, rook_att(geo, sq, occ) | bishop_att(geo, sq, occ));
+        u64 below;
+        const int sq = gcb_take(s, below);
+        GCB_APUT(below, rook_att(geo, sq, occ) | bishop_att(geo, sq, occ));
     }
     for (u64 s = bb_knights(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        GCB_APUT(1ULL << sq, geo.knight(sq));
+        u64 below;
+        const int sq = gcb_take(s, below);
+        GCB_APUT(below, geo.knight(sq));
     }
     for (u64 s = bb_kings(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        GCB_APUT(1ULL << sq, geo.king(sq));
+        u64 below;
+        const int sq = gcb_take(s, below);
+        GCB_APUT(below, geo.king(sq));
     }
     for (u64 s = bb_pawns(b) & mine; s;) {
-        const int sq = gcb_take(s);
-        GCB_APUT(1ULL << sq, geo.pawn(!white, sq, 1) & ~ownk);
+        u64 below;
+        const int sq = gcb_take(s, below);
+        GCB_APUT(below, geo.pawn(!white, sq, 1) & ~ownk);
     }
 #undef GCB_APUT
 }
