@@ -54,6 +54,9 @@ GCB_HD int gcb_lsb(u64 x) {  // index of the lowest set bit, x != 0
 #ifndef GCB_TAKE_BELOW  // piece loops clear the taken square with the mask they need for the slot rank anyway
 #define GCB_TAKE_BELOW 1
 #endif
+#ifndef GCB_ZONE_FILTER  // opponent attack map: only the sliders that can reach the king zone are evaluated
+#define GCB_ZONE_FILTER 1
+#endif
 #ifndef GCB_NTH_BSEARCH  // nth_target: binary search over cumulative direction masks instead of a walk over the 8 directions
 #define GCB_NTH_BSEARCH 1
 #endif
@@ -195,7 +198,10 @@ struct alignas(16) GeomTables {
     u64 pawn[2][64][2];  // [black][sq]: {push squares (one step; two from the start row), capture squares}
     u64 between[64][64]; // squares strictly between two aligned squares (0 when not aligned)
     u64 cum[5][64][8];   // cum[c][sq][k] = ord[c][sq][0] | ... | ord[c][sq][k]: nth_target's binary search
-    constexpr GeomTables() : line(), ord(), knight(), king(), pawn(), between(), cum() {
+    // zone[0/1][k]: the squares from which a rook / bishop mover could reach, on an empty board, the king square k, one of
+    // its neighbours or (k = e1 / e8) one of the castle squares -- the only places the opponent attack map is ever looked at
+    u64 zone[2][64];
+    constexpr GeomTables() : line(), ord(), knight(), king(), pawn(), between(), cum(), zone() {
         const int sl[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
         const int kg[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
         const int kn[8][2] = {{-2, -1}, {-2, 1}, {2, -1}, {2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}};
@@ -242,6 +248,13 @@ struct alignas(16) GeomTables {
                 u64 acc = 0;
                 for (int k = 0; k < 8; k++) acc |= ord[c5][sq][k], cum[c5][sq][k] = acc;
             }
+        }
+        for (int k = 0; k < 64; k++) {  // (after the loop above: needs line[] and king[] of every square)
+            u64 z = king[k] | (1ULL << k);
+            if (k == 60) z |= 0x7CULL << 56;  // c1..g1 (gen_castles)
+            if (k == 4) z |= 0x7CULL;         // c8..g8
+            for (int t = 0; t < 64; t++)
+                if ((z >> t) & 1) zone[0][k] |= line[t][0] | line[t][1] | (1ULL << t), zone[1][k] |= line[t][2] | line[t][3] | (1ULL << t);
         }
     }
 };
@@ -415,7 +428,8 @@ GCB_HD u64 line_through(int a, int b) {
 
 struct GenCtx {
     u64 occ, own, enemy;  // the per-type sets are recomputed from the planes where they are used (2 LOP3 each): fewer live registers
-    u64 eatt;     // opponent attack map on the CURRENT board, own king left on it (lib.rs:466-470; Q6)
+    u64 eatt;     // opponent attack map on the CURRENT board, own king left on it (lib.rs:466-470; Q6); exact on the
+                  // own kings' neighbourhoods and the castle squares, the only places it is read (see gen_prepare)
     u64 satt;     // attack map of the side to move, accumulated by gen_targets (check flag of the other side)
     u64 cm;       // targets that resolve the check for a non-king piece (all ones when not in check / no king)
     u64 pinned;   // own pieces whose removal opens a slider line onto the king square
@@ -438,12 +452,24 @@ GCB_HD void gen_prepare(const Board& b, int white_to_move, GenCtx& g, const G& g
     // opponent attack map (lib.rs:669-677): pawns minus squares holding the attacker's OWN king (Q14)
     u64 eatt = pawn_set_att(bb_pawns(b) & enemy, !white_to_move) & ~ekings;
     eatt |= knight_set_att(bb_knights(b) & enemy) | king_set_att(ekings);
-    for (u64 s = eRQ; s;) eatt |= rook_att(geo, gcb_take(s), occ);
-    for (u64 s = eBQ; s;) eatt |= bishop_att(geo, gcb_take(s), occ);
+    const u64 ownk = bb_kings(b) & g.own;
+    u64 zR = eRQ, zB = eBQ;
+#if GCB_ZONE_FILTER
+    // The map is only ever tested on the own kings' neighbourhoods (king targets) and on the castle squares (gen_castles),
+    // so a slider none of whose lines crosses that zone need not be evaluated: with one own king, two table words pick the
+    // sliders that matter (fewer trips of the two loops below for the whole warp).  Several own kings (Q15), or black to
+    // move with a WHITE king on e8 (the castle test of Q3 then looks at c8..g8): no filter.  No own king: nothing reads it.
+    if (!ownk) zR = zB = 0;
+    else if (!(ownk & (ownk - 1)) && (white_to_move || !((bb_kings(b) & b.w) >> 4 & 1ULL))) {
+        const int k = gcb_msb(ownk);
+        zR &= GCB_GEOM(zone[0][k]), zB &= GCB_GEOM(zone[1][k]);
+    }
+#endif
+    for (u64 s = zR; s;) eatt |= rook_att(geo, gcb_take(s), occ);
+    for (u64 s = zB; s;) eatt |= bishop_att(geo, gcb_take(s), occ);
     g.eatt = eatt;
 
     g.satt = 0, g.cm = ~0ULL, g.pinned = 0, g.pinrays = 0, g.ksq = 0, g.in_check = false;
-    const u64 ownk = bb_kings(b) & g.own;
     g.has_king = ownk != 0;
     if (!g.has_king) return;  // lib.rs:655-658: no king -> nothing is filtered
     const int ksq = ref_king_square(ownk);
@@ -537,11 +563,12 @@ GCB_HD void gen_targets(const Board& b, GenCtx& g, u64 subset, Sink& sink, const
         const u64 pw = bb_pawns(b) & mine, allp = bb_pawns(b) & own;
         g.satt |= pawn_set_att(pw, g.white) & ~(bb_kings(b) & own);  // Q14
         (void)allp;
+        const u64 free_cm = ~occ & g.cm, enemy_cm = g.enemy & g.cm;  // (hoisted: two LOP3 per half and pawn instead of three)
         for (u64 s = pw; s;) {
             u64 below;
             const int sq = gcb_take(s, below);
             const u64 push = geo.pawn(!g.white, sq, 0), cap = geo.pawn(!g.white, sq, 1);
-            GCB_PUT(sq, below, ((push & ~occ) | (cap & g.enemy)) & g.cm);
+            GCB_PUT(sq, below, (push & free_cm) | (cap & enemy_cm));
         }
     }
 #undef GCB_PUT
