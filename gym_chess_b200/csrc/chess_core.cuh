@@ -57,6 +57,9 @@ GCB_HD int gcb_lsb(u64 x) {  // index of the lowest set bit, x != 0
 #ifndef GCB_ZONE_FILTER  // opponent attack map: only the sliders that can reach the king zone are evaluated
 #define GCB_ZONE_FILTER 1
 #endif
+#ifndef GCB_NTH_TWO_LEVEL
+#define GCB_NTH_TWO_LEVEL 1
+#endif
 #ifndef GCB_NTH_BSEARCH  // nth_target: binary search over cumulative direction masks instead of a walk over the 8 directions
 #define GCB_NTH_BSEARCH 1
 #endif
@@ -655,6 +658,20 @@ GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
         (void)ROLLED;
         int k = 0, nb = 0;
         u64 below = 0, above = ~0ULL;
+#if GCB_NTH_TWO_LEVEL
+        {  // two round trips instead of three: the quarter from cum[1], cum[3], cum[5] (issued together), then one more word
+            const u64 m1 = GCB_GEOM(cum[cls][sq][1]), m3 = GCB_GEOM(cum[cls][sq][3]), m5 = GCB_GEOM(cum[cls][sq][5]);
+            const int c1 = gcb_popc(T & m1), c3 = gcb_popc(T & m3), c5 = gcb_popc(T & m5);
+            const bool r1 = idx >= c1, r3 = idx >= c3, r5 = idx >= c5;  // (monotone: r5 implies r3 implies r1)
+            k = r5 ? 6 : r3 ? 4 : r1 ? 2 : 0, nb = r5 ? c5 : r3 ? c3 : r1 ? c1 : 0;
+            below = r5 ? m5 : r3 ? m3 : r1 ? m1 : 0ULL, above = r5 ? ~0ULL : r3 ? m5 : r1 ? m3 : m1;
+            const u64 m = GCB_GEOM(cum[cls][sq][k]);
+            const int c = gcb_popc(T & m);
+            const bool right = idx >= c;
+            k = right ? k + 1 : k, nb = right ? c : nb;
+            below = right ? m : below, above = right ? above : m;
+        }
+#else
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -665,6 +682,7 @@ GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
             k = right ? k + step : k, nb = right ? c : nb;
             below = right ? m : below, above = right ? above : m;
         }
+#endif
         mf = T & above & ~below, idx -= nb;
         desc = (GCB_RAY_DESC_MASK >> k) & 1;
     }
