@@ -16,9 +16,12 @@ ap.add_argument("--envs", type=int, default=524288)
 ap.add_argument("--burn-in", type=int, default=600)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--opponent", default="none")
+ap.add_argument("--no-dephase", action="store_true", help="leave the batch phase-locked (all envs reset together)")
 args = ap.parse_args()
 
 env = BatchedChessEnv(args.envs, opponent=args.opponent, seed=2)
+if not args.no_dephase:
+    env.dephase()  # the steady-state mix of game phases bench.py measures (86 launches: 43 x (7 sampled steps + masked reset))
 env.step_sampled(args.burn_in)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

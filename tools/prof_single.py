@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """profiling driver for the single-step kernel (external random words on device): tools/prof_single.py [steps] [fused]
-With GCB_SAMPLED_RANGES=1 the first timed launch is k_env_step launch #13 (1 reset + 9 burn-in + 3 warm-up before it)."""
+With GCB_SAMPLED_RANGES=1 the first timed launch is k_env_step launch #99 (1 reset + 86 of dephase() + 9 burn-in + 3 warm-up
+before it)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,6 +9,7 @@ from gym_chess_b200 import BatchedChessEnv
 N = 524288
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 env = BatchedChessEnv(N, opponent="none", seed=2)
+env.dephase()  # the steady-state mix of game phases bench.py measures
 env.step_sampled(576)
 if len(sys.argv) > 2:
     bits = torch.empty((N, 66), dtype=torch.int64, device="cuda")
