@@ -651,9 +651,10 @@ GCB_HD int nth_target(int code, int white, int sq, u64 T, int idx) {
     u64 mf = 0;
     bool desc = false;
 #if GCB_NTH_BSEARCH
-    // the direction that holds the idx-th target = the first k with popc(T & cum[k]) > idx: three dependent table loads, the
-    // same instructions in every lane (the walk over the directions ran the warp for its slowest lane: 10 of 32 lanes
-    // active).  `below` / `above` end up as cum[k-1] / cum[k], so the direction's own targets need no fourth load.
+    // the direction that holds the idx-th target = the first k with popc(T & cum[k]) > idx: a search over the cumulative
+    // direction masks, the same instructions in every lane (the walk over the directions ran the warp for its slowest lane:
+    // 10 of 32 lanes active).  `below` / `above` end up as cum[k-1] / cum[k], so the direction's own targets need no
+    // further load.
     {
         (void)ROLLED;
         int k = 0, nb = 0;
