@@ -22,6 +22,11 @@ def timed(fn, reps=5):
 
 
 env = BatchedChessEnv(N, opponent="none", seed=2)
+if os.environ.get("R2_PERF_DEPHASE", "0") == "1":
+    env.dephase()  # the steady-state mix of game phases bench.py times
+# default: the batch stays phase-locked (all envs reset together) -- the A/B runs recorded in DESIGN.md 3.2 were made that way;
+# their 640-step figure averages over two whole episodes and so agrees with the phase-spread bench, the 20- and 64-step
+# figures belong to one window of plies and only compare builds with each other
 env.step_sampled(burn)
 for k in (20, 64, 640):
     ms = timed(lambda: env.step_sampled(k), reps=5 if k < 600 else 3)
