@@ -406,7 +406,8 @@ __device__ __forceinline__ void run_unit(const EnvView& v, StepIO io, const int 
 
 // one unit per block: the envs [io.e_begin, io.e_end), io.nsteps steps each (one for everything but the sampled mode)
 template <int MODE, int TILE = 0, bool SELFPLAY = false>
-__global__ void __launch_bounds__(GCB_BLOCK, MODE == MODE_SAMPLED ? GCB_SAMPLED_MIN_BLOCKS : GCB_STEP_MIN_BLOCKS) k_env_step(EnvView v, StepIO io) {
+__global__ void __launch_bounds__(GCB_BLOCK, (MODE == MODE_SAMPLED && TILE == 1) ? GCB_SAMPLED_MIN_BLOCKS : GCB_STEP_MIN_BLOCKS)
+    k_env_step(EnvView v, StepIO io) {  // (5 resident blocks at 96 registers for the multi-step tile kernel, 6 at 80 for the rest)
     __shared__ CountBytes s_counts[GCB_BLOCK];
     __shared__ u64 s_slots[TILE ? GCB_SLOTS * GCB_BLOCK : 1];
     __shared__ u64 s_geom[TILE ? GCB_SGEOM_WORDS : 1];
