@@ -617,10 +617,20 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
 
     bool do_apply = true;
     int cur = action;  // cur = the action of the ply being executed
+    // a bot ply draws its move at the top of the next loop trip: ONE site for the bot's reply (purpose 1) and for the bot's
+    // opening ply after a reset (purpose 2) -- the ordered pick is 250 instructions, and the bot kernels wait for
+    // instruction fetch more than for anything else
+    u32 draw_purpose = 0u, draw_step = 0u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     while (phase != PH_END) {
+        if (!SELFPLAY && draw_purpose) {
+            const u32 u = philox_draw(v.seed, genv, ep, draw_step, draw_purpose);
+            cur = action_at<MULTI>(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
+            if (draw_purpose == 1u) bot_action = cur;
+            draw_purpose = 0u;
+        }
         if (phase == PH_FINAL) {
             bool terminal;
             if (MODE == MODE_RESET) {
@@ -671,8 +681,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 } else if (v_agent_black) {
                     // the bot opens for White (chess_v2.py:208-216)
                     if (s.n_legal > 0) {
-                        u32 u = philox_draw(v.seed, genv, ep, 0u, 2u);
-                        cur = action_at<MULTI>(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
+                        draw_purpose = 2u, draw_step = 0u;  // (drawn with the NEW episode counter, at the top of the next trip)
                         do_apply = true;
                     } else {
                         do_apply = false;
@@ -698,9 +707,8 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
                 s.pending = 1, owe_bot = true;  // the step ends here; the reward so far is reported, the bot's ply follows
             } else if (!s.done && v_bot) {
                 if (s.n_legal > 0) {  // chess_v2.py:277-288
-                    u32 u = philox_draw(v.seed, genv, ep, step_idx, 1u);
-                    bot_action = action_at<MULTI>(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
-                    cur = bot_action, phase = PH_BOT;
+                    draw_purpose = 1u, draw_step = step_idx;
+                    phase = PH_BOT;
                     continue;
                 }
                 // bot without moves and not in check: the reference raises TypeError (Q9); stop here
