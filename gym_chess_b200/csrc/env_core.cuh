@@ -364,6 +364,9 @@ GCB_HD int rep_lookup_insert(const EnvView& v, int e, const EnvRegs& s, u64 key,
     return 1;
 }
 
+#ifndef GCB_ONE_PICK_SITE  // bot kernels: every sampled pick of a step (agent, bot reply, bot opening) through one code site
+#define GCB_ONE_PICK_SITE 1
+#endif
 #ifndef GCB_SWAR_PICK
 #define GCB_SWAR_PICK 1
 #endif
@@ -570,7 +573,7 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
     const u32 genv = v.env_offset + (u32)e;
     int action = ACT_RESIGN, bot_action = -1, R = 0, phase;
     u32 fl = 0;
-    bool d_out = false, agent_ply = false, owe_bot = false;
+    bool d_out = false, agent_ply = false, owe_bot = false, agent_draw = false;
     const int n0 = s.n_legal;
     const bool was_done = s.done, capped = s.move_count > v.moves_max;
     const u32 step_idx = (u32)s.step;
@@ -591,10 +594,15 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
             action = (int)input;
             valid = action_is_legal(pick_sr, s, action);  // action in possible_actions
         } else {
-            const u32 u = (MODE == MODE_INDEX) ? input : philox_draw(v.seed, genv, ep, step_idx, 0u);
-            if (n0 > 0) {
-                action = action_at<MULTI>(pick_sr, s, (int)gcb_umulhi(u, (u32)n0));
-                valid = true;
+            if (!SELFPLAY && GCB_ONE_PICK_SITE) {
+                // (bot kernels: the agent's draw also goes through the one pick site at the top of the phase loop)
+                if (n0 > 0) valid = true, agent_draw = true;
+            } else {
+                const u32 u = (MODE == MODE_INDEX) ? input : philox_draw(v.seed, genv, ep, step_idx, 0u);
+                if (n0 > 0) {
+                    action = action_at<MULTI>(pick_sr, s, (int)gcb_umulhi(u, (u32)n0));
+                    valid = true;
+                }
             }
         }
         if (!SELFPLAY && s.pending) valid = false;  // a bot ply is owed first: the agent's action is refused
@@ -625,11 +633,13 @@ GCB_HD void env_step_regs(const EnvView& v, const StepIO& io, int e, EnvRegs& s,
 #pragma unroll 1
 #endif
     while (phase != PH_END) {
-        if (!SELFPLAY && draw_purpose) {
-            const u32 u = philox_draw(v.seed, genv, ep, draw_step, draw_purpose);
-            cur = action_at<MULTI>(sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
-            if (draw_purpose == 1u) bot_action = cur;
-            draw_purpose = 0u;
+        if (!SELFPLAY && (draw_purpose || agent_draw)) {
+            // agent: purpose 0 at this step (or the caller's random word), from the slots the step found; bot: purpose 1 / 2
+            const u32 u = (agent_draw && MODE == MODE_INDEX) ? input : philox_draw(v.seed, genv, ep, agent_draw ? step_idx : draw_step, draw_purpose);
+            cur = action_at<MULTI>(agent_draw ? pick_sr : sr, s, (int)gcb_umulhi(u, (u32)s.n_legal));
+            if (agent_draw) action = cur;
+            else if (draw_purpose == 1u) bot_action = cur;
+            draw_purpose = 0u, agent_draw = false;
         }
         if (phase == PH_FINAL) {
             bool terminal;
