@@ -34,6 +34,8 @@ def lib():
         L.emul_update_state.argtypes = [C.c_int] + [vp] * 4
         L.emul_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.emul_philox.restype = C.c_uint32
+        L.emul_nth_target_check.argtypes = [C.c_uint64, C.c_int]
+        L.emul_nth_target_check.restype = C.c_long
         L.emul_env_create.argtypes = [C.c_int, C.c_uint32, C.c_uint64] + [C.c_int] * 7 + [vp]
         L.emul_env_create.restype = vp
         L.emul_env_destroy.argtypes = [vp]

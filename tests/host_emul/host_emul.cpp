@@ -95,6 +95,41 @@ void emul_update_state(int n, const int8_t* boards, const uint8_t* rights4, uint
     }
 }
 
+// nth_target (the ordered pick's "idx-th move of this piece") against the walk it abbreviates, emit_piece_moves: for every
+// piece class, colour and from-square, the full reach of the class and `rounds` random subsets of it, every idx.
+// Returns the number of (class, square, subset, idx) cases checked, or -(1 + first failing case) on a mismatch.
+long emul_nth_target_check(uint64_t seed, int rounds) {
+    struct Collect {
+        int to[64], n;
+        void push(int action) { to[n++] = action & 63; }
+    };
+    const int codes[6] = {PC_KING, PC_QUEEN, PC_ROOK, PC_BISHOP, PC_KNIGHT, PC_PAWN};
+    long cases = 0;
+    u64 x = seed | 1ULL;
+    for (int ci = 0; ci < 6; ci++)
+        for (int white = 0; white < 2; white++)
+            for (int sq = 0; sq < 64; sq++) {
+                const int code = codes[ci], cls = order_class(code, white);
+                u64 reach = 0;
+                for (int k = 0; k < 8; k++) reach |= g_geom_host.ord[cls][sq][k];
+                if (code == PC_ROOK) reach = g_geom_host.line[sq][0] | g_geom_host.line[sq][1];
+                if (code == PC_BISHOP) reach = g_geom_host.line[sq][2] | g_geom_host.line[sq][3];
+                for (int r = 0; r <= rounds; r++) {
+                    x = gcb_splitmix64(x);
+                    const u64 T = r == 0 ? reach : (reach & x & gcb_splitmix64(x ^ 0x5555ULL));
+                    Collect c;
+                    c.n = 0;
+                    emit_piece_moves(c, code, white, sq, T);
+                    if (c.n != gcb_popc(T)) return -(1 + cases);
+                    for (int idx = 0; idx < c.n; idx++, cases++) {
+                        if (nth_target<true>(code, white, sq, T, idx) != c.to[idx]) return -(1 + cases);
+                        if (nth_target<false>(code, white, sq, T, idx) != c.to[idx]) return -(1 + cases);
+                    }
+                }
+            }
+    return cases;
+}
+
 uint32_t emul_philox(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step, uint32_t purpose) {
     return philox_draw(seed, env, episode, step, purpose);
 }

@@ -248,3 +248,10 @@ def test_v1_castle_through_attack_vector():
         out, cnt, _ = emul.movegen(b[None], p, np.ones((1, 4), np.uint8), False, castles_only=True)
         return [int(a) for a in out[0, : cnt[0]]]
     ph.check_v1_castle_through_attack_vector(fn)
+
+
+def test_ordered_pick_equals_the_walk_over_the_directions():
+    """nth_target (search over the cumulative direction masks) == the idx-th move emit_piece_moves lists, for every piece
+    class, colour, from-square, the class's full reach and 24 random subsets of it, every index."""
+    n = emul.lib().emul_nth_target_check(20260101, 24)
+    assert n > 40000, n  # (a negative value is -(1 + index of the first mismatching case))
